@@ -1,0 +1,536 @@
+/*
+ * mp2_oracle.c -- CPU ORACLE (test infrastructure, NOT the product).  See mp2_oracle.h
+ * for provenance, pinning status and who may call this.  Every function cites the
+ * SURVEY.md Appendix-A clause (restating plonky2 0.2.2, which is not vendored in the
+ * reference tree) and the reference call site that constrains it.
+ */
+#include "mp2_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+
+#define GL_P 0xFFFFFFFF00000001ULL /* mp2-common/src/group_hashing/utils.rs:51 */
+#define GL_EPS 0xFFFFFFFFULL
+
+/* ------------------------------------------------------------------------- */
+/* A.1 field: p = 2^64 - 2^32 + 1                                             */
+/* ------------------------------------------------------------------------- */
+uint64_t orc_gl_canon(uint64_t a) { return a >= GL_P ? a - GL_P : a; }
+
+static inline uint64_t gl_add(uint64_t a, uint64_t b) { /* canonical in -> canonical out */
+  uint64_t s = a + b;
+  if (s < a || s >= GL_P) s -= GL_P;
+  return s;
+}
+static inline uint64_t gl_sub(uint64_t a, uint64_t b) {
+  uint64_t d = a - b;
+  if (a < b) d += GL_P;
+  return d;
+}
+/* reduce128 exactly as A.1: result in [0,2^64), then canonicalised */
+static inline uint64_t gl_reduce128(u128 x) {
+  uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+  uint64_t hh = hi >> 32, hl = hi & GL_EPS;
+  uint64_t t0 = lo - hh;
+  if (lo < hh) t0 -= GL_EPS;
+  uint64_t t1 = hl * GL_EPS;
+  uint64_t r = t0 + t1;
+  if (r < t0) r += GL_EPS;
+  return r >= GL_P ? r - GL_P : r;
+}
+static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128((u128)a * b); }
+
+uint64_t orc_gl_add(uint64_t a, uint64_t b) { return gl_add(orc_gl_canon(a), orc_gl_canon(b)); }
+uint64_t orc_gl_sub(uint64_t a, uint64_t b) { return gl_sub(orc_gl_canon(a), orc_gl_canon(b)); }
+uint64_t orc_gl_mul(uint64_t a, uint64_t b) { return gl_mul(a, b); }
+uint64_t orc_gl_pow(uint64_t a, uint64_t e) {
+  uint64_t r = 1, b = orc_gl_canon(a);
+  while (e) {
+    if (e & 1) r = gl_mul(r, b);
+    b = gl_mul(b, b);
+    e >>= 1;
+  }
+  return r;
+}
+uint64_t orc_gl_inv(uint64_t a) { return orc_gl_pow(a, GL_P - 2); }
+
+/* POWER_OF_TWO_GENERATOR = 7^((p-1)/2^32); primitive_root_of_unity(k) = that^(2^(32-k)) */
+uint64_t orc_gl_root_of_unity(uint32_t log_n) {
+  uint64_t w = orc_gl_pow(7, (GL_P - 1) >> 32);
+  for (uint32_t i = log_n; i < 32; i++) w = gl_mul(w, w);
+  return w;
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.6 Poseidon (width 12, x^7, 4+22+4) -- constants regenerated, naive rounds */
+/* ------------------------------------------------------------------------- */
+static inline uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+static inline uint32_t rotr32(uint32_t x, int r) { return r ? (x >> r) | (x << (32 - r)) : x; }
+
+/* rand_chacha ChaCha8Rng: 8 rounds, 64-bit block counter in words 12-13, stream 0 */
+static void chacha8_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+  uint32_t in[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+  for (int i = 0; i < 8; i++) in[4 + i] = key[i];
+  in[12] = (uint32_t)counter;
+  in[13] = (uint32_t)(counter >> 32);
+  in[14] = 0;
+  in[15] = 0;
+  uint32_t x[16];
+  memcpy(x, in, sizeof x);
+#define QR(a, b, c, d)                                                                             \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12);      \
+  x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+  for (int r = 0; r < 4; r++) {
+    QR(0, 4, 8, 12) QR(1, 5, 9, 13) QR(2, 6, 10, 14) QR(3, 7, 11, 15)
+    QR(0, 5, 10, 15) QR(1, 6, 11, 12) QR(2, 7, 8, 13) QR(3, 4, 9, 14)
+  }
+#undef QR
+  for (int i = 0; i < 16; i++) out[i] = x[i] + in[i];
+}
+
+static uint64_t POS_RC[360];
+static int pos_rc_ready = 0;
+
+/* RC[k] = ChaCha8Rng::seed_from_u64(0).gen_range(0..p), k = 0..359 */
+void orc_poseidon_round_constants(uint64_t out[360]) {
+  /* seed_from_u64(0): eight PCG32 outputs, little endian, form the 32-byte key */
+  uint32_t key[8];
+  uint64_t st = 0;
+  for (int i = 0; i < 8; i++) {
+    st = st * 6364136223846793005ULL + 11634580027462260723ULL;
+    uint32_t xs = (uint32_t)(((st >> 18) ^ st) >> 27);
+    key[i] = rotr32(xs, (int)(st >> 59));
+  }
+  uint32_t blk[16];
+  uint64_t ctr = 0;
+  int pos = 16;
+  for (int k = 0; k < 360;) {
+    if (pos == 16) {
+      chacha8_block(key, ctr++, blk);
+      pos = 0;
+    }
+    uint64_t v = (uint64_t)blk[pos] | ((uint64_t)blk[pos + 1] << 32); /* next_u64: lo then hi */
+    pos += 2;
+    u128 m = (u128)v * GL_P; /* UniformInt::sample_single, zone = p - 1 */
+    if ((uint64_t)m <= GL_P - 1) out[k++] = (uint64_t)(m >> 64);
+  }
+}
+
+static void pos_init(void) {
+  if (pos_rc_ready) return;
+#pragma omp critical(orc_pos_init)
+  {
+    if (!pos_rc_ready) {
+      orc_poseidon_round_constants(POS_RC);
+      __atomic_store_n(&pos_rc_ready, 1, __ATOMIC_RELEASE);
+    }
+  }
+}
+
+static const uint64_t POS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+static const uint64_t POS_DIAG[12] = {8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+static inline uint64_t sbox7(uint64_t x) {
+  uint64_t x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x, x2);
+  return gl_mul(x3, x4);
+}
+
+/* out[r] = sum_i state[(i+r)%12] * CIRC[i] + state[r] * DIAG[r]   (mds_row_shf) */
+static inline void pos_mds(uint64_t s[12]) {
+  uint64_t o[12];
+  for (int r = 0; r < 12; r++) {
+    u128 acc = (u128)s[r] * POS_DIAG[r];
+    for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * POS_CIRC[i];
+    o[r] = gl_reduce128(acc);
+  }
+  memcpy(s, o, sizeof o);
+}
+
+void orc_poseidon_permute(uint64_t s[12]) {
+  pos_init();
+  for (int i = 0; i < 12; i++) s[i] = orc_gl_canon(s[i]);
+  int rc = 0;
+  for (int round = 0; round < 30; round++) {
+    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POS_RC[rc++]);
+    if (round < 4 || round >= 26) {
+      for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+    } else {
+      s[0] = sbox7(s[0]);
+    }
+    pos_mds(s);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.7 Poseidon2 (Horizen-Labs Goldilocks t=12 instance; provenance unconfirmed) */
+/* ------------------------------------------------------------------------- */
+static uint64_t P2_RC[118];
+static int p2_rc_ready = 0;
+static const uint64_t P2_DIAG[12] = {
+    0xc3b6c08e23ba9300ULL, 0xd84b5de94a324fb6ULL, 0x0d0c371c5b35b84fULL, 0x7964f570e7188037ULL,
+    0x5daf18bbd996604bULL, 0x6743bc47b9595257ULL, 0x5528b9362c59bb70ULL, 0xac45e25b7127b68bULL,
+    0xa2077d7dfbb606b5ULL, 0xf3faac6faee378aeULL, 0x0c6388b51545e883ULL, 0xd27dbb6944917b60ULL};
+
+void orc_poseidon2_diag(uint64_t out[12]) { memcpy(out, P2_DIAG, sizeof P2_DIAG); }
+
+/* Poseidon Grain LFSR (80 bits) parameterised for field=1, sbox=0, n=64, t=12, R_F=8, R_P=22 */
+typedef struct {
+  uint8_t b[80];
+  int head;
+} grain_t;
+static int grain_step(grain_t *g) {
+  uint8_t *b = g->b;
+  int h = g->head;
+#define GB(i) b[(h + (i)) % 80]
+  int nb = GB(62) ^ GB(51) ^ GB(38) ^ GB(23) ^ GB(13) ^ GB(0);
+#undef GB
+  b[h] = (uint8_t)nb; /* overwrite oldest, advance head => new bit becomes position 79 */
+  g->head = (h + 1) % 80;
+  return nb;
+}
+static int grain_bit(grain_t *g) {
+  for (;;) {
+    int a = grain_step(g);
+    int c = grain_step(g);
+    if (a) return c;
+  }
+}
+void orc_poseidon2_round_constants(uint64_t out[118]) {
+  grain_t g;
+  g.head = 0;
+  int pos = 0;
+  const uint32_t fields[6][2] = {{1, 2}, {0, 4}, {64, 12}, {12, 12}, {8, 10}, {22, 10}};
+  for (int f = 0; f < 6; f++)
+    for (int i = (int)fields[f][1] - 1; i >= 0; i--) g.b[pos++] = (fields[f][0] >> i) & 1;
+  while (pos < 80) g.b[pos++] = 1;
+  for (int i = 0; i < 160; i++) grain_step(&g);
+  for (int k = 0; k < 118;) {
+    uint64_t v = 0;
+    for (int i = 0; i < 64; i++) v = (v << 1) | (uint64_t)grain_bit(&g);
+    if (v < GL_P) out[k++] = v;
+  }
+}
+static void p2_init(void) {
+  if (p2_rc_ready) return;
+#pragma omp critical(orc_p2_init)
+  {
+    if (!p2_rc_ready) {
+      orc_poseidon2_round_constants(P2_RC);
+      __atomic_store_n(&p2_rc_ready, 1, __ATOMIC_RELEASE);
+    }
+  }
+}
+
+/* M_E: M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] on each 4-lane chunk, then add column sums */
+static void p2_external(uint64_t s[12]) {
+  for (int c = 0; c < 12; c += 4) {
+    uint64_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
+    uint64_t t0 = gl_add(x0, x1), t1 = gl_add(x2, x3);
+    uint64_t t2 = gl_add(gl_add(x1, x1), t1), t3 = gl_add(gl_add(x3, x3), t0);
+    uint64_t t1_4 = gl_add(t1, t1); t1_4 = gl_add(t1_4, t1_4);
+    uint64_t t0_4 = gl_add(t0, t0); t0_4 = gl_add(t0_4, t0_4);
+    uint64_t t4 = gl_add(t1_4, t3), t5 = gl_add(t0_4, t2);
+    s[c] = gl_add(t3, t5);
+    s[c + 1] = t5;
+    s[c + 2] = gl_add(t2, t4);
+    s[c + 3] = t4;
+  }
+  uint64_t col[4];
+  for (int l = 0; l < 4; l++) col[l] = gl_add(gl_add(s[l], s[4 + l]), s[8 + l]);
+  for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], col[i % 4]);
+}
+/* M_I: out[i] = state[i] * mu_i + sum(state) */
+static void p2_internal(uint64_t s[12]) {
+  uint64_t sum = 0;
+  for (int i = 0; i < 12; i++) sum = gl_add(sum, s[i]);
+  for (int i = 0; i < 12; i++) s[i] = gl_add(gl_mul(s[i], P2_DIAG[i]), sum);
+}
+void orc_poseidon2_permute(uint64_t s[12]) {
+  p2_init();
+  for (int i = 0; i < 12; i++) s[i] = orc_gl_canon(s[i]);
+  const uint64_t *rc = P2_RC;
+  p2_external(s);
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], *rc++));
+    p2_external(s);
+  }
+  for (int r = 0; r < 22; r++) {
+    s[0] = sbox7(gl_add(s[0], *rc++));
+    p2_internal(s);
+  }
+  for (int r = 0; r < 4; r++) {
+    for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], *rc++));
+    p2_external(s);
+  }
+}
+
+void orc_permute(uint32_t kind, uint64_t s[12]) {
+  if (kind == ORC_HASH_POSEIDON2) orc_poseidon2_permute(s);
+  else orc_poseidon_permute(s);
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.5 sponge wrapper: rate 8, capacity 4, OVERWRITE absorb, squeeze state[0..4] */
+/* (mirrors mp2-common/src/poseidon.rs:151-171 and mp2-common/src/hash.rs:24-45) */
+/* ------------------------------------------------------------------------- */
+void orc_hash_no_pad(uint32_t kind, const uint64_t *in, size_t len, uint64_t out[4]) {
+  uint64_t st[12] = {0};
+  for (size_t off = 0; off < len; off += 8) {
+    size_t m = len - off < 8 ? len - off : 8;
+    for (size_t i = 0; i < m; i++) st[i] = orc_gl_canon(in[off + i]);
+    orc_permute(kind, st);
+  }
+  for (int i = 0; i < 4; i++) out[i] = st[i];
+}
+/* hash_pad: append 1, zeros until (len+1) % 8 == 0, then 1 (circuit_set.rs:149-151 uses hash_pad(&[])) */
+void orc_hash_pad(uint32_t kind, const uint64_t *in, size_t len, uint64_t out[4]) {
+  size_t padded = len + 1;
+  while ((padded + 1) % 8 != 0) padded++;
+  padded++;
+  uint64_t *buf = (uint64_t *)calloc(padded, sizeof(uint64_t));
+  if (len) memcpy(buf, in, len * sizeof(uint64_t));
+  buf[len] = 1;
+  buf[padded - 1] = 1;
+  orc_hash_no_pad(kind, buf, padded, out);
+  free(buf);
+}
+void orc_hash_or_noop(uint32_t kind, const uint64_t *in, size_t len, uint64_t out[4]) {
+  if (len <= 4) {
+    for (size_t i = 0; i < 4; i++) out[i] = i < len ? orc_gl_canon(in[i]) : 0;
+  } else {
+    orc_hash_no_pad(kind, in, len, out);
+  }
+}
+void orc_two_to_one(uint32_t kind, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]) {
+  uint64_t st[12] = {0};
+  for (int i = 0; i < 4; i++) {
+    st[i] = orc_gl_canon(a[i]);
+    st[4 + i] = orc_gl_canon(b[i]);
+  }
+  orc_permute(kind, st);
+  for (int i = 0; i < 4; i++) out[i] = st[i];
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.2 transforms                                                             */
+/* ------------------------------------------------------------------------- */
+static inline size_t bitrev(size_t x, uint32_t bits) {
+  size_t r = 0;
+  for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+
+void orc_fft(uint64_t *v, uint32_t log_n) {
+  size_t n = (size_t)1 << log_n;
+  for (size_t i = 0; i < n; i++) {
+    size_t j = bitrev(i, log_n);
+    if (i < j) {
+      uint64_t t = v[i];
+      v[i] = v[j];
+      v[j] = t;
+    }
+  }
+  for (size_t i = 0; i < n; i++) v[i] = orc_gl_canon(v[i]);
+  uint64_t *tw = (uint64_t *)malloc(sizeof(uint64_t) * (n / 2 + 1));
+  for (uint32_t s = 1; s <= log_n; s++) {
+    size_t half = (size_t)1 << (s - 1);
+    uint64_t w = orc_gl_root_of_unity(s);
+    tw[0] = 1;
+    for (size_t k = 1; k < half; k++) tw[k] = gl_mul(tw[k - 1], w);
+    for (size_t base = 0; base < n; base += 2 * half)
+      for (size_t k = 0; k < half; k++) {
+        uint64_t a = v[base + k], b = gl_mul(v[base + k + half], tw[k]);
+        v[base + k] = gl_add(a, b);
+        v[base + k + half] = gl_sub(a, b);
+      }
+  }
+  free(tw);
+}
+
+/* ifft = fft, then coeffs[i] = fft[(n-i)%n] * n^-1 */
+void orc_ifft(uint64_t *v, uint32_t log_n) {
+  size_t n = (size_t)1 << log_n;
+  orc_fft(v, log_n);
+  uint64_t ninv = orc_gl_inv((uint64_t)n);
+  for (size_t i = 1; i < n - i; i++) {
+    uint64_t t = v[i];
+    v[i] = v[n - i];
+    v[n - i] = t;
+  }
+  for (size_t i = 0; i < n; i++) v[i] = gl_mul(v[i], ninv);
+}
+
+/* lde(r) then coset_fft(shift): out[i] = P(shift * w_N^i), natural order */
+void orc_coset_lde(const uint64_t *coeffs, uint32_t log_n, uint32_t rate_bits, uint64_t shift,
+                   uint64_t *out) {
+  size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  uint64_t pw = 1;
+  for (size_t j = 0; j < n; j++) {
+    out[j] = gl_mul(coeffs[j], pw);
+    pw = gl_mul(pw, shift);
+  }
+  memset(out + n, 0, (N - n) * sizeof(uint64_t));
+  orc_fft(out, log_n + rate_bits);
+}
+
+void orc_eval_naive(const uint64_t *coeffs, size_t n, uint64_t shift, uint64_t w, size_t n_out,
+                    uint64_t *out) {
+  uint64_t x = orc_gl_canon(shift);
+  for (size_t i = 0; i < n_out; i++) {
+    uint64_t acc = 0;
+    for (size_t j = n; j-- > 0;) acc = gl_add(gl_mul(acc, x), orc_gl_canon(coeffs[j]));
+    out[i] = acc;
+    x = gl_mul(x, w);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* A.4 MerkleTree::new / prove -- plonky2's interleaved digest layout          */
+/* (called directly at circuit_set.rs:189; proof consumed at circuit_set.rs:216) */
+/* ------------------------------------------------------------------------- */
+static void fill_subtree(uint64_t *buf, size_t buf_len /* digests */, const uint64_t *leaves,
+                         size_t nleaves, size_t leaf_len, uint32_t kind, uint64_t out[4],
+                         int depth) {
+  if (buf_len == 0) {
+    orc_hash_or_noop(kind, leaves, leaf_len, out);
+    return;
+  }
+  size_t half = buf_len / 2;
+  uint64_t *lbuf = buf, *rbuf = buf + 4 * half;
+  uint64_t *lmem = lbuf + 4 * (half - 1); /* last digest of the left half */
+  uint64_t *rmem = rbuf;                  /* first digest of the right half */
+  uint64_t ld[4], rd[4];
+  if (depth > 0 && nleaves >= 64) {
+#pragma omp task shared(ld) firstprivate(lbuf, half, leaves, nleaves, leaf_len, kind, depth)
+    fill_subtree(lbuf, half - 1, leaves, nleaves / 2, leaf_len, kind, ld, depth - 1);
+#pragma omp task shared(rd) firstprivate(rbuf, half, leaves, nleaves, leaf_len, kind, depth)
+    fill_subtree(rbuf + 4, half - 1, leaves + (nleaves / 2) * leaf_len, nleaves / 2, leaf_len,
+                 kind, rd, depth - 1);
+#pragma omp taskwait
+  } else {
+    fill_subtree(lbuf, half - 1, leaves, nleaves / 2, leaf_len, kind, ld, 0);
+    fill_subtree(rbuf + 4, half - 1, leaves + (nleaves / 2) * leaf_len, nleaves / 2, leaf_len,
+                 kind, rd, 0);
+  }
+  memcpy(lmem, ld, 32);
+  memcpy(rmem, rd, 32);
+  orc_two_to_one(kind, ld, rd, out);
+}
+
+static int log2_exact(size_t n) {
+  if (n == 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}
+
+int orc_merkle_new(const uint64_t *leaves, size_t nleaves, size_t leaf_len, uint32_t cap_height,
+                   uint32_t kind, uint64_t *digests_out, uint64_t *cap_out, int nthreads) {
+  int lg = log2_exact(nleaves);
+  if (lg < 0 || (int)cap_height > lg) return -1;
+  pos_init();
+  p2_init();
+  size_t ncap = (size_t)1 << cap_height;
+  size_t sub_leaves = nleaves >> cap_height;
+  size_t sub_digests = 2 * (sub_leaves - 1); /* digests.len() / ncap */
+  if (nthreads < 1) nthreads = 1;
+  int depth = 0;
+  while (((size_t)1 << depth) * ncap < (size_t)nthreads * 4 && depth < 16) depth++;
+#pragma omp parallel num_threads(nthreads)
+#pragma omp single
+  {
+    for (size_t s = 0; s < ncap; s++) {
+#pragma omp task firstprivate(s)
+      fill_subtree(digests_out + 4 * s * sub_digests, sub_digests,
+                   leaves + s * sub_leaves * leaf_len, sub_leaves, leaf_len, kind, cap_out + 4 * s,
+                   depth);
+    }
+  }
+  return 0;
+}
+
+/* closed-form sibling indices (A.4): layer i pair k at digests 2q, 2q+1, q = (k<<(i+1)) + (1<<i) - 1 */
+int orc_merkle_prove(const uint64_t *digests, size_t nleaves, uint32_t cap_height,
+                     size_t leaf_index, uint64_t *siblings_out) {
+  int lg = log2_exact(nleaves);
+  if (lg < 0 || (int)cap_height > lg || leaf_index >= nleaves) return -1;
+  uint32_t h = (uint32_t)lg - cap_height;
+  size_t sub_digests = 2 * (((size_t)1 << h) - 1);
+  const uint64_t *sub = digests + 4 * (leaf_index >> h) * sub_digests;
+  size_t pair_index = leaf_index & (((size_t)1 << h) - 1);
+  for (uint32_t i = 0; i < h; i++) {
+    size_t parity = pair_index & 1;
+    pair_index >>= 1;
+    size_t q = (pair_index << (i + 1)) + ((size_t)1 << i) - 1;
+    memcpy(siblings_out + 4 * i, sub + 4 * (2 * q + (1 - parity)), 32);
+  }
+  return (int)h;
+}
+
+int orc_merkle_verify(const uint64_t *leaf, size_t leaf_len, size_t leaf_index,
+                      const uint64_t *siblings, size_t nsib, uint32_t kind, uint64_t root[4]) {
+  uint64_t cur[4], nxt[4];
+  orc_hash_or_noop(kind, leaf, leaf_len, cur);
+  size_t idx = leaf_index;
+  for (size_t i = 0; i < nsib; i++) {
+    if (idx & 1) orc_two_to_one(kind, siblings + 4 * i, cur, nxt);
+    else orc_two_to_one(kind, cur, siblings + 4 * i, nxt);
+    memcpy(cur, nxt, 32);
+    idx >>= 1;
+  }
+  memcpy(root, cur, 32);
+  return (int)idx; /* cap index */
+}
+
+/* ------------------------------------------------------------------------- */
+/* a1/a2 PolynomialBatch::from_values / from_coeffs                            */
+/* ------------------------------------------------------------------------- */
+int orc_commit(const uint64_t *const *cols, size_t ncols, uint32_t log_n, uint32_t rate_bits,
+               uint32_t cap_height, uint32_t kind, int from_coeffs, uint64_t *coeffs_out,
+               uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out, int nthreads) {
+  size_t n = (size_t)1 << log_n, N = n << rate_bits;
+  uint32_t log_N = log_n + rate_bits;
+  if (cap_height > log_N || ncols == 0) return -1;
+  if (nthreads < 1) nthreads = 1;
+  pos_init();
+  p2_init();
+  uint64_t *lde = (uint64_t *)malloc(sizeof(uint64_t) * N * ncols); /* column-major */
+  uint64_t *leaves = leaves_out ? leaves_out : (uint64_t *)malloc(sizeof(uint64_t) * N * ncols);
+  if (!lde || !leaves) return -1;
+  /* "IFFT" + "FFT + blinding" scopes: one task per column, like rayon over polynomials */
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)
+  for (size_t c = 0; c < ncols; c++) {
+    uint64_t *tmp = (uint64_t *)malloc(sizeof(uint64_t) * n);
+    memcpy(tmp, cols[c], sizeof(uint64_t) * n);
+    if (!from_coeffs) orc_ifft(tmp, log_n);
+    else
+      for (size_t i = 0; i < n; i++) tmp[i] = orc_gl_canon(tmp[i]);
+    if (coeffs_out) memcpy(coeffs_out + c * n, tmp, sizeof(uint64_t) * n);
+    orc_coset_lde(tmp, log_n, rate_bits, 7 /* coset_shift() = MULTIPLICATIVE_GROUP_GENERATOR */,
+                  lde + c * N);
+    free(tmp);
+  }
+  /* "transpose LDEs" + reverse_index_bits_in_place: leaves[i] = row bitrev(i)  (A.3) */
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+  for (size_t i = 0; i < N; i++) {
+    size_t src = bitrev(i, log_N);
+    for (size_t c = 0; c < ncols; c++) leaves[i * ncols + c] = lde[c * N + src];
+  }
+  free(lde);
+  int rc = orc_merkle_new(leaves, N, ncols, cap_height, kind, digests_out, cap_out, nthreads);
+  if (!leaves_out) free(leaves);
+  return rc;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}

@@ -1,0 +1,101 @@
+/*
+ * mp2_oracle.h -- CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * Plain-C restatement of the plonky2 0.2.2 polynomial-batch commitment path that
+ * every proof of Lagrange-Labs/mapreduce-plonky2 goes through.  The algorithm
+ * itself lives in third-party crates that are NOT vendored under /root/reference:
+ *   plonky2 / plonky2_field / plonky2_util 0.2.x  and  poseidon2_plonky2 0.1.0,
+ *   git+https://github.com/Lagrange-Labs/plonky2?branch=upstream
+ *   #22c42f64367e8f087e565bdb664525910a62fc76   (Cargo.toml:63,114-117; Cargo.lock:4716-4719)
+ * so this file restates the published algorithm and is
+ * anchored on the reference's call sites:
+ *   recursion-framework/src/universal_verifier_gadget/circuit_set.rs:173-237 (MerkleTree::new / prove)
+ *   recursion-framework/src/universal_verifier_gadget/circuit_set.rs:136-158 (circuit digest formula)
+ *   mp2-common/src/poseidon.rs:136-172, mp2-common/src/hash.rs:16-46       (sponge semantics)
+ *   mp2-common/src/lib.rs:36-47                                            (F, D, C, standard config)
+ *   mp2-common/src/group_hashing/utils.rs:11,51                            (field order, 2/3 mod p)
+ *
+ * PARITY STATUS: "parity unpinned" at the commitment boundary -- the reference's
+ * own tests hold no golden vectors for NTT/LDE/Merkle.  What IS
+ * pinned: the 360 Poseidon round constants (regenerated from ChaCha8Rng seed 0 and
+ * checked against the published table anchors), plonky2's three Poseidon
+ * permutation test vectors, the Horizen-Labs Poseidon2 t=12 KAT, and the
+ * Goldilocks generators (tests/test_oracle_pins.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may call into this library.
+ */
+#ifndef MP2_ORACLE_H
+#define MP2_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_HASH_POSEIDON 0u
+#define ORC_HASH_POSEIDON2 1u
+
+/* ---- field (A.1) ---- */
+uint64_t orc_gl_add(uint64_t a, uint64_t b);
+uint64_t orc_gl_sub(uint64_t a, uint64_t b);
+uint64_t orc_gl_mul(uint64_t a, uint64_t b);
+uint64_t orc_gl_pow(uint64_t a, uint64_t e);
+uint64_t orc_gl_inv(uint64_t a);
+uint64_t orc_gl_canon(uint64_t a);
+uint64_t orc_gl_root_of_unity(uint32_t log_n); /* primitive_root_of_unity(log_n) */
+
+/* ---- permutations (A.6, A.7) ---- */
+void orc_poseidon_round_constants(uint64_t out[360]); /* regenerated, ChaCha8Rng(0) */
+void orc_poseidon_permute(uint64_t state[12]);        /* naive schedule */
+void orc_poseidon2_round_constants(uint64_t out[118]); /* Grain LFSR */
+void orc_poseidon2_diag(uint64_t out[12]);
+void orc_poseidon2_permute(uint64_t state[12]);
+void orc_permute(uint32_t hash_kind, uint64_t state[12]);
+
+/* ---- sponge wrapper (A.5) ---- */
+void orc_hash_no_pad(uint32_t hash_kind, const uint64_t *in, size_t len, uint64_t out[4]);
+void orc_hash_pad(uint32_t hash_kind, const uint64_t *in, size_t len, uint64_t out[4]);
+void orc_hash_or_noop(uint32_t hash_kind, const uint64_t *in, size_t len, uint64_t out[4]);
+void orc_two_to_one(uint32_t hash_kind, const uint64_t a[4], const uint64_t b[4], uint64_t out[4]);
+
+/* ---- transforms (A.2), in place on one column ---- */
+void orc_fft(uint64_t *v, uint32_t log_n);  /* v[i] <- sum_j v[j] w^(ij), natural order */
+void orc_ifft(uint64_t *v, uint32_t log_n); /* inverse, natural order */
+/* coeffs (n = 2^log_n) -> out (N = n << rate_bits): out[i] = P(shift * w_N^i) */
+void orc_coset_lde(const uint64_t *coeffs, uint32_t log_n, uint32_t rate_bits, uint64_t shift,
+                   uint64_t *out);
+/* O(n^2) evaluation by definition, for cross-checks on tiny sizes */
+void orc_eval_naive(const uint64_t *coeffs, size_t n, uint64_t shift, uint64_t w, size_t n_out,
+                    uint64_t *out);
+
+/* ---- Merkle tree (A.4) ---- */
+/* leaves: row-major nleaves x leaf_len.  digests_out: 2*(nleaves - 2^cap_height) x 4.
+ * cap_out: 2^cap_height x 4.  Returns 0 on success, -1 on bad arguments
+ * (nleaves not a power of two, cap_height > log2(nleaves)). */
+int orc_merkle_new(const uint64_t *leaves, size_t nleaves, size_t leaf_len, uint32_t cap_height,
+                   uint32_t hash_kind, uint64_t *digests_out, uint64_t *cap_out, int nthreads);
+/* siblings_out: (log2(nleaves) - cap_height) x 4; returns number of siblings or -1 */
+int orc_merkle_prove(const uint64_t *digests, size_t nleaves, uint32_t cap_height,
+                     size_t leaf_index, uint64_t *siblings_out);
+/* recompute the cap entry index and value from a leaf and its proof */
+int orc_merkle_verify(const uint64_t *leaf, size_t leaf_len, size_t leaf_index,
+                      const uint64_t *siblings, size_t nsiblings, uint32_t hash_kind,
+                      uint64_t root_out[4]);
+
+/* ---- PolynomialBatch::from_values / from_coeffs (a1, a2) ----
+ * cols: ncols pointers to n = 2^log_n u64 each (values or coeffs).
+ * coeffs_out: ncols x n (column-major, natural order) or NULL.
+ * leaves_out: (n << rate_bits) x ncols row-major, bit-reversed row order, or NULL.
+ * digests_out / cap_out as orc_merkle_new.  Returns 0 / -1. */
+int orc_commit(const uint64_t *const *cols, size_t ncols, uint32_t log_n, uint32_t rate_bits,
+               uint32_t cap_height, uint32_t hash_kind, int from_coeffs, uint64_t *coeffs_out,
+               uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out, int nthreads);
+
+int orc_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

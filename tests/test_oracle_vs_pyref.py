@@ -1,0 +1,137 @@
+"""C oracle vs. the independent pure-Python restatement and the committed golden fixtures."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import pyref as R
+from util import GOLDEN_DIR, P, field_elems, hexlist, unhex
+
+COMMITS = json.load(open(os.path.join(GOLDEN_DIR, "commit_small.json")))["cases"]
+MERKLE = json.load(open(os.path.join(GOLDEN_DIR, "merkle_small.json")))
+CAPS = json.load(open(os.path.join(GOLDEN_DIR, "config1_caps.json")))["cases"]
+
+
+def u2(rows):
+    return np.array([[int(x, 16) for x in r] for r in rows], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("case", COMMITS, ids=lambda c: "k%d_%dx2^%d_r%d_cap%d%s" % (
+    c["hash_kind"], c["ncols"], c["log_n"], c["rate_bits"], c["cap_height"], "_coeffs" if c["from_coeffs"] else ""))
+def test_commit_matches_golden(oracle, case):
+    out = oracle.commit(u2(case["cols"]), case["rate_bits"], case["cap_height"], case["hash_kind"],
+                        case["from_coeffs"])
+    assert np.array_equal(out["coeffs"], u2(case["coeffs"]))
+    assert np.array_equal(out["leaves"], u2(case["leaves"]))
+    if case["digests"]:
+        assert np.array_equal(out["digests"], u2(case["digests"]))
+    else:
+        assert out["digests"].size == 0
+    assert np.array_equal(out["cap"], u2(case["cap"]))
+
+
+@pytest.mark.parametrize("idx", range(len(MERKLE["cases"])))
+def test_merkle_matches_golden(oracle, idx):
+    case = MERKLE["cases"][idx]
+    kind, nl, cap = case["hash_kind"], case["nleaves"], case["cap_height"]
+    rows = [[int(x, 16) for x in r] for r in case["leaves"]]
+    if isinstance(case["leaf_len"], int):
+        digests, capv = oracle.merkle_new(np.array(rows, dtype=np.uint64), cap, kind)
+    else:
+        # ragged circuit-set leaves (4-element digests + [0] padding): hash_or_noop zero-pads both to
+        # the same 4-element no-op digest, so padding the short leaves with zeros is equivalent
+        rows4 = [r + [0] * (4 - len(r)) for r in rows]
+        digests, capv = oracle.merkle_new(np.array(rows4, dtype=np.uint64), cap, kind)
+    if case["digests"]:
+        assert np.array_equal(digests, u2(case["digests"]))
+    assert np.array_equal(capv, u2(case["cap"]))
+    for i, sib in case["proofs"].items():
+        got = oracle.merkle_prove(digests, nl, cap, int(i))
+        want = u2(sib) if sib else np.zeros((0, 4), dtype=np.uint64)
+        assert np.array_equal(got, want)
+        leaf = rows[int(i)]
+        cap_idx, root = oracle.merkle_verify(np.array(leaf, dtype=np.uint64), int(i), got, kind)
+        assert np.array_equal(root, capv[cap_idx])
+
+
+def test_hash_pad_and_empty(oracle):
+    for k in (0, 1):
+        assert hexlist(oracle.hash_pad([], k)) == MERKLE["misc"]["hash_pad_empty"][str(k)]
+    assert hexlist(oracle.hash_no_pad([], 0)) == MERKLE["misc"]["hash_no_pad_empty"] == ["0" * 16] * 4
+
+
+def test_sponge_overwrite_semantics(oracle):
+    """A short last chunk overwrites only state[0..len) (mp2-common/src/poseidon.rs:151-171)."""
+    rng = random.Random(3)
+    for k in (0, 1):
+        for ln in (1, 4, 5, 7, 8, 9, 15, 16, 17, 135):
+            x = [rng.randrange(P) for _ in range(ln)]
+            assert [int(v) for v in oracle.hash_no_pad(x, k)] == R.hash_no_pad(x, k)
+            assert [int(v) for v in oracle.hash_or_noop(x, k)] == R.hash_or_noop(x, k)
+        a = [rng.randrange(P) for _ in range(4)]
+        b = [rng.randrange(P) for _ in range(4)]
+        assert [int(v) for v in oracle.two_to_one(a, b, k)] == R.two_to_one(a, b, k)
+        assert np.array_equal(oracle.two_to_one(a, b, k), oracle.hash_no_pad(a + b, k))
+
+
+@pytest.mark.parametrize("log_n", [0, 1, 2, 3, 5, 7])
+def test_transforms_by_definition(oracle, log_n):
+    n = 1 << log_n
+    v = field_elems(100 + log_n, (n,))
+    coeffs = oracle.ifft(v)
+    assert [int(x) for x in coeffs] == R.ifft([int(x) for x in v])
+    assert np.array_equal(oracle.fft(coeffs), v)
+    for r in (0, 1, 3):
+        lde = oracle.coset_lde(coeffs, r)
+        w = oracle.root_of_unity(log_n + r)
+        assert np.array_equal(lde, oracle.eval_naive(coeffs, 7, w, n << r))
+        if log_n <= 5:
+            assert [int(x) for x in lde] == R.coset_lde([int(x) for x in coeffs], r)
+    # shift-1 LDE restricted to the subgroup (every 2^r-th point) gives the values back
+    lde1 = oracle.coset_lde(coeffs, 2, shift=1)
+    assert np.array_equal(lde1[::4], v)
+
+
+def test_merkle_new_rejects_like_plonky2(oracle):
+    leaves = field_elems(1, (8, 5))
+    with pytest.raises(ValueError):
+        oracle.merkle_new(leaves, 4)           # cap_height > log2(len)
+    with pytest.raises(ValueError):
+        oracle.merkle_new(leaves[:6], 0)       # not a power of two (cases (3,0),(6,0) of the serde rstest)
+    d, cap = oracle.merkle_new(leaves, 3)      # tree is all cap
+    assert d.size == 0 and cap.shape == (8, 4)
+    assert np.array_equal(cap[5], oracle.hash_or_noop(leaves[5]))
+
+
+def test_closed_form_prove_vs_explicit_tree(oracle):
+    rng = random.Random(11)
+    for log_n in range(0, 7):
+        for cap in range(0, log_n + 1):
+            n = 1 << log_n
+            leaves = [[rng.randrange(P) for _ in range(6)] for _ in range(n)]
+            _, capv, trees = R.merkle_new(leaves, cap, 0)
+            digests, cap_c = oracle.merkle_new(np.array(leaves, dtype=np.uint64), cap, 0)
+            assert cap_c.tolist() == capv
+            for i in sorted({0, n // 2, n - 1, rng.randrange(n)}):
+                want = R.merkle_prove_from_tree(trees, n, cap, i)
+                got = oracle.merkle_prove(digests, n, cap, i)
+                assert got.tolist() == want
+
+
+def test_thread_count_does_not_change_results(oracle):
+    cols = field_elems(5, (7, 64))
+    a = oracle.commit(cols, 3, 2, 0, nthreads=1)
+    b = oracle.commit(cols, 3, 2, 0, nthreads=5)
+    for k in a:
+        assert np.array_equal(a[k], b[k])
+
+
+@pytest.mark.parametrize("case", [c for c in CAPS if c["ncols"] <= 20], ids=lambda c: "%s_k%d" % (c["name"], c["hash_kind"]))
+def test_config1_sibling_caps_regression(oracle, case):
+    cols = field_elems(case["seed"], (case["ncols"], 1 << case["log_n"]))
+    res = oracle.commit(cols, case["rate_bits"], case["cap_height"], case["hash_kind"], case["from_coeffs"],
+                        want_leaves=False)
+    assert hexlist(res["cap"]) == case["cap"]
+    assert hexlist(np.bitwise_xor.reduce(res["digests"], axis=0)) == case["digest_xor"]
