@@ -1,0 +1,163 @@
+/*
+ * mp2gpu.h -- C ABI of the B200 (sm_100a) polynomial-batch commitment library.
+ *
+ * This is the drop-in boundary for the ONE data-parallel hot path of
+ * Lagrange-Labs/mapreduce-plonky2: plonky2's PolynomialBatch::from_values / from_coeffs and
+ * MerkleTree::new.  The reference reaches that path only through the plonky2
+ * crate it patches in at Cargo.toml:114-117; a fork of that crate forwards its fri/oracle.rs and
+ * hash/merkle_tree.rs bodies to these symbols (binding shown in INTEGRATION.md).
+ *
+ * Conventions (modelled on the reference's only extern "C" interface,
+ * gnark-utils/src/lib.rs:17-52 and gnark-utils/src/utils.rs:9-20):
+ *   - every entry point returns NULL on success, else a heap-allocated, NUL-terminated error string
+ *     that the caller releases with mp2gpu_free_string();  nothing ever unwinds across the boundary;
+ *   - the caller owns all host buffers; the library never keeps a host pointer past the call;
+ *   - inputs may hold non-canonical field elements (>= p = 2^64 - 2^32 + 1); every output is
+ *     canonical (< p), so ==, serde and to_bytes agree with the CPU path;
+ *   - entry points are re-entrant: each calling thread gets its own CUDA stream, the device is the
+ *     one last chosen by that thread with mp2gpu_init() (default 0);
+ *   - there is NO CPU fallback: without a usable CUDA device every call returns an error string.
+ *
+ * Layouts:
+ *   coeffs   ncols x n            column-major, natural order
+ *   leaves   N x ncols            row-major, N = n << rate_bits, row i = LDE row bitrev(i),
+ *                                 i.e. leaves[i][c] = P_c(7 * w_N^bitrev(i))
+ *   digests  2*(N - 2^cap) x 4    plonky2's interleaved per-subtree layout
+ *   cap      2^cap_height x 4
+ */
+#ifndef MP2GPU_H
+#define MP2GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP2GPU_HASH_POSEIDON 0u  /* PoseidonGoldilocksConfig  (feature original_poseidon, and WrapC) */
+#define MP2GPU_HASH_POSEIDON2 1u /* Poseidon2GoldilocksConfig (default C, mp2-common/src/lib.rs:37-40) */
+
+typedef struct mp2gpu_batch mp2gpu_batch; /* device-resident PolynomialBatch */
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* Binds the calling thread to `device`, uploads the constant tables on first use. */
+const char *mp2gpu_init(int device);
+const char *mp2gpu_device_count(int *count_out);
+/* Releases an error string (the FreeString of gnark-utils/src/lib.rs:51). */
+void mp2gpu_free_string(const char *s);
+/* "major.minor.patch (sm_100a)" -- static storage, do not free. */
+const char *mp2gpu_version(void);
+/* Page-locked host buffers (optional; any host pointer is accepted, pinned ones copy faster). */
+const char *mp2gpu_host_alloc(void **ptr_out, size_t bytes);
+const char *mp2gpu_host_free(void *ptr);
+
+/* ---- PolynomialBatch::from_values / from_coeffs (plonky2 fri/oracle.rs; reached from
+ *      recursion-framework/src/circuit_builder.rs:177,308 and
+ *      recursion-framework/src/universal_verifier_gadget/wrap_circuit.rs:98,143) -------------------
+ * cols[c]       n = 2^n_log field elements of column c (values resp. coefficients), host memory.
+ * coeffs_out[c] n elements (may be NULL as a whole: coefficients are then not returned).
+ * leaves_out    N*ncols elements or NULL (keep leaves on the device only).
+ * digests_out   2*(N-2^cap_height)*4 elements or NULL.
+ * cap_out       2^cap_height*4 elements (required).
+ * handle_out    if non-NULL receives a device-resident handle (release with mp2gpu_batch_free).
+ * blinding (salt columns) is not supported: the reference never enables it
+ * (zero_knowledge = false, mp2-common/src/lib.rs:45-47). */
+const char *mp2gpu_commit_from_values(const uint64_t *const *cols, size_t ncols, uint32_t n_log,
+                                      uint32_t rate_bits, uint32_t cap_height, uint32_t hash_kind,
+                                      uint64_t *const *coeffs_out, uint64_t *leaves_out,
+                                      uint64_t *digests_out, uint64_t *cap_out,
+                                      mp2gpu_batch **handle_out);
+const char *mp2gpu_commit_from_coeffs(const uint64_t *const *cols, size_t ncols, uint32_t n_log,
+                                      uint32_t rate_bits, uint32_t cap_height, uint32_t hash_kind,
+                                      uint64_t *const *coeffs_out, uint64_t *leaves_out,
+                                      uint64_t *digests_out, uint64_t *cap_out,
+                                      mp2gpu_batch **handle_out);
+
+/* ---- MerkleTree::new (plonky2 hash/merkle_tree.rs; called directly at
+ *      recursion-framework/src/universal_verifier_gadget/circuit_set.rs:189) -----------------------
+ * leaves: nleaves x leaf_len row-major, host memory.  Errors (where plonky2 panics): nleaves not a
+ * power of two, cap_height > log2(nleaves).  leaf_len <= 4 takes hash_or_noop's no-op branch. */
+const char *mp2gpu_merkle_new(const uint64_t *leaves, size_t nleaves, size_t leaf_len,
+                              uint32_t cap_height, uint32_t hash_kind, uint64_t *digests_out,
+                              uint64_t *cap_out);
+/* Vec<Vec<F>> with per-leaf lengths (the circuit-set tree pads with vec![F::ZERO],
+ * circuit_set.rs:184-185).  leaves[i] points to leaf_lens[i] elements. */
+const char *mp2gpu_merkle_new_ragged(const uint64_t *const *leaves, const size_t *leaf_lens,
+                                     size_t nleaves, uint32_t cap_height, uint32_t hash_kind,
+                                     uint64_t *digests_out, uint64_t *cap_out);
+/* MerkleTree::prove (circuit_set.rs:216): siblings bottom-up from a host digests array.
+ * siblings_out: (log2(nleaves) - cap_height) x 4.  Pure index arithmetic (no GPU work). */
+const char *mp2gpu_merkle_prove(const uint64_t *digests, size_t nleaves, uint32_t cap_height,
+                                size_t leaf_index, uint64_t *siblings_out, size_t *nsiblings_out);
+
+/* ---- Hasher::{hash_no_pad, hash_or_noop, two_to_one} in batches (plonky2 hash/hashing.rs; native
+ *      uses at mp2-common/src/poseidon.rs:49-51, mp2-common/src/utils.rs:294-315) -------------------
+ * inputs: count x input_len row-major; out: count x 4. */
+const char *mp2gpu_hash_no_pad_batch(const uint64_t *inputs, size_t count, size_t input_len,
+                                     uint32_t hash_kind, uint64_t *out);
+/* a, b, out: count x 4. */
+const char *mp2gpu_two_to_one_batch(const uint64_t *a, const uint64_t *b, size_t count,
+                                    uint32_t hash_kind, uint64_t *out);
+/* states: count x 12, permuted in place (PlonkyPermutation::permute). */
+const char *mp2gpu_permute_batch(uint64_t *states, size_t count, uint32_t hash_kind);
+
+/* ---- device-resident PolynomialBatch handle ------------------------------------------------ */
+/* get_lde_values(index, step): out[r] = leaves[row_idx[r]] (ncols elements each); row_idx are LEAF
+ * indices (callers apply bitrev(index*step) as plonky2 does). */
+const char *mp2gpu_batch_fetch_rows(const mp2gpu_batch *b, const uint64_t *row_idx, size_t nrows,
+                                    uint64_t *out);
+/* MerkleTree::prove on the device-resident digests. */
+const char *mp2gpu_batch_prove(const mp2gpu_batch *b, size_t leaf_index, uint64_t *siblings_out,
+                               size_t *nsiblings_out);
+/* Any of the outputs may be NULL. Sizes as for mp2gpu_commit_from_values. */
+const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_out,
+                               uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out);
+const char *mp2gpu_batch_shape(const mp2gpu_batch *b, size_t *ncols, uint32_t *n_log,
+                               uint32_t *rate_bits, uint32_t *cap_height, uint32_t *hash_kind);
+void mp2gpu_batch_free(mp2gpu_batch *b);
+
+/* ---- device-pointer stages (inputs already resident in HBM; asynchronous on `stream`, a
+ *      cudaStream_t passed as void*; NULL = the calling thread's library stream).  These are what
+ *      the multi-GPU driver and bench.py's device-resident leg call. ----------------------------- */
+/* values (ncols x n, column c at values + c*in_stride) -> coefficients (same shape, out_stride). */
+const char *mp2gpu_dev_intt(const uint64_t *values, size_t in_stride, uint64_t *coeffs,
+                            size_t out_stride, size_t ncols, uint32_t n_log, void *stream);
+/* coefficients -> coset LDE on 7*<w_N>, written LEAF-ordered and column-major:
+ * element (column c, leaf L) at lde[(L >> shard_log') ...] -- precisely
+ *   lde[(L / Ls) * shard_stride + c * lde_stride + (L % Ls)],  Ls = N >> shard_log,
+ * so that with shard_log = log2(G) the block destined for rank g of a row-sharded exchange is the
+ * contiguous range [g*shard_stride, g*shard_stride + ncols*lde_stride).  shard_log = 0 gives plain
+ * column-major (shard_stride ignored). */
+const char *mp2gpu_dev_coset_lde(const uint64_t *coeffs, size_t in_stride, uint64_t *lde,
+                                 size_t lde_stride, size_t ncols, uint32_t n_log,
+                                 uint32_t rate_bits, uint32_t shard_log, size_t shard_stride,
+                                 void *stream);
+/* Leaf-ordered column-major LDE (column c at lde + c*lde_stride, nleaves elements) -> optional
+ * row-major leaves (nleaves x ncols), digests and cap of a tree with `nleaves` leaves.  A rank of a
+ * G-way row-sharded batch passes nleaves = N/G and cap_height - log2(G): its digests/cap are the
+ * contiguous slices of the global arrays. */
+const char *mp2gpu_dev_merkle_colmajor(const uint64_t *lde, size_t lde_stride, size_t ncols,
+                                       size_t nleaves, uint32_t cap_height, uint32_t hash_kind,
+                                       uint64_t *leaves_out, uint64_t *digests_out,
+                                       uint64_t *cap_out, void *stream);
+/* Row-major leaves already on the device -> digests and cap. */
+const char *mp2gpu_dev_merkle_rowmajor(const uint64_t *leaves, size_t nleaves, size_t leaf_len,
+                                       uint32_t cap_height, uint32_t hash_kind,
+                                       uint64_t *digests_out, uint64_t *cap_out, void *stream);
+/* Whole commitment on device buffers: cols_dev is ncols x n column-major (stride n).
+ * coeffs_dev (ncols x n), lde_dev (ncols x N scratch, leaf-ordered column-major), leaves_dev
+ * (N x ncols, may be NULL), digests_dev, cap_dev are device buffers owned by the caller. */
+const char *mp2gpu_dev_commit(const uint64_t *cols_dev, size_t ncols, uint32_t n_log,
+                              uint32_t rate_bits, uint32_t cap_height, uint32_t hash_kind,
+                              int from_coeffs, uint64_t *coeffs_dev, uint64_t *lde_dev,
+                              uint64_t *leaves_dev, uint64_t *digests_dev, uint64_t *cap_dev,
+                              void *stream);
+/* Blocks until the calling thread's library stream (or `stream`) has drained. */
+const char *mp2gpu_sync(void *stream);
+/* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t mp2gpu_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MP2GPU_H */

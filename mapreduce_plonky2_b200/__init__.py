@@ -1,0 +1,12 @@
+"""mp2gpu -- B200-native (sm_100a) polynomial-batch commitment for plonky2 / mapreduce-plonky2.
+
+The package holds only what the hot path needs: ``csrc/`` (hand-written CUDA kernels + the C ABI of
+``include/mp2gpu.h``), ``plonky2.py`` (host-side mirror of the plonky2 surface the reference calls),
+``device.py`` (device-pointer stages for resident data) and ``sharded.py`` (multi-GPU driver).
+"""
+from ._lib import LIB_PATH, Mp2GpuError  # noqa: F401
+from .plonky2 import (POSEIDON, POSEIDON2, MerkleCap, MerkleProof, MerkleTree, PolynomialBatch,  # noqa: F401
+                      device_count, hash_no_pad, hash_no_pad_batch, hash_or_noop, hash_pad, init, launch_count,
+                      permute, reverse_bits, two_to_one, two_to_one_batch, verify_merkle_proof_to_cap)
+
+__version__ = "0.1.0"

@@ -1,0 +1,551 @@
+// extern "C" surface of libmp2gpu.so -- see include/mp2gpu.h for the contract of every symbol and
+// the reference interface it replaces.  Error convention copied from the reference's only FFI
+// (gnark-utils/src/lib.rs:17-52, gnark-utils/src/utils.rs:9-20): NULL = ok, else a malloc'ed string.
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <vector>
+
+#include "../../include/mp2gpu.h"
+#include "internal.h"
+
+namespace mp2 {
+std::atomic<uint64_t> g_launches{0};
+
+namespace {
+
+struct ThreadCtx {
+  int device = 0;
+  bool device_set = false;
+  cudaStream_t stream = nullptr;
+  int stream_device = -1;
+};
+thread_local ThreadCtx t_ctx;
+
+// Binds the calling thread to its device and returns its private stream.
+Status ctx_stream(cudaStream_t *out) {
+  ThreadCtx &c = t_ctx;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+  if (c.device >= ndev) return "device " + std::to_string(c.device) + " out of range";
+  MP2_CUDA(cudaSetDevice(c.device));
+  if (!c.stream || c.stream_device != c.device) {
+    MP2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.stream_device = c.device;
+    // keep freed blocks in the stream-ordered pool: commitments reuse the same sizes over and over
+    cudaMemPool_t pool;
+    MP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
+    uint64_t keep = UINT64_MAX;
+    MP2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  *out = c.stream;
+  return "";
+}
+
+Status pick_stream(void *user, cudaStream_t *out) {
+  cudaStream_t own;
+  MP2_TRY(ctx_stream(&own));  // also validates the device
+  *out = user ? (cudaStream_t)user : own;
+  return "";
+}
+
+const char *to_c(const Status &s) {
+  if (s.empty()) return nullptr;
+  char *p = (char *)malloc(s.size() + 1);
+  if (p) memcpy(p, s.c_str(), s.size() + 1);
+  return p;
+}
+
+// RAII for stream-ordered scratch
+struct DevBuf {
+  u64 *p = nullptr;
+  cudaStream_t st = nullptr;
+  Status alloc(size_t elems, cudaStream_t s) {
+    st = s;
+    if (elems == 0) elems = 1;
+    MP2_CUDA(cudaMallocAsync(&p, elems * sizeof(u64), s));
+    return "";
+  }
+  u64 *release() {
+    u64 *r = p;
+    p = nullptr;
+    return r;
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+
+Status check_commit_args(size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind) {
+  if (ncols == 0) return "PolynomialBatch: no polynomials";
+  if (n_log + rate_bits > 32) return "PolynomialBatch: degree_log + rate_bits exceeds two-adicity 32";
+  if (cap_height > n_log + rate_bits)
+    return "MerkleTree::new: cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())=" +
+           std::to_string(n_log + rate_bits);
+  if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
+  return "";
+}
+
+Status dev_commit(const u64 *cols, size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind,
+                  int from_coeffs, u64 *coeffs, u64 *lde, u64 *leaves, u64 *digests, u64 *cap, cudaStream_t st) {
+  MP2_TRY(check_commit_args(ncols, n_log, rate_bits, cap_height, hash_kind));
+  const size_t n = (size_t)1 << n_log, N = n << rate_bits;
+  if (from_coeffs) MP2_TRY(ntt_canonicalize(cols, n, coeffs, n, ncols, n, st));
+  else MP2_TRY(ntt_intt(cols, n, coeffs, n, ncols, n_log, st));
+  MP2_TRY(ntt_coset_lde(coeffs, n, lde, N, ncols, n_log, rate_bits, 0, 0, st));
+  MP2_TRY(merkle_colmajor(lde, N, ncols, N, cap_height, hash_kind, leaves, digests, cap, st));
+  return "";
+}
+
+}  // namespace
+}  // namespace mp2
+
+struct mp2gpu_batch {
+  int device;
+  size_t ncols;
+  u32 n_log, rate_bits, cap_height, hash_kind;
+  u64 *coeffs, *lde, *leaves, *digests, *cap;  // device
+};
+
+using namespace mp2;
+
+namespace {
+
+Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height,
+                   u32 hash_kind, int from_coeffs, uint64_t *const *coeffs_out, uint64_t *leaves_out,
+                   uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **handle_out) {
+  MP2_TRY(check_commit_args(ncols, n_log, rate_bits, cap_height, hash_kind));
+  if (!cols || !cap_out) return "null cols / cap_out";
+  cudaStream_t st;
+  MP2_TRY(ctx_stream(&st));
+  const size_t n = (size_t)1 << n_log, N = n << rate_bits, ncap = (size_t)1 << cap_height;
+  const size_t ndig = 2 * (N - ncap);
+  const bool want_rows = leaves_out != nullptr || handle_out != nullptr;
+  DevBuf d_in, d_coeffs, d_lde, d_leaves, d_dig, d_cap;
+  MP2_TRY(d_in.alloc(ncols * n, st));
+  MP2_TRY(d_coeffs.alloc(ncols * n, st));
+  MP2_TRY(d_lde.alloc(ncols * N, st));
+  if (want_rows) MP2_TRY(d_leaves.alloc(ncols * N, st));
+  MP2_TRY(d_dig.alloc(ndig * 4, st));
+  MP2_TRY(d_cap.alloc(ncap * 4, st));
+  for (size_t c = 0; c < ncols; c++) {
+    if (!cols[c]) return "null column pointer";
+    MP2_CUDA(cudaMemcpyAsync(d_in.p + c * n, cols[c], n * sizeof(u64), cudaMemcpyHostToDevice, st));
+  }
+  MP2_TRY(dev_commit(d_in.p, ncols, n_log, rate_bits, cap_height, hash_kind, from_coeffs, d_coeffs.p, d_lde.p,
+                     d_leaves.p, d_dig.p, d_cap.p, st));
+  if (coeffs_out)
+    for (size_t c = 0; c < ncols; c++)
+      if (coeffs_out[c])
+        MP2_CUDA(cudaMemcpyAsync(coeffs_out[c], d_coeffs.p + c * n, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  MP2_CUDA(cudaMemcpyAsync(cap_out, d_cap.p, ncap * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  if (digests_out && ndig)
+    MP2_CUDA(cudaMemcpyAsync(digests_out, d_dig.p, ndig * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  if (leaves_out)
+    MP2_CUDA(cudaMemcpyAsync(leaves_out, d_leaves.p, ncols * N * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  MP2_CUDA(cudaStreamSynchronize(st));
+  if (handle_out) {
+    mp2gpu_batch *b = new mp2gpu_batch();
+    MP2_CUDA(cudaGetDevice(&b->device));
+    b->ncols = ncols;
+    b->n_log = n_log;
+    b->rate_bits = rate_bits;
+    b->cap_height = cap_height;
+    b->hash_kind = hash_kind;
+    b->coeffs = d_coeffs.release();
+    b->lde = d_lde.release();
+    b->leaves = d_leaves.release();
+    b->digests = d_dig.release();
+    b->cap = d_cap.release();
+    *handle_out = b;
+  }
+  return "";
+}
+
+Status merkle_prove_indices(size_t nleaves, u32 cap_height, size_t leaf_index, std::vector<size_t> *idx) {
+  int lg = log2_exact(nleaves);
+  if (lg < 0) return "MerkleTree::prove: number of leaves is not a power of two";
+  if ((int)cap_height > lg) return "MerkleTree::prove: cap_height > log2(leaves.len())";
+  if (leaf_index >= nleaves) return "MerkleTree::prove: leaf_index out of range";
+  u32 h = (u32)lg - cap_height;
+  size_t per = 2 * (((size_t)1 << h) - 1);
+  size_t base = (leaf_index >> h) * per;
+  size_t pair_index = leaf_index & (((size_t)1 << h) - 1);
+  for (u32 i = 0; i < h; i++) {
+    size_t parity = pair_index & 1;
+    pair_index >>= 1;
+    size_t q = (pair_index << (i + 1)) + ((size_t)1 << i) - 1;
+    idx->push_back(base + 2 * q + (1 - parity));
+  }
+  return "";
+}
+
+template <typename F>
+const char *guarded(F f) {
+  try {
+    return to_c(f());
+  } catch (const std::exception &e) {
+    return to_c(std::string("exception: ") + e.what());
+  } catch (...) {
+    return to_c("unknown exception");
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *mp2gpu_version(void) { return "0.1.0 (sm_100a)"; }
+
+void mp2gpu_free_string(const char *s) { free((void *)s); }
+
+const char *mp2gpu_device_count(int *count_out) {
+  return guarded([&]() -> Status {
+    if (!count_out) return "null count_out";
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+      *count_out = 0;
+      return std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e);
+    }
+    *count_out = n;
+    return "";
+  });
+}
+
+const char *mp2gpu_init(int device) {
+  return guarded([&]() -> Status {
+    if (device < 0) return "negative device index";
+    t_ctx.device = device;
+    t_ctx.device_set = true;
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    cudaDeviceProp prop;
+    MP2_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+      return "device " + std::to_string(device) + " (" + prop.name + ", sm_" + std::to_string(prop.major) +
+             std::to_string(prop.minor) + ") is not a Blackwell sm_100 part; libmp2gpu is built for sm_100a only";
+    return "";
+  });
+}
+
+const char *mp2gpu_host_alloc(void **ptr_out, size_t bytes) {
+  return guarded([&]() -> Status {
+    if (!ptr_out) return "null ptr_out";
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    MP2_CUDA(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return "";
+  });
+}
+const char *mp2gpu_host_free(void *ptr) {
+  return guarded([&]() -> Status {
+    if (ptr) MP2_CUDA(cudaFreeHost(ptr));
+    return "";
+  });
+}
+
+const char *mp2gpu_commit_from_values(const uint64_t *const *cols, size_t ncols, uint32_t n_log, uint32_t rate_bits,
+                                      uint32_t cap_height, uint32_t hash_kind, uint64_t *const *coeffs_out,
+                                      uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out,
+                                      mp2gpu_batch **handle_out) {
+  return guarded([&]() {
+    return commit_host(cols, ncols, n_log, rate_bits, cap_height, hash_kind, 0, coeffs_out, leaves_out, digests_out,
+                       cap_out, handle_out);
+  });
+}
+const char *mp2gpu_commit_from_coeffs(const uint64_t *const *cols, size_t ncols, uint32_t n_log, uint32_t rate_bits,
+                                      uint32_t cap_height, uint32_t hash_kind, uint64_t *const *coeffs_out,
+                                      uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out,
+                                      mp2gpu_batch **handle_out) {
+  return guarded([&]() {
+    return commit_host(cols, ncols, n_log, rate_bits, cap_height, hash_kind, 1, coeffs_out, leaves_out, digests_out,
+                       cap_out, handle_out);
+  });
+}
+
+const char *mp2gpu_merkle_new(const uint64_t *leaves, size_t nleaves, size_t leaf_len, uint32_t cap_height,
+                              uint32_t hash_kind, uint64_t *digests_out, uint64_t *cap_out) {
+  return guarded([&]() -> Status {
+    int lg = log2_exact(nleaves);
+    if (lg < 0) return "MerkleTree::new: number of leaves (" + std::to_string(nleaves) + ") is not a power of two";
+    if ((int)cap_height > lg)
+      return "MerkleTree::new: cap_height=" + std::to_string(cap_height) +
+             " should be at most log2(leaves.len())=" + std::to_string(lg);
+    if (!cap_out || (!leaves && leaf_len)) return "null leaves / cap_out";
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    size_t ncap = (size_t)1 << cap_height, ndig = 2 * (nleaves - ncap);
+    DevBuf d_lv, d_dig, d_cap;
+    MP2_TRY(d_lv.alloc(nleaves * leaf_len, st));
+    MP2_TRY(d_dig.alloc(ndig * 4, st));
+    MP2_TRY(d_cap.alloc(ncap * 4, st));
+    if (leaf_len)
+      MP2_CUDA(cudaMemcpyAsync(d_lv.p, leaves, nleaves * leaf_len * sizeof(u64), cudaMemcpyHostToDevice, st));
+    MP2_TRY(merkle_rowmajor(d_lv.p, nleaves, leaf_len, cap_height, hash_kind, d_dig.p, d_cap.p, st));
+    MP2_CUDA(cudaMemcpyAsync(cap_out, d_cap.p, ncap * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (digests_out && ndig)
+      MP2_CUDA(cudaMemcpyAsync(digests_out, d_dig.p, ndig * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+const char *mp2gpu_merkle_new_ragged(const uint64_t *const *leaves, const size_t *leaf_lens, size_t nleaves,
+                                     uint32_t cap_height, uint32_t hash_kind, uint64_t *digests_out,
+                                     uint64_t *cap_out) {
+  return guarded([&]() -> Status {
+    int lg = log2_exact(nleaves);
+    if (lg < 0) return "MerkleTree::new: number of leaves (" + std::to_string(nleaves) + ") is not a power of two";
+    if ((int)cap_height > lg)
+      return "MerkleTree::new: cap_height=" + std::to_string(cap_height) +
+             " should be at most log2(leaves.len())=" + std::to_string(lg);
+    if (!cap_out || !leaves || !leaf_lens) return "null leaves / leaf_lens / cap_out";
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    std::vector<u64> off(nleaves + 1, 0);
+    for (size_t i = 0; i < nleaves; i++) off[i + 1] = off[i] + leaf_lens[i];
+    std::vector<u64> flat(off[nleaves] ? off[nleaves] : 1);
+    for (size_t i = 0; i < nleaves; i++)
+      if (leaf_lens[i]) memcpy(flat.data() + off[i], leaves[i], leaf_lens[i] * sizeof(u64));
+    size_t ncap = (size_t)1 << cap_height, ndig = 2 * (nleaves - ncap);
+    DevBuf d_flat, d_off, d_dig, d_cap;
+    MP2_TRY(d_flat.alloc(flat.size(), st));
+    MP2_TRY(d_off.alloc(off.size(), st));
+    MP2_TRY(d_dig.alloc(ndig * 4, st));
+    MP2_TRY(d_cap.alloc(ncap * 4, st));
+    MP2_CUDA(cudaMemcpyAsync(d_flat.p, flat.data(), flat.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    MP2_CUDA(cudaMemcpyAsync(d_off.p, off.data(), off.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+    MP2_TRY(merkle_ragged(d_flat.p, d_off.p, nleaves, cap_height, hash_kind, d_dig.p, d_cap.p, st));
+    MP2_CUDA(cudaMemcpyAsync(cap_out, d_cap.p, ncap * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (digests_out && ndig)
+      MP2_CUDA(cudaMemcpyAsync(digests_out, d_dig.p, ndig * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+const char *mp2gpu_merkle_prove(const uint64_t *digests, size_t nleaves, uint32_t cap_height, size_t leaf_index,
+                                uint64_t *siblings_out, size_t *nsiblings_out) {
+  return guarded([&]() -> Status {
+    std::vector<size_t> idx;
+    MP2_TRY(merkle_prove_indices(nleaves, cap_height, leaf_index, &idx));
+    if (!idx.empty() && (!digests || !siblings_out)) return "null digests / siblings_out";
+    for (size_t i = 0; i < idx.size(); i++) memcpy(siblings_out + 4 * i, digests + 4 * idx[i], 32);
+    if (nsiblings_out) *nsiblings_out = idx.size();
+    return "";
+  });
+}
+
+const char *mp2gpu_hash_no_pad_batch(const uint64_t *inputs, size_t count, size_t input_len, uint32_t hash_kind,
+                                     uint64_t *out) {
+  return guarded([&]() -> Status {
+    if (count == 0) return "";
+    if (!out || (!inputs && input_len)) return "null inputs / out";
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    DevBuf d_in, d_out;
+    MP2_TRY(d_in.alloc(count * input_len, st));
+    MP2_TRY(d_out.alloc(count * 4, st));
+    if (input_len)
+      MP2_CUDA(cudaMemcpyAsync(d_in.p, inputs, count * input_len * sizeof(u64), cudaMemcpyHostToDevice, st));
+    MP2_TRY(hash_no_pad_batch(d_in.p, count, input_len, hash_kind, d_out.p, st));
+    MP2_CUDA(cudaMemcpyAsync(out, d_out.p, count * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+const char *mp2gpu_two_to_one_batch(const uint64_t *a, const uint64_t *b, size_t count, uint32_t hash_kind,
+                                    uint64_t *out) {
+  return guarded([&]() -> Status {
+    if (count == 0) return "";
+    if (!a || !b || !out) return "null a / b / out";
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    DevBuf d_a, d_b, d_out;
+    MP2_TRY(d_a.alloc(count * 4, st));
+    MP2_TRY(d_b.alloc(count * 4, st));
+    MP2_TRY(d_out.alloc(count * 4, st));
+    MP2_CUDA(cudaMemcpyAsync(d_a.p, a, count * 32, cudaMemcpyHostToDevice, st));
+    MP2_CUDA(cudaMemcpyAsync(d_b.p, b, count * 32, cudaMemcpyHostToDevice, st));
+    MP2_TRY(two_to_one_batch(d_a.p, d_b.p, count, hash_kind, d_out.p, st));
+    MP2_CUDA(cudaMemcpyAsync(out, d_out.p, count * 32, cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+const char *mp2gpu_permute_batch(uint64_t *states, size_t count, uint32_t hash_kind) {
+  return guarded([&]() -> Status {
+    if (count == 0) return "";
+    if (!states) return "null states";
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    DevBuf d;
+    MP2_TRY(d.alloc(count * 12, st));
+    MP2_CUDA(cudaMemcpyAsync(d.p, states, count * 96, cudaMemcpyHostToDevice, st));
+    MP2_TRY(permute_batch(d.p, count, hash_kind, st));
+    MP2_CUDA(cudaMemcpyAsync(states, d.p, count * 96, cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+// ---- handle ---------------------------------------------------------------------------------
+const char *mp2gpu_batch_shape(const mp2gpu_batch *b, size_t *ncols, uint32_t *n_log, uint32_t *rate_bits,
+                               uint32_t *cap_height, uint32_t *hash_kind) {
+  return guarded([&]() -> Status {
+    if (!b) return "null batch handle";
+    if (ncols) *ncols = b->ncols;
+    if (n_log) *n_log = b->n_log;
+    if (rate_bits) *rate_bits = b->rate_bits;
+    if (cap_height) *cap_height = b->cap_height;
+    if (hash_kind) *hash_kind = b->hash_kind;
+    return "";
+  });
+}
+
+const char *mp2gpu_batch_fetch_rows(const mp2gpu_batch *b, const uint64_t *row_idx, size_t nrows, uint64_t *out) {
+  return guarded([&]() -> Status {
+    if (!b) return "null batch handle";
+    if (nrows == 0) return "";
+    if (!row_idx || !out) return "null row_idx / out";
+    const size_t N = ((size_t)1 << b->n_log) << b->rate_bits;
+    for (size_t i = 0; i < nrows; i++)
+      if (row_idx[i] >= N) return "get_lde_values: row index out of range";
+    t_ctx.device = b->device;
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    DevBuf d_idx, d_out;
+    MP2_TRY(d_idx.alloc(nrows, st));
+    MP2_TRY(d_out.alloc(nrows * b->ncols, st));
+    MP2_CUDA(cudaMemcpyAsync(d_idx.p, row_idx, nrows * sizeof(u64), cudaMemcpyHostToDevice, st));
+    MP2_TRY(gather_rows(b->leaves, b->lde, N, b->ncols, d_idx.p, nrows, d_out.p, st));
+    MP2_CUDA(cudaMemcpyAsync(out, d_out.p, nrows * b->ncols * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+const char *mp2gpu_batch_prove(const mp2gpu_batch *b, size_t leaf_index, uint64_t *siblings_out,
+                               size_t *nsiblings_out) {
+  return guarded([&]() -> Status {
+    if (!b) return "null batch handle";
+    const size_t N = ((size_t)1 << b->n_log) << b->rate_bits;
+    std::vector<size_t> idx;
+    MP2_TRY(merkle_prove_indices(N, b->cap_height, leaf_index, &idx));
+    if (!idx.empty() && !siblings_out) return "null siblings_out";
+    t_ctx.device = b->device;
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    for (size_t i = 0; i < idx.size(); i++)
+      MP2_CUDA(cudaMemcpyAsync(siblings_out + 4 * i, b->digests + 4 * idx[i], 32, cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    if (nsiblings_out) *nsiblings_out = idx.size();
+    return "";
+  });
+}
+
+const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_out, uint64_t *leaves_out,
+                               uint64_t *digests_out, uint64_t *cap_out) {
+  return guarded([&]() -> Status {
+    if (!b) return "null batch handle";
+    t_ctx.device = b->device;
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    const size_t n = (size_t)1 << b->n_log, N = n << b->rate_bits, ncap = (size_t)1 << b->cap_height;
+    if (coeffs_out)
+      for (size_t c = 0; c < b->ncols; c++)
+        if (coeffs_out[c])
+          MP2_CUDA(cudaMemcpyAsync(coeffs_out[c], b->coeffs + c * n, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (leaves_out) {
+      if (!b->leaves) return "batch holds no row-major leaves";
+      MP2_CUDA(cudaMemcpyAsync(leaves_out, b->leaves, N * b->ncols * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    }
+    if (digests_out && N > ncap)
+      MP2_CUDA(cudaMemcpyAsync(digests_out, b->digests, 2 * (N - ncap) * 32, cudaMemcpyDeviceToHost, st));
+    if (cap_out) MP2_CUDA(cudaMemcpyAsync(cap_out, b->cap, ncap * 32, cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+void mp2gpu_batch_free(mp2gpu_batch *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  for (u64 *p : {b->coeffs, b->lde, b->leaves, b->digests, b->cap})
+    if (p) cudaFree(p);
+  delete b;
+}
+
+// ---- device-pointer stages --------------------------------------------------------------------
+const char *mp2gpu_dev_intt(const uint64_t *values, size_t in_stride, uint64_t *coeffs, size_t out_stride,
+                            size_t ncols, uint32_t n_log, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    return ntt_intt((const u64 *)values, in_stride, (u64 *)coeffs, out_stride, ncols, n_log, st);
+  });
+}
+
+const char *mp2gpu_dev_coset_lde(const uint64_t *coeffs, size_t in_stride, uint64_t *lde, size_t lde_stride,
+                                 size_t ncols, uint32_t n_log, uint32_t rate_bits, uint32_t shard_log,
+                                 size_t shard_stride, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    return ntt_coset_lde((const u64 *)coeffs, in_stride, (u64 *)lde, lde_stride, ncols, n_log, rate_bits, shard_log,
+                         shard_stride, st);
+  });
+}
+
+const char *mp2gpu_dev_merkle_colmajor(const uint64_t *lde, size_t lde_stride, size_t ncols, size_t nleaves,
+                                       uint32_t cap_height, uint32_t hash_kind, uint64_t *leaves_out,
+                                       uint64_t *digests_out, uint64_t *cap_out, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    return merkle_colmajor((const u64 *)lde, lde_stride, ncols, nleaves, cap_height, hash_kind, (u64 *)leaves_out,
+                           (u64 *)digests_out, (u64 *)cap_out, st);
+  });
+}
+
+const char *mp2gpu_dev_merkle_rowmajor(const uint64_t *leaves, size_t nleaves, size_t leaf_len, uint32_t cap_height,
+                                       uint32_t hash_kind, uint64_t *digests_out, uint64_t *cap_out, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    return merkle_rowmajor((const u64 *)leaves, nleaves, leaf_len, cap_height, hash_kind, (u64 *)digests_out,
+                           (u64 *)cap_out, st);
+  });
+}
+
+const char *mp2gpu_dev_commit(const uint64_t *cols_dev, size_t ncols, uint32_t n_log, uint32_t rate_bits,
+                              uint32_t cap_height, uint32_t hash_kind, int from_coeffs, uint64_t *coeffs_dev,
+                              uint64_t *lde_dev, uint64_t *leaves_dev, uint64_t *digests_dev, uint64_t *cap_dev,
+                              void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    if (!cols_dev || !coeffs_dev || !lde_dev || !cap_dev) return "null device buffer";
+    if (!digests_dev && cap_height < n_log + rate_bits) return "null digests buffer";
+    return dev_commit((const u64 *)cols_dev, ncols, n_log, rate_bits, cap_height, hash_kind, from_coeffs,
+                      (u64 *)coeffs_dev, (u64 *)lde_dev, (u64 *)leaves_dev, (u64 *)digests_dev, (u64 *)cap_dev, st);
+  });
+}
+
+const char *mp2gpu_sync(void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  });
+}
+
+uint64_t mp2gpu_launch_count(void) { return g_launches.load(); }
+
+}  // extern "C"

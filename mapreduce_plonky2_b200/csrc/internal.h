@@ -1,0 +1,96 @@
+// Internal C++ interface between the translation units of libmp2gpu.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <string>
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+namespace mp2 {
+
+// "" = success; anything else is the message handed back across the C ABI.
+typedef std::string Status;
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define MP2_CUDA(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return std::string(#expr) + ": " + cudaGetErrorName(_e) + ": " + cudaGetErrorString(_e); \
+  } while (0)
+#define MP2_TRY(expr)            \
+  do {                           \
+    mp2::Status _s = (expr);     \
+    if (!_s.empty()) return _s;  \
+  } while (0)
+#define MP2_LAUNCH_CHECK()     \
+  do {                         \
+    mp2::count_launch();       \
+    MP2_CUDA(cudaGetLastError()); \
+  } while (0)
+
+// ---- host-side Goldilocks helpers (table seeds only; no data-path work happens on the host) ----
+static const u64 kP = 0xFFFFFFFF00000001ULL;
+inline u64 h_mul(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) % kP); }
+inline u64 h_pow(u64 a, u64 e) {
+  u64 r = 1;
+  a %= kP;
+  while (e) {
+    if (e & 1) r = h_mul(r, a);
+    a = h_mul(a, a);
+    e >>= 1;
+  }
+  return r;
+}
+inline u64 h_inv(u64 a) { return h_pow(a, kP - 2); }
+// plonky2 primitive_root_of_unity(k) = POWER_OF_TWO_GENERATOR^(2^(32-k)), generator 7^((p-1)/2^32)
+inline u64 h_root_of_unity(u32 log_n) {
+  u64 w = h_pow(7, (kP - 1) >> 32);
+  for (u32 i = log_n; i < 32; i++) w = h_mul(w, w);
+  return w;
+}
+
+// ---- device tables, cached per device (tables.cu) ----
+// W[m] = w_T^m for m < T = 2^log_t (T >= 1)
+Status table_roots(u32 log_t, cudaStream_t st, const u64 **out);
+// pow7[j] = 7^j for j < 2^log_n
+Status table_shift_powers(u32 log_n, cudaStream_t st, const u64 **out);
+
+// ---- transforms (ntt.cu) ----
+Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_stride, size_t ncols,
+                u32 n_log, cudaStream_t st);
+Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols,
+                     u32 n_log, u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st);
+Status ntt_canonicalize(const u64 *in, size_t in_stride, u64 *out, size_t out_stride, size_t ncols,
+                        size_t n, cudaStream_t st);
+
+// ---- hashing / Merkle (merkle.cu) ----
+Status merkle_colmajor(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves,
+                       u32 cap_height, u32 hash_kind, u64 *leaves_out, u64 *digests, u64 *cap,
+                       cudaStream_t st);
+Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 cap_height,
+                       u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st);
+// flat: concatenated leaves, offsets: nleaves+1 prefix sums (device)
+Status merkle_ragged(const u64 *flat, const u64 *offsets, size_t nleaves, u32 cap_height,
+                     u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st);
+Status hash_no_pad_batch(const u64 *inputs, size_t count, size_t input_len, u32 hash_kind, u64 *out,
+                         cudaStream_t st);
+Status two_to_one_batch(const u64 *a, const u64 *b, size_t count, u32 hash_kind, u64 *out,
+                        cudaStream_t st);
+Status permute_batch(u64 *states, size_t count, u32 hash_kind, cudaStream_t st);
+Status gather_rows(const u64 *leaves_rowmajor, const u64 *lde_colmajor, size_t lde_stride,
+                   size_t ncols, const u64 *row_idx, size_t nrows, u64 *out, cudaStream_t st);
+
+inline int log2_exact(size_t n) {
+  if (n == 0 || (n & (n - 1))) return -1;
+  int l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}
+
+}  // namespace mp2

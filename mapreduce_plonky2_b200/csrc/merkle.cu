@@ -1,0 +1,290 @@
+// Poseidon / Poseidon2 leaf hashing and Merkle tree + cap construction in plonky2's digest layout.
+//
+// Replaces plonky2::hash::merkle_tree::MerkleTree::new (fill_digests_buf / fill_subtree) and
+// Hasher::{hash_or_noop, hash_no_pad, two_to_one} -- SURVEY.md 8(a) a5/a6/a7, Appendix A.4/A.5.
+// Reference call sites: recursion-framework/src/universal_verifier_gadget/circuit_set.rs:189
+// (MerkleTree::new) and :216 (prove); sponge semantics restated in-circuit at
+// mp2-common/src/poseidon.rs:136-172 and mp2-common/src/hash.rs:16-46.
+//
+// Digest layout (A.4): the digests array is split into 2^cap_height equal chunks, one per cap
+// subtree of 2^h leaves.  Inside a chunk, node m of layer i (layer 0 = leaf digests, i < h) lives
+// at digest index 2*(((m>>1) << (i+1)) + (1<<i) - 1) + (m&1).  The subtree roots form the cap.
+#include "internal.h"
+#include "poseidon.cuh"
+
+namespace mp2 {
+
+// index (in digests) of node m of layer i inside one subtree chunk
+GL_DEV size_t node_slot(u32 layer, size_t m) {
+  return 2 * (((m >> 1) << (layer + 1)) + ((size_t)1 << layer) - 1) + (m & 1);
+}
+
+GL_DEV void store_digest(u64 *dst, const u64 (&s)[12]) {
+  ulonglong2 a = make_ulonglong2(gl_canon(s[0]), gl_canon(s[1]));
+  ulonglong2 b = make_ulonglong2(gl_canon(s[2]), gl_canon(s[3]));
+  reinterpret_cast<ulonglong2 *>(dst)[0] = a;
+  reinterpret_cast<ulonglong2 *>(dst)[1] = b;
+}
+
+// where the digest of leaf L goes: layer-0 slot of its subtree, or the cap if the tree is all cap
+GL_DEV u64 *leaf_digest_ptr(size_t L, u32 h, u64 *digests, u64 *cap) {
+  if (h == 0) return cap + 4 * L;
+  size_t sub = L >> h, l = L & (((size_t)1 << h) - 1);
+  size_t per = 2 * (((size_t)1 << h) - 1);
+  return digests + 4 * (sub * per + node_slot(0, l));
+}
+
+// ---- K4: leaf sponge.  One thread per leaf; rate 8, overwrite absorb (A.5). ---------------------
+// COLMAJOR: element (column c, leaf L) at in[c*stride + L]  -> loads coalesce across the warp.
+// !COLMAJOR: element at in[L*stride + c] (row-major user leaves, FRI layers).
+template <u32 KIND, bool COLMAJOR>
+__global__ void __launch_bounds__(128)
+k_leaf_hash(const u64 *__restrict__ in, size_t stride, u32 ncols, size_t nleaves, u32 h,
+            u64 *__restrict__ leaves_out, u64 *__restrict__ digests, u64 *__restrict__ cap) {
+  size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (L >= nleaves) return;
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = 0;
+  const u64 *src = COLMAJOR ? in + L : in + L * stride;
+  const size_t step = COLMAJOR ? stride : 1;
+  u64 *row = leaves_out ? leaves_out + L * (size_t)ncols : nullptr;
+  if (ncols <= 4) {  // hash_or_noop: no permutation, zero padded
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if (j < ncols) {
+        u64 v = gl_canon(src[j * step]);
+        st[j] = v;
+        if (row) row[j] = v;
+      }
+  } else {
+    for (u32 c0 = 0; c0 < ncols; c0 += 8) {
+      u32 m = ncols - c0 < 8 ? ncols - c0 : 8;
+      u64 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < m) v[j] = src[(size_t)(c0 + j) * step];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < m) {
+          st[j] = v[j];
+          if (row) row[c0 + j] = gl_canon(v[j]);
+        }
+      permute<KIND>(st);
+    }
+  }
+  store_digest(leaf_digest_ptr(L, h, digests, cap), st);
+}
+
+// ragged leaves: leaf L = flat[off[L] .. off[L+1])
+template <u32 KIND>
+__global__ void __launch_bounds__(128)
+k_leaf_hash_ragged(const u64 *__restrict__ flat, const u64 *__restrict__ off, size_t nleaves, u32 h,
+                   u64 *__restrict__ digests, u64 *__restrict__ cap) {
+  size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (L >= nleaves) return;
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = 0;
+  const u64 *src = flat + off[L];
+  size_t len = off[L + 1] - off[L];
+  if (len <= 4) {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      if ((size_t)j < len) st[j] = gl_canon(src[j]);
+  } else {
+    for (size_t c0 = 0; c0 < len; c0 += 8) {
+      size_t m = len - c0 < 8 ? len - c0 : 8;
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if ((size_t)j < m) st[j] = src[c0 + j];
+      permute<KIND>(st);
+    }
+  }
+  store_digest(leaf_digest_ptr(L, h, digests, cap), st);
+}
+
+// ---- K5: one Merkle layer.  Thread t -> node m of layer `layer` (1..h) of subtree sub. ---------
+template <u32 KIND>
+__global__ void __launch_bounds__(128)
+k_merkle_layer(u64 *__restrict__ digests, u64 *__restrict__ cap, u32 h, u32 layer, size_t nnodes) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnodes) return;
+  u32 width_log = h - layer;  // nodes of this layer per subtree = 2^width_log
+  size_t sub = t >> width_log, m = t & (((size_t)1 << width_log) - 1);
+  size_t per = 2 * (((size_t)1 << h) - 1);
+  u64 *base = digests + 4 * sub * per;
+  // children: nodes 2m, 2m+1 of layer-1 share one pair slot -> 8 contiguous u64
+  const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(base + 4 * node_slot(layer - 1, 2 * m));
+  ulonglong2 c0 = ch[0], c1 = ch[1], c2 = ch[2], c3 = ch[3];
+  u64 st[12] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y, 0, 0, 0, 0};
+  permute<KIND>(st);
+  u64 *dst = layer == h ? cap + 4 * sub : base + 4 * node_slot(layer, m);
+  store_digest(dst, st);
+}
+
+template <u32 KIND>
+__global__ void __launch_bounds__(128)
+k_two_to_one(const u64 *__restrict__ a, const u64 *__restrict__ b, size_t count, u64 *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    st[i] = a[4 * t + i];
+    st[4 + i] = b[4 * t + i];
+    st[8 + i] = 0;
+  }
+  permute<KIND>(st);
+  store_digest(out + 4 * t, st);
+}
+
+template <u32 KIND>
+__global__ void __launch_bounds__(128) k_permute(u64 *__restrict__ states, size_t count) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = states[12 * t + i];
+  permute<KIND>(st);
+#pragma unroll
+  for (int i = 0; i < 12; i++) states[12 * t + i] = gl_canon(st[i]);
+}
+
+// hash_no_pad over row-major inputs (never the no-op branch); len == 0 -> zeros
+template <u32 KIND>
+__global__ void __launch_bounds__(128)
+k_hash_no_pad(const u64 *__restrict__ in, size_t count, size_t len, u64 *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = 0;
+  const u64 *src = in + t * len;
+  for (size_t c0 = 0; c0 < len; c0 += 8) {
+    size_t m = len - c0 < 8 ? len - c0 : 8;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if ((size_t)j < m) st[j] = src[c0 + j];
+    permute<KIND>(st);
+  }
+  store_digest(out + 4 * t, st);
+}
+
+// get_lde_values: out[r][c] = leaf row row_idx[r]
+__global__ void k_gather_rows(const u64 *__restrict__ rowmajor, const u64 *__restrict__ colmajor,
+                              size_t stride, u32 ncols, const u64 *__restrict__ row_idx, size_t nrows,
+                              u64 *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows * ncols) return;
+  size_t r = t / ncols, c = t % ncols;
+  size_t L = row_idx[r];
+  out[t] = rowmajor ? rowmajor[L * ncols + c] : colmajor[c * stride + L];
+}
+
+static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+template <u32 KIND>
+static Status build_levels(u64 *digests, u64 *cap, u32 h, u32 cap_height, cudaStream_t st) {
+  for (u32 layer = 1; layer <= h; layer++) {
+    size_t nnodes = ((size_t)1 << (h - layer)) << cap_height;
+    k_merkle_layer<KIND><<<grid_for(nnodes, 128), 128, 0, st>>>(digests, cap, h, layer, nnodes);
+    MP2_LAUNCH_CHECK();
+  }
+  return "";
+}
+
+static Status check_tree_args(size_t nleaves, u32 cap_height, u32 hash_kind, u32 *h_out) {
+  int lg = log2_exact(nleaves);
+  if (lg < 0) return "MerkleTree::new: number of leaves (" + std::to_string(nleaves) + ") is not a power of two";
+  if ((int)cap_height > lg)
+    return "MerkleTree::new: cap_height=" + std::to_string(cap_height) + " should be at most log2(leaves.len())=" + std::to_string(lg);
+  if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
+  *h_out = (u32)lg - cap_height;
+  return "";
+}
+
+Status merkle_colmajor(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves, u32 cap_height,
+                       u32 hash_kind, u64 *leaves_out, u64 *digests, u64 *cap, cudaStream_t st) {
+  u32 h;
+  MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
+  if (ncols == 0 || ncols > 0xFFFFFFFFu) return "bad number of columns";
+  unsigned g = grid_for(nleaves, 128);
+  if (hash_kind == MP2_HASH_POSEIDON2)
+    k_leaf_hash<MP2_HASH_POSEIDON2, true><<<g, 128, 0, st>>>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap);
+  else
+    k_leaf_hash<MP2_HASH_POSEIDON, true><<<g, 128, 0, st>>>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap);
+  MP2_LAUNCH_CHECK();
+  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
+                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
+}
+
+Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 cap_height, u32 hash_kind,
+                       u64 *digests, u64 *cap, cudaStream_t st) {
+  u32 h;
+  MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
+  if (leaf_len > 0xFFFFFFFFu) return "leaf too long";
+  unsigned g = grid_for(nleaves, 128);
+  if (hash_kind == MP2_HASH_POSEIDON2)
+    k_leaf_hash<MP2_HASH_POSEIDON2, false><<<g, 128, 0, st>>>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap);
+  else
+    k_leaf_hash<MP2_HASH_POSEIDON, false><<<g, 128, 0, st>>>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap);
+  MP2_LAUNCH_CHECK();
+  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
+                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
+}
+
+Status merkle_ragged(const u64 *flat, const u64 *offsets, size_t nleaves, u32 cap_height, u32 hash_kind,
+                     u64 *digests, u64 *cap, cudaStream_t st) {
+  u32 h;
+  MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
+  unsigned g = grid_for(nleaves, 128);
+  if (hash_kind == MP2_HASH_POSEIDON2)
+    k_leaf_hash_ragged<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(flat, offsets, nleaves, h, digests, cap);
+  else
+    k_leaf_hash_ragged<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(flat, offsets, nleaves, h, digests, cap);
+  MP2_LAUNCH_CHECK();
+  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
+                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
+}
+
+Status hash_no_pad_batch(const u64 *inputs, size_t count, size_t input_len, u32 hash_kind, u64 *out,
+                         cudaStream_t st) {
+  if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
+  if (count == 0) return "";
+  unsigned g = grid_for(count, 128);
+  if (hash_kind == MP2_HASH_POSEIDON2) k_hash_no_pad<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(inputs, count, input_len, out);
+  else k_hash_no_pad<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(inputs, count, input_len, out);
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+
+Status two_to_one_batch(const u64 *a, const u64 *b, size_t count, u32 hash_kind, u64 *out, cudaStream_t st) {
+  if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
+  if (count == 0) return "";
+  unsigned g = grid_for(count, 128);
+  if (hash_kind == MP2_HASH_POSEIDON2) k_two_to_one<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(a, b, count, out);
+  else k_two_to_one<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(a, b, count, out);
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+
+Status permute_batch(u64 *states, size_t count, u32 hash_kind, cudaStream_t st) {
+  if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
+  if (count == 0) return "";
+  unsigned g = grid_for(count, 128);
+  if (hash_kind == MP2_HASH_POSEIDON2) k_permute<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(states, count);
+  else k_permute<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(states, count);
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+
+Status gather_rows(const u64 *rowmajor, const u64 *colmajor, size_t stride, size_t ncols, const u64 *row_idx,
+                   size_t nrows, u64 *out, cudaStream_t st) {
+  if (nrows == 0) return "";
+  k_gather_rows<<<grid_for(nrows * ncols, 256), 256, 0, st>>>(rowmajor, colmajor, stride, (u32)ncols, row_idx, nrows, out);
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+
+}  // namespace mp2

@@ -1,0 +1,61 @@
+// Device-resident twiddle tables, built once per (device, size) and cached for the process lifetime.
+// They stand in for plonky2's FftRootTable (the `fft_root_table` argument of
+// PolynomialBatch::from_values, which the GPU path ignores -- SURVEY.md 8(b) "Threading").
+#include <map>
+#include <mutex>
+
+#include "gl.cuh"
+#include "internal.h"
+
+namespace mp2 {
+
+__global__ void k_fill_powers(u64 *out, u64 base, size_t count) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < count) out[m] = gl_canon(gl_pow(base, m));
+}
+
+namespace {
+struct Key {
+  int device;
+  int kind;  // 0 roots, 1 shift powers
+  u32 log;
+  bool operator<(const Key &o) const {
+    if (device != o.device) return device < o.device;
+    if (kind != o.kind) return kind < o.kind;
+    return log < o.log;
+  }
+};
+std::mutex g_mu;
+std::map<Key, u64 *> g_tables;
+
+Status get_table(int kind, u32 log, u64 base, cudaStream_t st, const u64 **out) {
+  int dev = 0;
+  MP2_CUDA(cudaGetDevice(&dev));
+  Key key = {dev, kind, log};
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_tables.find(key);
+  if (it != g_tables.end()) {
+    *out = it->second;
+    return "";
+  }
+  size_t count = (size_t)1 << log;
+  u64 *d = nullptr;
+  MP2_CUDA(cudaMalloc(&d, sizeof(u64) * count));
+  k_fill_powers<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d, base, count);
+  MP2_LAUNCH_CHECK();
+  // other threads (other streams) may pick the table up from the cache right away
+  MP2_CUDA(cudaStreamSynchronize(st));
+  g_tables[key] = d;
+  *out = d;
+  return "";
+}
+}  // namespace
+
+Status table_roots(u32 log_t, cudaStream_t st, const u64 **out) {
+  return get_table(0, log_t, h_root_of_unity(log_t), st, out);
+}
+Status table_shift_powers(u32 log_n, cudaStream_t st, const u64 **out) {
+  return get_table(1, log_n, 7 /* coset_shift() = MULTIPLICATIVE_GROUP_GENERATOR */, st, out);
+}
+
+}  // namespace mp2

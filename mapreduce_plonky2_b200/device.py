@@ -1,0 +1,98 @@
+"""Device-pointer stages of the commitment for data already resident in HBM.
+
+PyTorch is used only as plumbing here: device memory (``torch.int64`` tensors viewed as u64 field
+elements), streams and, in ``sharded.py``, ``torch.distributed``.  All arithmetic is done by the
+hand-written kernels of ``libmp2gpu.so`` reached through the ``mp2gpu_dev_*`` C ABI, launched on
+torch's current stream so that ``torch.cuda.Event`` timings bracket them.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+POSEIDON, POSEIDON2 = 0, 1
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, name: str) -> int:
+    if t.dtype != torch.int64 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError("%s must be a contiguous CUDA int64 tensor (u64 field elements)" % name)
+    return t.data_ptr()
+
+
+def bind_current_device() -> None:
+    _lib.call("mp2gpu_init", torch.cuda.current_device())
+
+
+class CommitBuffers:
+    """Caller-owned device buffers of one commitment (allocated once, reused every step)."""
+
+    def __init__(self, ncols: int, n_log: int, rate_bits: int, cap_height: int, want_leaves: bool = True,
+                 device=None):
+        n, N = 1 << n_log, (1 << n_log) << rate_bits
+        ncap = 1 << cap_height
+        kw = dict(dtype=torch.int64, device=device or torch.device("cuda", torch.cuda.current_device()))
+        self.shape = (ncols, n_log, rate_bits, cap_height)
+        self.coeffs = torch.empty((ncols, n), **kw)
+        self.lde = torch.empty((ncols, N), **kw)            # leaf-ordered, column-major
+        self.leaves = torch.empty((N, ncols), **kw) if want_leaves else None  # plonky2's row-major leaves
+        self.digests = torch.empty((max(2 * (N - ncap), 1), 4), **kw)
+        self.cap = torch.empty((ncap, 4), **kw)
+
+
+def commit_resident(cols: torch.Tensor, bufs: CommitBuffers, hash_kind: int = POSEIDON2,
+                    from_coeffs: bool = False) -> None:
+    """PolynomialBatch::from_values / from_coeffs on resident inputs; asynchronous on the current stream."""
+    ncols, n_log, rate_bits, cap_height = bufs.shape
+    if tuple(cols.shape) != (ncols, 1 << n_log):
+        raise ValueError("cols must be (ncols, n)")
+    _lib.call("mp2gpu_dev_commit", _chk(cols, "cols"), ncols, n_log, rate_bits, cap_height, hash_kind,
+              1 if from_coeffs else 0, _chk(bufs.coeffs, "coeffs"), _chk(bufs.lde, "lde"),
+              _chk(bufs.leaves, "leaves") if bufs.leaves is not None else None, _chk(bufs.digests, "digests"),
+              _chk(bufs.cap, "cap"), _stream_ptr())
+
+
+def intt(values: torch.Tensor, coeffs: torch.Tensor) -> None:
+    ncols, n = values.shape
+    _lib.call("mp2gpu_dev_intt", _chk(values, "values"), n, _chk(coeffs, "coeffs"), n, ncols,
+              n.bit_length() - 1, _stream_ptr())
+
+
+def coset_lde(coeffs: torch.Tensor, lde: torch.Tensor, rate_bits: int, shard_log: int = 0) -> None:
+    """coeffs (ncols, n) -> leaf-ordered column-major LDE.  With ``shard_log = log2(G)`` ``lde`` has shape
+    (G, ncols, N/G): block g holds the leaves of row-shard g (the all-to-all payload for rank g)."""
+    ncols, n = coeffs.shape
+    N = n << rate_bits
+    if shard_log:
+        G = 1 << shard_log
+        if tuple(lde.shape) != (G, ncols, N // G):
+            raise ValueError("sharded lde must be (G, ncols, N/G)")
+        lde_stride, shard_stride = N // G, ncols * (N // G)
+    else:
+        if tuple(lde.shape) != (ncols, N):
+            raise ValueError("lde must be (ncols, N)")
+        lde_stride, shard_stride = N, 0
+    _lib.call("mp2gpu_dev_coset_lde", _chk(coeffs, "coeffs"), n, _chk(lde, "lde"), lde_stride, ncols,
+              n.bit_length() - 1, rate_bits, shard_log, shard_stride, _stream_ptr())
+
+
+def merkle_colmajor(lde: torch.Tensor, cap_height: int, hash_kind: int, leaves: Optional[torch.Tensor],
+                    digests: torch.Tensor, cap: torch.Tensor) -> None:
+    """lde (ncols, nleaves) leaf-ordered column-major -> row-major leaves (optional), digests, cap."""
+    ncols, nleaves = lde.shape
+    _lib.call("mp2gpu_dev_merkle_colmajor", _chk(lde, "lde"), nleaves, ncols, nleaves, cap_height, hash_kind,
+              _chk(leaves, "leaves") if leaves is not None else None, _chk(digests, "digests"), _chk(cap, "cap"),
+              _stream_ptr())
+
+
+def merkle_rowmajor(leaves: torch.Tensor, cap_height: int, hash_kind: int, digests: torch.Tensor,
+                    cap: torch.Tensor) -> None:
+    nleaves, leaf_len = leaves.shape
+    _lib.call("mp2gpu_dev_merkle_rowmajor", _chk(leaves, "leaves"), nleaves, leaf_len, cap_height, hash_kind,
+              _chk(digests, "digests"), _chk(cap, "cap"), _stream_ptr())

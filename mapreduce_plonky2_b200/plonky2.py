@@ -1,0 +1,299 @@
+"""Host-side mirror of the plonky2 surface the reference reaches the hot path through.
+
+Names, argument meaning and error behaviour follow plonky2 0.2.2 (the reference's pinned crate,
+Cargo.toml:63,114-117) so that the parity tests read like the reference's own:
+
+* ``PolynomialBatch.from_values / from_coeffs / get_lde_values``  (plonky2 ``fri/oracle.rs``; reached via
+  ``circuit_data.prove`` at recursion-framework/src/circuit_builder.rs:308 and ``builder.build`` at :177)
+* ``MerkleTree.new / prove / get``, ``MerkleCap``, ``MerkleProof`` (plonky2 ``hash/merkle_tree.rs``; called
+  directly at recursion-framework/src/universal_verifier_gadget/circuit_set.rs:189, :216)
+* ``hash_no_pad / hash_or_noop / two_to_one / hash_pad / permute`` (plonky2 ``hash/hashing.rs``;
+  native uses mp2-common/src/poseidon.rs:49-51, mp2-common/src/utils.rs:294-315)
+
+Where Rust would panic (``MerkleTree::new`` with a bad ``cap_height`` ...), :class:`Mp2GpuError` is
+raised.  All work is done by ``libmp2gpu.so`` through its C ABI; nothing here computes on the CPU.
+The hasher is a compile-time feature in the reference (``original_poseidon``); here it is the
+``hash_kind`` argument (default Poseidon2 = the reference's default ``C``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Mp2GpuError, u64p, u64pp
+
+POSEIDON = 0   # PoseidonGoldilocksConfig
+POSEIDON2 = 1  # Poseidon2GoldilocksConfig (default C, mp2-common/src/lib.rs:37-40)
+SALT_SIZE = 4
+ORDER = 0xFFFFFFFF00000001
+
+
+def _arr(x, ndim=None) -> np.ndarray:
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.uint64))
+    if ndim is not None and a.ndim != ndim:
+        raise ValueError("expected a %d-d array of field elements" % ndim)
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(u64p) if a is not None else None
+
+
+def _col_ptrs(a: np.ndarray):
+    return (u64p * a.shape[0])(*[C.cast(a[c].ctypes.data, u64p) for c in range(a.shape[0])])
+
+
+def init(device: int = 0) -> None:
+    """Bind the calling thread to ``device`` (and fail loudly if it is not a usable sm_100 GPU)."""
+    _lib.call("mp2gpu_init", device)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    _lib.call("mp2gpu_device_count", C.byref(n))
+    return n.value
+
+
+def launch_count() -> int:
+    return int(_lib.load().mp2gpu_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# Hasher
+# ------------------------------------------------------------------------------------------------
+def permute(states, hash_kind: int = POSEIDON2) -> np.ndarray:
+    """PlonkyPermutation::permute on a batch of width-12 states (shape (..., 12))."""
+    s = _arr(states).copy()
+    if s.shape[-1] != 12:
+        raise ValueError("states must have 12 lanes")
+    _lib.call("mp2gpu_permute_batch", _ptr(s), s.size // 12, hash_kind)
+    return s
+
+
+def hash_no_pad_batch(inputs, hash_kind: int = POSEIDON2) -> np.ndarray:
+    x = _arr(inputs, 2)
+    out = np.zeros((x.shape[0], 4), dtype=np.uint64)
+    _lib.call("mp2gpu_hash_no_pad_batch", _ptr(x) if x.size else None, x.shape[0], x.shape[1], hash_kind, _ptr(out))
+    return out
+
+
+def hash_no_pad(x, hash_kind: int = POSEIDON2) -> np.ndarray:
+    x = _arr(x).reshape(-1)
+    if x.size == 0:  # hash_no_pad(&[]) absorbs nothing: mp2-common/src/poseidon.rs:49-51
+        return np.zeros(4, dtype=np.uint64)
+    return hash_no_pad_batch(x.reshape(1, -1), hash_kind)[0]
+
+
+def hash_pad(x, hash_kind: int = POSEIDON2) -> np.ndarray:
+    """pad10*1 to a multiple of the rate (8), then hash_no_pad (circuit_set.rs:149-151)."""
+    x = [int(v) for v in _arr(x).reshape(-1)] + [1]
+    while (len(x) + 1) % 8:
+        x.append(0)
+    return hash_no_pad(np.array(x + [1], dtype=np.uint64), hash_kind)
+
+
+def hash_or_noop(x, hash_kind: int = POSEIDON2) -> np.ndarray:
+    x = _arr(x).reshape(-1)
+    if x.size <= 4:
+        out = np.zeros(4, dtype=np.uint64)
+        out[:x.size] = np.where(x >= np.uint64(ORDER), x - np.uint64(ORDER), x)
+        return out
+    return hash_no_pad(x, hash_kind)
+
+
+def two_to_one_batch(a, b, hash_kind: int = POSEIDON2) -> np.ndarray:
+    a, b = _arr(a, 2), _arr(b, 2)
+    if a.shape != b.shape or a.shape[1] != 4:
+        raise ValueError("two_to_one takes (count, 4) digests")
+    out = np.zeros_like(a)
+    _lib.call("mp2gpu_two_to_one_batch", _ptr(a), _ptr(b), a.shape[0], hash_kind, _ptr(out))
+    return out
+
+
+def two_to_one(a, b, hash_kind: int = POSEIDON2) -> np.ndarray:
+    return two_to_one_batch(_arr(a).reshape(1, 4), _arr(b).reshape(1, 4), hash_kind)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# MerkleTree
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class MerkleCap:
+    """``MerkleCap(pub Vec<H::Hash>)``: 2^cap_height digests."""
+    hashes: np.ndarray  # (2^cap_height, 4)
+
+    def height(self) -> int:
+        return int(self.hashes.shape[0]).bit_length() - 1
+
+    def __len__(self) -> int:
+        return int(self.hashes.shape[0])
+
+    def flatten(self) -> np.ndarray:
+        return self.hashes.reshape(-1)
+
+
+@dataclass
+class MerkleProof:
+    siblings: np.ndarray  # (log2(leaves) - cap_height, 4), bottom-up
+
+    def __len__(self) -> int:
+        return int(self.siblings.shape[0])
+
+
+class MerkleTree:
+    """``MerkleTree<F, H>{ leaves, digests, cap }`` built on the GPU."""
+
+    def __init__(self, leaves, digests: np.ndarray, cap: MerkleCap, hash_kind: int):
+        self.leaves = leaves
+        self.digests = digests
+        self.cap = cap
+        self.hash_kind = hash_kind
+
+    @classmethod
+    def new(cls, leaves, cap_height: int, hash_kind: int = POSEIDON2) -> "MerkleTree":
+        """``MerkleTree::new(leaves: Vec<Vec<F>>, cap_height)``.
+
+        ``leaves`` is a 2-d array, or a list of 1-d arrays of differing lengths (the circuit-set tree
+        pads with ``vec![F::ZERO]``).  Raises where plonky2 panics: length not a power of two,
+        ``cap_height > log2(len)``."""
+        ragged = not isinstance(leaves, np.ndarray) and len({len(l) for l in leaves}) > 1
+        n = len(leaves)
+        ncap = 1 << cap_height
+        digests = np.zeros((max(2 * (n - ncap), 0), 4), dtype=np.uint64)
+        cap = np.zeros((ncap, 4), dtype=np.uint64)
+        if ragged:
+            rows = [_arr(l).reshape(-1) for l in leaves]
+            ptrs = (u64p * n)(*[C.cast(r.ctypes.data, u64p) for r in rows])
+            lens = (C.c_size_t * n)(*[r.size for r in rows])
+            _lib.call("mp2gpu_merkle_new_ragged", ptrs, lens, n, cap_height, hash_kind,
+                      _ptr(digests) if digests.size else None, _ptr(cap))
+            return cls(rows, digests, MerkleCap(cap), hash_kind)
+        lv = _arr(leaves, 2)
+        _lib.call("mp2gpu_merkle_new", _ptr(lv) if lv.size else None, lv.shape[0], lv.shape[1], cap_height,
+                  hash_kind, _ptr(digests) if digests.size else None, _ptr(cap))
+        return cls(lv, digests, MerkleCap(cap), hash_kind)
+
+    def get(self, i: int) -> np.ndarray:
+        return self.leaves[i]
+
+    def prove(self, leaf_index: int) -> MerkleProof:
+        n = len(self.leaves)
+        h = (n.bit_length() - 1) - self.cap.height()
+        sib = np.zeros((max(h, 1), 4), dtype=np.uint64)
+        cnt = C.c_size_t(0)
+        _lib.call("mp2gpu_merkle_prove", _ptr(self.digests) if self.digests.size else None, n,
+                  self.cap.height(), leaf_index, _ptr(sib), C.byref(cnt))
+        return MerkleProof(sib[:cnt.value])
+
+
+def verify_merkle_proof_to_cap(leaf_data, leaf_index: int, cap: MerkleCap, proof: MerkleProof,
+                               hash_kind: int = POSEIDON2) -> None:
+    """plonky2's ``verify_merkle_proof_to_cap`` (native twin of the gadget used at
+    recursion-framework/src/universal_verifier_gadget/verifier_gadget.rs:136-167)."""
+    cur = hash_or_noop(leaf_data, hash_kind)
+    idx = leaf_index
+    for sib in proof.siblings:
+        cur = two_to_one(sib, cur, hash_kind) if idx & 1 else two_to_one(cur, sib, hash_kind)
+        idx >>= 1
+    if not np.array_equal(cur, cap.hashes[idx]):
+        raise Mp2GpuError("Invalid Merkle proof.")
+
+
+# ------------------------------------------------------------------------------------------------
+# PolynomialBatch
+# ------------------------------------------------------------------------------------------------
+def reverse_bits(x: int, bits: int) -> int:
+    return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
+
+
+class PolynomialBatch:
+    """``PolynomialBatch<F, C, D>{ polynomials, merkle_tree, degree_log, rate_bits, blinding }``."""
+
+    def __init__(self, polynomials, merkle_tree: MerkleTree, degree_log: int, rate_bits: int, blinding: bool,
+                 handle=None):
+        self.polynomials = polynomials  # (ncols, n) coefficients
+        self.merkle_tree = merkle_tree
+        self.degree_log = degree_log
+        self.rate_bits = rate_bits
+        self.blinding = blinding
+        self._handle = handle  # device-resident copy (mp2gpu_batch*), optional
+
+    # -- constructors ------------------------------------------------------------------------
+    @classmethod
+    def _commit(cls, fn: str, cols, rate_bits, blinding, cap_height, hash_kind, keep_on_device, fetch_leaves):
+        if blinding:
+            raise Mp2GpuError("blinding (salted) batches are not supported: the reference never enables "
+                              "zero_knowledge (mp2-common/src/lib.rs:45-47)")
+        cols = _arr(cols, 2)
+        ncols, n = cols.shape
+        n_log = int(n).bit_length() - 1
+        if ncols == 0 or n == 0 or (1 << n_log) != n:
+            raise Mp2GpuError("PolynomialValues length must be a power of two and the batch non-empty")
+        N = n << rate_bits
+        ncap = 1 << cap_height
+        coeffs = np.empty((ncols, n), dtype=np.uint64)
+        leaves = np.empty((N, ncols), dtype=np.uint64) if fetch_leaves else None
+        digests = np.empty((max(2 * (N - ncap), 0), 4), dtype=np.uint64)
+        cap = np.empty((ncap, 4), dtype=np.uint64)
+        handle = C.c_void_p(None)
+        _lib.call(fn, _col_ptrs(cols), ncols, n_log, rate_bits, cap_height, hash_kind, _col_ptrs(coeffs),
+                  _ptr(leaves), _ptr(digests) if digests.size else None, _ptr(cap),
+                  C.byref(handle) if keep_on_device else None)
+        tree = MerkleTree(leaves, digests, MerkleCap(cap), hash_kind)
+        return cls(coeffs, tree, n_log, rate_bits, False, handle if keep_on_device else None)
+
+    @classmethod
+    def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
+                    fft_root_table=None, hash_kind: int = POSEIDON2, keep_on_device: bool = False,
+                    fetch_leaves: bool = True) -> "PolynomialBatch":
+        """``PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table)``.
+        ``timing`` / ``fft_root_table`` are accepted and ignored (twiddles are device resident)."""
+        return cls._commit("mp2gpu_commit_from_values", values, rate_bits, blinding, cap_height, hash_kind,
+                           keep_on_device, fetch_leaves)
+
+    @classmethod
+    def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
+                    fft_root_table=None, hash_kind: int = POSEIDON2, keep_on_device: bool = False,
+                    fetch_leaves: bool = True) -> "PolynomialBatch":
+        return cls._commit("mp2gpu_commit_from_coeffs", polynomials, rate_bits, blinding, cap_height, hash_kind,
+                           keep_on_device, fetch_leaves)
+
+    # -- accessors -----------------------------------------------------------------------------
+    def get_lde_values(self, index: int, step: int) -> np.ndarray:
+        """Row ``reverse_bits(index * step, degree_log + rate_bits)`` of the leaves (minus salt)."""
+        row = reverse_bits(index * step, self.degree_log + self.rate_bits)
+        if self.merkle_tree.leaves is not None:
+            return self.merkle_tree.leaves[row]
+        return self.fetch_rows([row])[0]
+
+    def fetch_rows(self, rows: Sequence[int]) -> np.ndarray:
+        if self._handle is None:
+            raise Mp2GpuError("batch was not kept on the device")
+        idx = _arr(rows, 1)
+        out = np.empty((idx.size, self.polynomials.shape[0]), dtype=np.uint64)
+        _lib.call("mp2gpu_batch_fetch_rows", self._handle, _ptr(idx), idx.size, _ptr(out))
+        return out
+
+    def prove_on_device(self, leaf_index: int) -> MerkleProof:
+        if self._handle is None:
+            raise Mp2GpuError("batch was not kept on the device")
+        h = self.degree_log + self.rate_bits - self.merkle_tree.cap.height()
+        sib = np.zeros((max(h, 1), 4), dtype=np.uint64)
+        cnt = C.c_size_t(0)
+        _lib.call("mp2gpu_batch_prove", self._handle, leaf_index, _ptr(sib), C.byref(cnt))
+        return MerkleProof(sib[:cnt.value])
+
+    def free(self) -> None:
+        if self._handle is not None:
+            _lib.load().mp2gpu_batch_free(self._handle)
+            self._handle = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
