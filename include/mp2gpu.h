@@ -117,8 +117,10 @@ const char *mp2gpu_batch_shape(const mp2gpu_batch *b, size_t *ncols, uint32_t *n
 void mp2gpu_batch_free(mp2gpu_batch *b);
 
 /* ---- device-pointer stages (inputs already resident in HBM; asynchronous on `stream`, a
- *      cudaStream_t passed as void*; NULL = the calling thread's library stream).  These are what
- *      the multi-GPU driver and bench.py's device-resident leg call. ----------------------------- */
+ *      cudaStream_t passed as void*: NULL is CUDA's legacy default stream, MP2GPU_STREAM_THREAD the
+ *      calling thread's private library stream).  These are what the multi-GPU driver and bench.py's
+ *      device-resident leg call. ------------------------------------------------------------------ */
+#define MP2GPU_STREAM_THREAD ((void *)(~(uintptr_t)0))
 /* values (ncols x n, column c at values + c*in_stride) -> coefficients (same shape, out_stride). */
 const char *mp2gpu_dev_intt(const uint64_t *values, size_t in_stride, uint64_t *coeffs,
                             size_t out_stride, size_t ncols, uint32_t n_log, void *stream);
@@ -152,10 +154,23 @@ const char *mp2gpu_dev_commit(const uint64_t *cols_dev, size_t ncols, uint32_t n
                               int from_coeffs, uint64_t *coeffs_dev, uint64_t *lde_dev,
                               uint64_t *leaves_dev, uint64_t *digests_dev, uint64_t *cap_dev,
                               void *stream);
-/* Blocks until the calling thread's library stream (or `stream`) has drained. */
+/* Blocks until `stream` (see above for NULL / MP2GPU_STREAM_THREAD) has drained. */
 const char *mp2gpu_sync(void *stream);
+/* Canonicalises `count` field elements (x >= p -> x - p); in == out allowed. */
+const char *mp2gpu_dev_canonicalize(const uint64_t *in, uint64_t *out, size_t count, void *stream);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t mp2gpu_launch_count(void);
+
+/* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
+/* While enabled, every kernel launch is bracketed by CUDA events on its own stream. */
+const char *mp2gpu_profile_enable(int on);
+/* Synchronises the device and writes "kernel_name launches total_ms\n" lines for everything
+ * recorded since the last report into buf (NUL terminated). */
+const char *mp2gpu_profile_report(char *buf, size_t buf_len);
+/* Live probe of the 32-bit integer multiply-add issue rate (the Poseidon roofline denominator):
+ * thread-instructions per clock per SM, SM clock held during the probe (MHz), and T IMAD/s. */
+const char *mp2gpu_debug_int_pipe_peak(double *imad_per_clk_per_sm, double *sm_clock_mhz,
+                                       double *t_imad_per_s);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmp2gpu.so")
+LIB_PATH = os.environ.get("MP2GPU_LIB") or os.path.join(HERE, "libmp2gpu.so")  # override: tuning variants
 
 u64p = C.POINTER(C.c_uint64)
 u64pp = C.POINTER(u64p)
@@ -54,7 +54,11 @@ SIGNATURES = {
                                           C.c_void_p, C.c_void_p]),
     "mp2gpu_dev_commit": (_ERR, [C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mp2gpu_dev_canonicalize": (_ERR, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "mp2gpu_sync": (_ERR, [C.c_void_p]),
+    "mp2gpu_profile_enable": (_ERR, [C.c_int]),
+    "mp2gpu_profile_report": (_ERR, [C.c_char_p, C.c_size_t]),
+    "mp2gpu_debug_int_pipe_peak": (_ERR, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mp2gpu_launch_count": (C.c_uint64, []),
 }
 

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmp2gpu.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "ntt.cu", "merkle.cu", "tables.cu"]
+SOURCES = ["api.cu", "ntt.cu", "merkle.cu", "tables.cu", "prof.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--use_fast_math"]
 
@@ -27,7 +27,15 @@ def _newest_dep() -> float:
     return max(os.path.getmtime(d) for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, out: str = None) -> str:
+    global LIB, OBJ_DIR
+    if out:
+        LIB = os.path.abspath(out)
+        OBJ_DIR = LIB + ".objs"
+        force = True
+    extra = os.environ.get("MP2_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DMP2_HASH_BLOCK=512
+    if extra:
+        force = True
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_dep():
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -38,7 +46,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -57,4 +65,5 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     import sys
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, out=out))

@@ -47,7 +47,7 @@ Status ctx_stream(cudaStream_t *out) {
 Status pick_stream(void *user, cudaStream_t *out) {
   cudaStream_t own;
   MP2_TRY(ctx_stream(&own));  // also validates the device
-  *out = user ? (cudaStream_t)user : own;
+  *out = user == MP2GPU_STREAM_THREAD ? own : (cudaStream_t)user;  // NULL = CUDA's legacy default stream
   return "";
 }
 
@@ -534,6 +534,14 @@ const char *mp2gpu_dev_commit(const uint64_t *cols_dev, size_t ncols, uint32_t n
     if (!digests_dev && cap_height < n_log + rate_bits) return "null digests buffer";
     return dev_commit((const u64 *)cols_dev, ncols, n_log, rate_bits, cap_height, hash_kind, from_coeffs,
                       (u64 *)coeffs_dev, (u64 *)lde_dev, (u64 *)leaves_dev, (u64 *)digests_dev, (u64 *)cap_dev, st);
+  });
+}
+
+const char *mp2gpu_dev_canonicalize(const uint64_t *in, uint64_t *out, size_t count, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    return ntt_canonicalize((const u64 *)in, count, (u64 *)out, count, 1, count, st);
   });
 }
 

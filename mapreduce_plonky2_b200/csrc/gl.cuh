@@ -1,8 +1,12 @@
 // Goldilocks field arithmetic for sm_100a: p = 2^64 - 2^32 + 1, eps = 2^32 - 1 = 2^64 mod p.
 // Replaces plonky2_field::goldilocks_field (field order also stated at
-// mp2-common/src/group_hashing/utils.rs:51).  Everything is built from 32-bit IMAD.WIDE / IADD3
-// chains: the B200 has no 64-bit integer multiplier, so a 64x64->128 product is four
-// mad.wide.u32 and the reduction uses 2^64 = eps, 2^96 = -1 (mod p).
+// mp2-common/src/group_hashing/utils.rs:51).
+//
+// The B200 has no 64-bit integer multiplier: a 64x64->128 product is four IMAD.WIDE.U32, and on this
+// part IMAD.WIDE / IMAD.HI issue at ~1/3.2 of the plain 32-bit IMAD rate (measured by
+// tools/intpipe_peak.cu: 20 vs 63 thread-instr/clk/SM).  Everything around the four wide multiplies
+// is therefore written as explicit carry chains (add.cc/addc -> IADD3/IADD3.X), which ptxas spreads
+// over the alu and fma pipes, and reductions use 2^64 = eps, 2^96 = -1 (mod p) with no multiply.
 //
 // Value conventions used by the kernels:
 //   "canonical"  x <  p          -- what is written to memory that leaves the library
@@ -22,7 +26,11 @@ GL_DEV u64 gl_canon(u64 a) { return a >= GL_P ? a - GL_P : a; }
 
 GL_DEV u32 lo32(u64 x) { return (u32)x; }
 GL_DEV u32 hi32(u64 x) { return (u32)(x >> 32); }
-GL_DEV u64 pack64(u32 lo, u32 hi) { return ((u64)hi << 32) | lo; }
+GL_DEV u64 pack64(u32 lo, u32 hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
 
 // a*b + c with 32-bit a, b and 64-bit c: one IMAD.WIDE.U32
 GL_DEV u64 mad_wide(u32 a, u32 b, u64 c) {
@@ -39,66 +47,90 @@ GL_DEV u64 mul_wide(u32 a, u32 b) {
 // loose + loose -> loose.  2^64 = eps, so a carry out is folded back as +eps; a second carry is
 // possible only when both inputs are >= 2^64 - 2^32, and is folded the same way.
 GL_DEV u64 gl_add(u64 a, u64 b) {
-  u64 s = a + b;
-  if (s < a) {
-    u64 t = s + GL_EPS;
-    s = t < s ? t + GL_EPS : t;
-  }
-  return s;
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 c, m;\n\t"
+      "add.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
+      "sub.u32 m, 0, c;\n\t"                                     // eps if carry
+      "add.cc.u32 %0, %0, m;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 c, 0, 0;\n\t"
+      "sub.u32 m, 0, c;\n\t"
+      "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+  return pack64(r0, r1);
 }
-// canonical/loose a, CANONICAL b -> loose  (single fold is enough: s_wrapped <= a - 2^32 + 1... )
+// loose a + CANONICAL b -> loose: the wrapped sum is <= p - 2, so one fold is enough
 GL_DEV u64 gl_add_c(u64 a, u64 b_canonical) {
-  u64 s = a + b_canonical;
-  return s < a ? s + GL_EPS : s;
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 c, m;\n\t"
+      "add.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
+      "sub.u32 m, 0, c;\n\t"
+      "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b_canonical)), "r"(hi32(b_canonical)));
+  return pack64(r0, r1);
 }
-// loose - loose -> loose
+// loose - loose -> loose (borrow: -2^64 = -eps; a second borrow only for near-zero wrapped results)
 GL_DEV u64 gl_sub(u64 a, u64 b) {
-  u64 d = a - b;
-  if (a < b) {
-    u64 t = d - GL_EPS;       // borrow: -2^64 = -eps
-    d = t > d ? t - GL_EPS : t;  // second borrow possible only for loose, near-zero results
-  }
-  return d;
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 m;\n\t"
+      "sub.cc.u32 %0, %2, %4;\n\tsubc.cc.u32 %1, %3, %5;\n\tsubc.u32 m, 0, 0;\n\t"  // m = eps if borrow
+      "sub.cc.u32 %0, %0, m;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+  return pack64(r0, r1);
 }
 
-// x = lo + 2^64 * hi (hi < 2^32)  ->  loose.   2^64 = eps.
-GL_DEV u64 gl_reduce96(u64 lo, u32 hi) {
-  u64 t = mul_wide(hi, GL_EPS);  // hi*eps < 2^64 - 2^33 + 1
-  u64 r = lo + t;
-  return r < lo ? r + GL_EPS : r;  // wrapped r <= lo - 2^33, cannot carry twice
+// w0 + w1*2^32 + w2*2^64 + w3*2^96  ->  loose.        2^64 = eps, 2^96 = -1:
+//   x = {w0,w1} - w3          (borrow  => - eps; the wrapped value is > eps, no second borrow)
+//   t = w2*eps = {-w2, w2 - (w2 != 0)}
+//   r = x + t                 (carry   => + eps; the wrapped value is < 2^64 - 2^33, no second carry)
+GL_DEV u64 gl_reduce128w(u32 w0, u32 w1, u32 w2, u32 w3) {
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 b, t0, t1, c, m;\n\t"
+      "sub.cc.u32 %0, %2, %5;\n\tsubc.cc.u32 %1, %3, 0;\n\tsubc.u32 b, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, b;\n\tsubc.u32 %1, %1, 0;\n\t"
+      "sub.cc.u32 t0, 0, %4;\n\tsubc.u32 t1, %4, 0;\n\t"
+      "add.cc.u32 %0, %0, t0;\n\taddc.cc.u32 %1, %1, t1;\n\taddc.u32 c, 0, 0;\n\t"
+      "sub.u32 m, 0, c;\n\t"
+      "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
+  return pack64(r0, r1);
 }
+GL_DEV u64 gl_reduce128(u64 lo, u64 hi) { return gl_reduce128w(lo32(lo), hi32(lo), lo32(hi), hi32(hi)); }
 
-// x = lo + 2^64 * hi (full 128 bit) -> loose.   hi = hh*2^32 + hl : 2^96 = -1, 2^64 = eps.
-GL_DEV u64 gl_reduce128(u64 lo, u64 hi) {
-  u32 hh = hi32(hi), hl = lo32(hi);
-  u64 t0 = lo - hh;
-  if (lo < hh) t0 -= GL_EPS;  // wrapped value >= 2^64 - 2^32 + 1 > eps: no second borrow
-  u64 t1 = mul_wide(hl, GL_EPS);
-  u64 r = t0 + t1;
-  return r < t0 ? r + GL_EPS : r;
-}
+// x = lo + 2^64 * hi (hi < 2^32)  ->  loose
+GL_DEV u64 gl_reduce96(u64 lo, u32 hi) { return gl_reduce128w(lo32(lo), hi32(lo), hi, 0u); }
 
-// full 64x64 -> 128 product from four 32x32 IMAD.WIDE
-GL_DEV void mul64x64(u64 a, u64 b, u64 &lo, u64 &hi) {
-  u32 a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
-  u64 t0 = mul_wide(a0, b0);
-  u64 t1 = mad_wide(a0, b1, (u64)hi32(t0));   // <= (2^32-1)^2 + 2^32-1 : no overflow
-  u64 t2 = mad_wide(a1, b0, (u64)lo32(t1));   // same bound
-  u64 t3 = mad_wide(a1, b1, (u64)hi32(t1));   // <= (2^32-1)^2 + 2(2^32-1) = 2^64-1 after next add
-  t3 += hi32(t2);
-  lo = pack64(lo32(t0), lo32(t2));
-  hi = t3;
-}
-
-// loose * loose -> loose
+// loose * loose -> loose: four IMAD.WIDE + two 3-word carry chains + the reduction above
 GL_DEV u64 gl_mul(u64 a, u64 b) {
-  u64 lo, hi;
-  mul64x64(a, b, lo, hi);
-  return gl_reduce128(lo, hi);
+  u32 w0, w1, w2, w3;
+  asm("{\n\t.reg .u64 p00, p01, p10, p11;\n\t.reg .u32 h00, l01, h01, l10, h10, l11, h11;\n\t"
+      "mul.wide.u32 p00, %4, %6;\n\tmul.wide.u32 p01, %4, %7;\n\t"
+      "mul.wide.u32 p10, %5, %6;\n\tmul.wide.u32 p11, %5, %7;\n\t"
+      "mov.b64 {%0, h00}, p00;\n\tmov.b64 {l01, h01}, p01;\n\t"
+      "mov.b64 {l10, h10}, p10;\n\tmov.b64 {l11, h11}, p11;\n\t"
+      "add.cc.u32 %1, h00, l01;\n\taddc.cc.u32 %2, h01, l11;\n\taddc.u32 %3, h11, 0;\n\t"
+      "add.cc.u32 %1, %1, l10;\n\taddc.cc.u32 %2, %2, h10;\n\taddc.u32 %3, %3, 0;\n\t}"
+      : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+  return gl_reduce128w(w0, w1, w2, w3);
 }
-GL_DEV u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+// loose^2 -> loose: three IMAD.WIDE (the cross product is added twice)
+GL_DEV u64 gl_sqr(u64 a) {
+  u32 w0, w1, w2, w3;
+  asm("{\n\t.reg .u64 p00, p01, p11;\n\t.reg .u32 h00, l01, h01, l11, h11;\n\t"
+      "mul.wide.u32 p00, %4, %4;\n\tmul.wide.u32 p01, %4, %5;\n\tmul.wide.u32 p11, %5, %5;\n\t"
+      "mov.b64 {%0, h00}, p00;\n\tmov.b64 {l01, h01}, p01;\n\tmov.b64 {l11, h11}, p11;\n\t"
+      "add.cc.u32 %1, h00, l01;\n\taddc.cc.u32 %2, h01, l11;\n\taddc.u32 %3, h11, 0;\n\t"
+      "add.cc.u32 %1, %1, l01;\n\taddc.cc.u32 %2, %2, h01;\n\taddc.u32 %3, %3, 0;\n\t}"
+      : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+      : "r"(lo32(a)), "r"(hi32(a)));
+  return gl_reduce128w(w0, w1, w2, w3);
+}
 
-// x^7: 4 multiplications (S-box of both permutations)
+// x^7: 2 squarings + 2 multiplications (S-box of both permutations)
 GL_DEV u64 gl_pow7(u64 x) {
   u64 x2 = gl_sqr(x);
   u64 x3 = gl_mul(x2, x);

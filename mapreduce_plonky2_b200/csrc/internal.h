@@ -17,6 +17,22 @@ typedef std::string Status;
 extern std::atomic<uint64_t> g_launches;
 inline void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Optional per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+// Disabled by default: a ProfScope is then two predictable branches.
+extern std::atomic<int> g_profile_on;
+void prof_record(const char *name, cudaStream_t st, bool begin);
+struct ProfScope {
+  const char *name;
+  cudaStream_t st;
+  bool on;
+  ProfScope(const char *n, cudaStream_t s) : name(n), st(s), on(g_profile_on.load(std::memory_order_relaxed) != 0) {
+    if (on) prof_record(name, st, true);
+  }
+  ~ProfScope() {
+    if (on) prof_record(name, st, false);
+  }
+};
+
 #define MP2_CUDA(expr)                                                                      \
   do {                                                                                      \
     cudaError_t _e = (expr);                                                                \

@@ -9,8 +9,14 @@
 // Digest layout (A.4): the digests array is split into 2^cap_height equal chunks, one per cap
 // subtree of 2^h leaves.  Inside a chunk, node m of layer i (layer 0 = leaf digests, i < h) lives
 // at digest index 2*(((m>>1) << (i+1)) + (1<<i) - 1) + (m&1).  The subtree roots form the cap.
+#include <cstdlib>
+
 #include "internal.h"
 #include "poseidon.cuh"
+
+#ifndef MP2_HASH_BLOCK
+#define MP2_HASH_BLOCK 128
+#endif
 
 namespace mp2 {
 
@@ -37,18 +43,19 @@ GL_DEV u64 *leaf_digest_ptr(size_t L, u32 h, u64 *digests, u64 *cap) {
 // ---- K4: leaf sponge.  One thread per leaf; rate 8, overwrite absorb (A.5). ---------------------
 // COLMAJOR: element (column c, leaf L) at in[c*stride + L]  -> loads coalesce across the warp.
 // !COLMAJOR: element at in[L*stride + c] (row-major user leaves, FRI layers).
-template <u32 KIND, bool COLMAJOR>
-__global__ void __launch_bounds__(128)
+template <u32 KIND, bool COLMAJOR, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 k_leaf_hash(const u64 *__restrict__ in, size_t stride, u32 ncols, size_t nleaves, u32 h,
             u64 *__restrict__ leaves_out, u64 *__restrict__ digests, u64 *__restrict__ cap) {
   size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (L >= nleaves) return;
+  const bool active = L < nleaves;  // inactive threads still walk the rounds (block-wide barriers)
+  if (!active) L = nleaves - 1;
   u64 st[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) st[i] = 0;
   const u64 *src = COLMAJOR ? in + L : in + L * stride;
   const size_t step = COLMAJOR ? stride : 1;
-  u64 *row = leaves_out ? leaves_out + L * (size_t)ncols : nullptr;
+  u64 *row = (leaves_out && active) ? leaves_out + L * (size_t)ncols : nullptr;
   if (ncols <= 4) {  // hash_or_noop: no permutation, zero padded
 #pragma unroll
     for (int j = 0; j < 4; j++)
@@ -70,15 +77,15 @@ k_leaf_hash(const u64 *__restrict__ in, size_t stride, u32 ncols, size_t nleaves
           st[j] = v[j];
           if (row) row[c0 + j] = gl_canon(v[j]);
         }
-      permute<KIND>(st);
+      permute<KIND, true>(st);
     }
   }
-  store_digest(leaf_digest_ptr(L, h, digests, cap), st);
+  if (active) store_digest(leaf_digest_ptr(L, h, digests, cap), st);
 }
 
 // ragged leaves: leaf L = flat[off[L] .. off[L+1])
 template <u32 KIND>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MP2_HASH_BLOCK)
 k_leaf_hash_ragged(const u64 *__restrict__ flat, const u64 *__restrict__ off, size_t nleaves, u32 h,
                    u64 *__restrict__ digests, u64 *__restrict__ cap) {
   size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,10 +113,11 @@ k_leaf_hash_ragged(const u64 *__restrict__ flat, const u64 *__restrict__ off, si
 
 // ---- K5: one Merkle layer.  Thread t -> node m of layer `layer` (1..h) of subtree sub. ---------
 template <u32 KIND>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MP2_HASH_BLOCK)
 k_merkle_layer(u64 *__restrict__ digests, u64 *__restrict__ cap, u32 h, u32 layer, size_t nnodes) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nnodes) return;
+  const bool active = t < nnodes;
+  if (!active) t = nnodes - 1;
   u32 width_log = h - layer;  // nodes of this layer per subtree = 2^width_log
   size_t sub = t >> width_log, m = t & (((size_t)1 << width_log) - 1);
   size_t per = 2 * (((size_t)1 << h) - 1);
@@ -118,16 +126,17 @@ k_merkle_layer(u64 *__restrict__ digests, u64 *__restrict__ cap, u32 h, u32 laye
   const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(base + 4 * node_slot(layer - 1, 2 * m));
   ulonglong2 c0 = ch[0], c1 = ch[1], c2 = ch[2], c3 = ch[3];
   u64 st[12] = {c0.x, c0.y, c1.x, c1.y, c2.x, c2.y, c3.x, c3.y, 0, 0, 0, 0};
-  permute<KIND>(st);
+  permute<KIND, true>(st);
   u64 *dst = layer == h ? cap + 4 * sub : base + 4 * node_slot(layer, m);
-  store_digest(dst, st);
+  if (active) store_digest(dst, st);
 }
 
 template <u32 KIND>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MP2_HASH_BLOCK)
 k_two_to_one(const u64 *__restrict__ a, const u64 *__restrict__ b, size_t count, u64 *__restrict__ out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
+  const bool active = t < count;
+  if (!active) t = count - 1;
   u64 st[12];
 #pragma unroll
   for (int i = 0; i < 4; i++) {
@@ -135,28 +144,32 @@ k_two_to_one(const u64 *__restrict__ a, const u64 *__restrict__ b, size_t count,
     st[4 + i] = b[4 * t + i];
     st[8 + i] = 0;
   }
-  permute<KIND>(st);
-  store_digest(out + 4 * t, st);
+  permute<KIND, true>(st);
+  if (active) store_digest(out + 4 * t, st);
 }
 
 template <u32 KIND>
-__global__ void __launch_bounds__(128) k_permute(u64 *__restrict__ states, size_t count) {
+__global__ void __launch_bounds__(MP2_HASH_BLOCK) k_permute(u64 *__restrict__ states, size_t count) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
+  const bool active = t < count;
+  if (!active) t = count - 1;
   u64 st[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) st[i] = states[12 * t + i];
-  permute<KIND>(st);
+  permute<KIND, true>(st);
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < 12; i++) states[12 * t + i] = gl_canon(st[i]);
+    for (int i = 0; i < 12; i++) states[12 * t + i] = gl_canon(st[i]);
+  }
 }
 
 // hash_no_pad over row-major inputs (never the no-op branch); len == 0 -> zeros
 template <u32 KIND>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MP2_HASH_BLOCK)
 k_hash_no_pad(const u64 *__restrict__ in, size_t count, size_t len, u64 *__restrict__ out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
+  const bool active = t < count;
+  if (!active) t = count - 1;
   u64 st[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) st[i] = 0;
@@ -166,9 +179,9 @@ k_hash_no_pad(const u64 *__restrict__ in, size_t count, size_t len, u64 *__restr
 #pragma unroll
     for (int j = 0; j < 8; j++)
       if ((size_t)j < m) st[j] = src[c0 + j];
-    permute<KIND>(st);
+    permute<KIND, true>(st);
   }
-  store_digest(out + 4 * t, st);
+  if (active) store_digest(out + 4 * t, st);
 }
 
 // get_lde_values: out[r][c] = leaf row row_idx[r]
@@ -184,11 +197,92 @@ __global__ void k_gather_rows(const u64 *__restrict__ rowmajor, const u64 *__res
 
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
+
+// ---- leaf-hash launch shape ----------------------------------------------------------------------
+// A leaf is an indivisible unit (a sequential sponge of ceil(ncols/8) permutations), so with T
+// resident threads per SM the kernel takes ceil(nleaves / (nSM*T)) "waves".  2^17 leaves on 148 SMs
+// are 885.6 leaves per SM: T = 640 (what the register budget allows) needs two waves at 69 %
+// efficiency, T = 448 needs two at 99 %.  We therefore pick the block size and cap the resident CTAs
+// per SM (by asking for dynamic shared memory we never touch) to minimise ceil(waves)*T.
+struct HashLaunch {
+  int block;        // threads per CTA
+  int ctas_per_sm;  // resident CTAs per SM we want
+  size_t smem;      // dynamic shared memory that enforces it (0 = no cap)
+};
+
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+template <typename K>
+static Status plan_hash_launch(K kernel, int block, size_t nthreads, int max_regs_ctas, HashLaunch *out) {
+  int dev = 0, nsm = 0;
+  MP2_CUDA(cudaGetDevice(&dev));
+  MP2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  int kmax = 0;
+  MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kmax, kernel, block, 0));
+  if (kmax < 1) return "leaf-hash kernel cannot be resident";
+  if (max_regs_ctas > 0 && kmax > max_regs_ctas) kmax = max_regs_ctas;
+  int forced = env_int("MP2_HASH_CTAS", 0);
+  int best_k = kmax;
+  if (forced > 0) {
+    best_k = forced < kmax ? forced : kmax;
+  } else {
+    // fewer than ~12 warps per SM no longer hides the arithmetic latency: do not go below that
+    int kmin = (384 + block - 1) / block;
+    if (kmin > kmax) kmin = kmax;
+    double best_cost = 1e300;
+    for (int k = kmax; k >= kmin; k--) {
+      double per_wave = (double)nsm * k * block;
+      double waves = (double)((nthreads + (size_t)per_wave - 1) / (size_t)per_wave);
+      double cost = waves * k * block;  // ~ time, if an SM's throughput does not depend on k
+      if (cost < best_cost * 0.97) {    // prefer more resident warps unless the gain is real
+        best_cost = cost;
+        best_k = k;
+      }
+    }
+  }
+  out->block = block;
+  out->ctas_per_sm = best_k;
+  out->smem = 0;
+  if (best_k < kmax) {
+    size_t per = (size_t)(228 * 1024) / best_k - 1024;  // each CTA also reserves 1 KB
+    per &= ~(size_t)127;
+    if (per > 227 * 1024) per = 227 * 1024;
+    MP2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per));
+    MP2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    out->smem = per;
+  }
+  return "";
+}
+
+template <u32 KIND, bool COLMAJOR, int BLOCK>
+static Status launch_leaf_hash_b(const u64 *in, size_t stride, u32 ncols, size_t nleaves, u32 h, u64 *leaves_out,
+                                 u64 *digests, u64 *cap, cudaStream_t st) {
+  HashLaunch hl;
+  MP2_TRY(plan_hash_launch(k_leaf_hash<KIND, COLMAJOR, BLOCK>, BLOCK, nleaves, 0, &hl));
+  { ProfScope _p("k_leaf_hash", st); k_leaf_hash<KIND, COLMAJOR, BLOCK><<<grid_for(nleaves, BLOCK), BLOCK, hl.smem, st>>>(in, stride, ncols, nleaves, h,
+                                                                                      leaves_out, digests, cap); }
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+
+template <u32 KIND, bool COLMAJOR>
+static Status launch_leaf_hash(const u64 *in, size_t stride, u32 ncols, size_t nleaves, u32 h, u64 *leaves_out,
+                               u64 *digests, u64 *cap, cudaStream_t st) {
+  switch (env_int("MP2_HASH_BLOCK", MP2_HASH_BLOCK)) {
+    case 64: return launch_leaf_hash_b<KIND, COLMAJOR, 64>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
+    case 256: return launch_leaf_hash_b<KIND, COLMAJOR, 256>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
+    default: return launch_leaf_hash_b<KIND, COLMAJOR, 128>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
+  }
+}
+
 template <u32 KIND>
 static Status build_levels(u64 *digests, u64 *cap, u32 h, u32 cap_height, cudaStream_t st) {
   for (u32 layer = 1; layer <= h; layer++) {
     size_t nnodes = ((size_t)1 << (h - layer)) << cap_height;
-    k_merkle_layer<KIND><<<grid_for(nnodes, 128), 128, 0, st>>>(digests, cap, h, layer, nnodes);
+    { ProfScope _p("k_merkle_layer", st); k_merkle_layer<KIND><<<grid_for(nnodes, MP2_HASH_BLOCK), MP2_HASH_BLOCK, 0, st>>>(digests, cap, h, layer, nnodes); }
     MP2_LAUNCH_CHECK();
   }
   return "";
@@ -209,12 +303,10 @@ Status merkle_colmajor(const u64 *lde, size_t lde_stride, size_t ncols, size_t n
   u32 h;
   MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
   if (ncols == 0 || ncols > 0xFFFFFFFFu) return "bad number of columns";
-  unsigned g = grid_for(nleaves, 128);
   if (hash_kind == MP2_HASH_POSEIDON2)
-    k_leaf_hash<MP2_HASH_POSEIDON2, true><<<g, 128, 0, st>>>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap);
+    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON2, true>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap, st)));
   else
-    k_leaf_hash<MP2_HASH_POSEIDON, true><<<g, 128, 0, st>>>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap);
-  MP2_LAUNCH_CHECK();
+    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON, true>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap, st)));
   return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
                                          : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
 }
@@ -224,12 +316,10 @@ Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 c
   u32 h;
   MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
   if (leaf_len > 0xFFFFFFFFu) return "leaf too long";
-  unsigned g = grid_for(nleaves, 128);
   if (hash_kind == MP2_HASH_POSEIDON2)
-    k_leaf_hash<MP2_HASH_POSEIDON2, false><<<g, 128, 0, st>>>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap);
+    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON2, false>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap, st)));
   else
-    k_leaf_hash<MP2_HASH_POSEIDON, false><<<g, 128, 0, st>>>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap);
-  MP2_LAUNCH_CHECK();
+    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON, false>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap, st)));
   return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
                                          : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
 }
@@ -238,11 +328,11 @@ Status merkle_ragged(const u64 *flat, const u64 *offsets, size_t nleaves, u32 ca
                      u64 *digests, u64 *cap, cudaStream_t st) {
   u32 h;
   MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
-  unsigned g = grid_for(nleaves, 128);
+  unsigned g = grid_for(nleaves, MP2_HASH_BLOCK);
   if (hash_kind == MP2_HASH_POSEIDON2)
-    k_leaf_hash_ragged<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(flat, offsets, nleaves, h, digests, cap);
+    { ProfScope _p("k_leaf_hash_ragged", st); k_leaf_hash_ragged<MP2_HASH_POSEIDON2><<<g, MP2_HASH_BLOCK, 0, st>>>(flat, offsets, nleaves, h, digests, cap); }
   else
-    k_leaf_hash_ragged<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(flat, offsets, nleaves, h, digests, cap);
+    { ProfScope _p("k_leaf_hash_ragged", st); k_leaf_hash_ragged<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(flat, offsets, nleaves, h, digests, cap); }
   MP2_LAUNCH_CHECK();
   return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
                                          : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
@@ -252,9 +342,9 @@ Status hash_no_pad_batch(const u64 *inputs, size_t count, size_t input_len, u32 
                          cudaStream_t st) {
   if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
   if (count == 0) return "";
-  unsigned g = grid_for(count, 128);
-  if (hash_kind == MP2_HASH_POSEIDON2) k_hash_no_pad<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(inputs, count, input_len, out);
-  else k_hash_no_pad<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(inputs, count, input_len, out);
+  unsigned g = grid_for(count, MP2_HASH_BLOCK);
+  if (hash_kind == MP2_HASH_POSEIDON2) { ProfScope _p("k_hash_no_pad", st); k_hash_no_pad<MP2_HASH_POSEIDON2><<<g, MP2_HASH_BLOCK, 0, st>>>(inputs, count, input_len, out); }
+  else { ProfScope _p("k_hash_no_pad", st); k_hash_no_pad<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(inputs, count, input_len, out); }
   MP2_LAUNCH_CHECK();
   return "";
 }
@@ -262,9 +352,9 @@ Status hash_no_pad_batch(const u64 *inputs, size_t count, size_t input_len, u32 
 Status two_to_one_batch(const u64 *a, const u64 *b, size_t count, u32 hash_kind, u64 *out, cudaStream_t st) {
   if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
   if (count == 0) return "";
-  unsigned g = grid_for(count, 128);
-  if (hash_kind == MP2_HASH_POSEIDON2) k_two_to_one<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(a, b, count, out);
-  else k_two_to_one<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(a, b, count, out);
+  unsigned g = grid_for(count, MP2_HASH_BLOCK);
+  if (hash_kind == MP2_HASH_POSEIDON2) { ProfScope _p("k_two_to_one", st); k_two_to_one<MP2_HASH_POSEIDON2><<<g, MP2_HASH_BLOCK, 0, st>>>(a, b, count, out); }
+  else { ProfScope _p("k_two_to_one", st); k_two_to_one<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(a, b, count, out); }
   MP2_LAUNCH_CHECK();
   return "";
 }
@@ -272,9 +362,9 @@ Status two_to_one_batch(const u64 *a, const u64 *b, size_t count, u32 hash_kind,
 Status permute_batch(u64 *states, size_t count, u32 hash_kind, cudaStream_t st) {
   if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
   if (count == 0) return "";
-  unsigned g = grid_for(count, 128);
-  if (hash_kind == MP2_HASH_POSEIDON2) k_permute<MP2_HASH_POSEIDON2><<<g, 128, 0, st>>>(states, count);
-  else k_permute<MP2_HASH_POSEIDON><<<g, 128, 0, st>>>(states, count);
+  unsigned g = grid_for(count, MP2_HASH_BLOCK);
+  if (hash_kind == MP2_HASH_POSEIDON2) { ProfScope _p("k_permute", st); k_permute<MP2_HASH_POSEIDON2><<<g, MP2_HASH_BLOCK, 0, st>>>(states, count); }
+  else { ProfScope _p("k_permute", st); k_permute<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(states, count); }
   MP2_LAUNCH_CHECK();
   return "";
 }
@@ -282,7 +372,7 @@ Status permute_batch(u64 *states, size_t count, u32 hash_kind, cudaStream_t st) 
 Status gather_rows(const u64 *rowmajor, const u64 *colmajor, size_t stride, size_t ncols, const u64 *row_idx,
                    size_t nrows, u64 *out, cudaStream_t st) {
   if (nrows == 0) return "";
-  k_gather_rows<<<grid_for(nrows * ncols, 256), 256, 0, st>>>(rowmajor, colmajor, stride, (u32)ncols, row_idx, nrows, out);
+  { ProfScope _p("k_gather_rows", st); k_gather_rows<<<grid_for(nrows * ncols, 256), 256, 0, st>>>(rowmajor, colmajor, stride, (u32)ncols, row_idx, nrows, out); }
   MP2_LAUNCH_CHECK();
   return "";
 }

@@ -209,7 +209,7 @@ Status ntt_canonicalize(const u64 *in, size_t in_stride, u64 *out, size_t out_st
                         cudaStream_t st) {
   size_t total = ncols * n;
   if (!total) return "";
-  k_canonicalize<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, in_stride, out, out_stride, n, total);
+  { ProfScope _p("k_canonicalize", st); k_canonicalize<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, in_stride, out, out_stride, n, total); }
   MP2_LAUNCH_CHECK();
   return "";
 }
@@ -238,8 +238,8 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_intt_single, smem));
     unsigned grid = (unsigned)((ncols + ((size_t)1 << lines_log) - 1) >> lines_log);
-    k_intt_single<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, coeffs, out_stride, (u32)ncols,
-                                                              n_log, lines_log, roots, n_inv);
+    { ProfScope _p("k_intt_single", st); k_intt_single<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, coeffs, out_stride, (u32)ncols,
+                                                              n_log, lines_log, roots, n_inv); }
     MP2_LAUNCH_CHECK();
     return "";
   }
@@ -256,7 +256,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass1, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.b) >> tp.lines_log), (unsigned)ncols, 1);
-    k_pass1<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, tmp, n, none, tp, roots, nullptr);
+    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, tmp, n, none, tp, roots, nullptr); }
     MP2_LAUNCH_CHECK();
   }
   {
@@ -267,7 +267,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, 1);
-    k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, tp2, roots);
+    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, tp2, roots); }
     MP2_LAUNCH_CHECK();
   }
   MP2_CUDA(cudaFreeAsync(tmp, st));
@@ -294,8 +294,8 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_lde_single, smem));
     dim3 grid((unsigned)((ncols + ((size_t)1 << lines_log) - 1) >> lines_log), cosets, 1);
-    k_lde_single<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, map, (u32)ncols, n_log,
-                                                             lines_log, rate_bits, roots, pow7);
+    { ProfScope _p("k_lde_single", st); k_lde_single<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, map, (u32)ncols, n_log,
+                                                             lines_log, rate_bits, roots, pow7); }
     MP2_LAUNCH_CHECK();
     return "";
   }
@@ -309,7 +309,7 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass1, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.b) >> tp.lines_log), (unsigned)ncols, cosets);
-    k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, 0, map, tp, roots, pow7);
+    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, 0, map, tp, roots, pow7); }
     MP2_LAUNCH_CHECK();
   }
   {
@@ -320,7 +320,7 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, cosets);
-    k_pass2<<<grid, threads_for(tile_log), smem, st>>>(lde, 0, lde, 0, map, tp2, roots);
+    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(lde, 0, lde, 0, map, tp2, roots); }
     MP2_LAUNCH_CHECK();
   }
   return "";

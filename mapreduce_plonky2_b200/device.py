@@ -96,3 +96,34 @@ def merkle_rowmajor(leaves: torch.Tensor, cap_height: int, hash_kind: int, diges
     nleaves, leaf_len = leaves.shape
     _lib.call("mp2gpu_dev_merkle_rowmajor", _chk(leaves, "leaves"), nleaves, leaf_len, cap_height, hash_kind,
               _chk(digests, "digests"), _chk(cap, "cap"), _stream_ptr())
+
+
+def canonicalize(src: torch.Tensor, dst: torch.Tensor) -> None:
+    _lib.call("mp2gpu_dev_canonicalize", _chk(src, "src"), _chk(dst, "dst"), src.numel(), _stream_ptr())
+
+
+# ---- measurement hooks ---------------------------------------------------------------------------
+def profile_enable(on: bool) -> None:
+    _lib.call("mp2gpu_profile_enable", 1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{kernel_name: (launches, total_ms)} since the last report (synchronises the device)."""
+    import ctypes as C
+
+    buf = C.create_string_buffer(1 << 16)
+    _lib.call("mp2gpu_profile_report", buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        out[name] = (int(cnt), float(ms))
+    return out
+
+
+def int_pipe_peak() -> dict:
+    """Live IMAD issue-rate probe: the Poseidon roofline denominator."""
+    import ctypes as C
+
+    a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+    _lib.call("mp2gpu_debug_int_pipe_peak", C.byref(a), C.byref(b), C.byref(c))
+    return {"imad_per_clk_per_sm": a.value, "sm_clock_mhz": b.value, "t_imad_per_s": c.value}

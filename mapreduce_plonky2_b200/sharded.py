@@ -1,0 +1,128 @@
+"""One wide batch across the GPUs of a node:
+
+    columns sharded -> per-rank iNTT + coset LDE -> ONE exchange (all-to-all: column shards become
+    row shards aligned with the cap subtrees) -> per-rank leaf hashing + subtrees -> all-gather of the
+    cap (<= 16 x 32 B).
+
+Rank g of G owns columns [g*c/G, (g+1)*c/G) before the exchange and leaves [g*N/G, (g+1)*N/G) after
+it.  Leaf L is LDE row bitrev(L), and the LDE kernel already writes its output leaf-ordered and
+blocked by destination rank (``shard_log``), so the all-to-all payload for rank s is one contiguous
+block and what arrives is directly the column-major input of the leaf-hash kernel: no pack/unpack
+kernels on either side.  A rank's digests / cap entries are contiguous slices of the global
+``MerkleTree.digests`` / ``cap`` (plonky2 splits digests into 2^cap_height per-subtree chunks).
+
+``torch.distributed`` is plumbing only (NCCL over NVLink on GPUs; gloo in the CPU tests); the
+arithmetic is delegated to an *engine*: :class:`CudaEngine` (libmp2gpu.so kernels) in production,
+an oracle-backed stand-in inside ``tests/`` to exercise this file's index logic without a GPU.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+class CudaEngine:
+    """Stages implemented by the hand-written kernels (device pointers on the current CUDA stream)."""
+
+    def __init__(self):
+        from . import device
+
+        self.d = device
+        device.bind_current_device()
+
+    def empty(self, shape):
+        return torch.empty(shape, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def intt(self, values, coeffs):
+        self.d.intt(values, coeffs)
+
+    def canonical_copy(self, src, dst):
+        self.d.canonicalize(src, dst)
+
+    def coset_lde(self, coeffs, lde, rate_bits, shard_log):
+        self.d.coset_lde(coeffs, lde, rate_bits, shard_log)
+
+    def merkle_colmajor(self, lde, cap_height, hash_kind, leaves, digests, cap):
+        self.d.merkle_colmajor(lde, cap_height, hash_kind, leaves, digests, cap)
+
+
+@dataclass
+class ShardedBatch:
+    """This rank's part of the PolynomialBatch."""
+    coeffs: torch.Tensor            # (c/G, n)   coefficients of the local columns
+    leaves: Optional[torch.Tensor]  # (N/G, c)   rows [g*N/G, (g+1)*N/G) of MerkleTree.leaves
+    digests: torch.Tensor           # slice [g*D/G, (g+1)*D/G) of MerkleTree.digests, D = 2*(N - 2^cap)
+    cap: torch.Tensor               # (2^cap, 4) the whole cap (all-gathered)
+    rank: int
+    world: int
+
+
+def _log2(x: int) -> int:
+    l = x.bit_length() - 1
+    if x <= 0 or (1 << l) != x:
+        raise ValueError("%d is not a power of two" % x)
+    return l
+
+
+def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, cap_height: int, hash_kind: int,
+                   engine, group=None, from_coeffs: bool = False, want_leaves: bool = True,
+                   scratch: Optional[dict] = None) -> ShardedBatch:
+    """PolynomialBatch::from_values / from_coeffs of one (ncols_total x n) batch over ``group``.
+
+    ``cols_local``: this rank's columns, shape (ncols_total / G, n).  Requirements: G is a power of two,
+    G divides ncols_total, and G <= 2^cap_height (every rank owns whole cap subtrees).
+    ``scratch`` may hold reusable buffers (keys: coeffs, send, recv, leaves, digests, cap_local, cap)."""
+    G = dist.get_world_size(group)
+    g = dist.get_rank(group)
+    glog = _log2(G)
+    c_loc, n = cols_local.shape
+    n_log = _log2(n)
+    if c_loc * G != ncols_total:
+        raise ValueError("columns must be split evenly: %d local x %d ranks != %d" % (c_loc, G, ncols_total))
+    if glog > cap_height:
+        raise ValueError("world size %d exceeds the number of cap subtrees 2^%d" % (G, cap_height))
+    N = n << rate_bits
+    n_loc = N >> glog                      # leaves per rank
+    ncap_loc = (1 << cap_height) >> glog   # cap entries per rank
+    ndig_loc = 2 * (n_loc - ncap_loc)      # digests per rank
+    sc = scratch if scratch is not None else {}
+
+    def buf(name, shape):
+        t = sc.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = engine.empty(shape)
+            sc[name] = t
+        return t
+
+    # 1. per-column work on the local column shard
+    coeffs = buf("coeffs", (c_loc, n))
+    if from_coeffs:
+        engine.canonical_copy(cols_local, coeffs)
+    else:
+        engine.intt(cols_local, coeffs)
+    # 2. LDE written leaf-ordered and blocked by destination rank: send[s] = (c_loc, n_loc) block for rank s
+    send = buf("send", (G, c_loc, n_loc))
+    engine.coset_lde(coeffs, send, rate_bits, glog)
+    # 3. the one exchange of the path
+    if G > 1:
+        recv = buf("recv", (G, c_loc, n_loc))
+        dist.all_to_all_single(recv, send, group=group)
+    else:
+        recv = send
+    # recv[s][j] is column s*c_loc + j restricted to my leaves: a (ncols_total, n_loc) column-major LDE
+    lde_rows = recv.view(ncols_total, n_loc)
+    # 4. my leaves, my subtrees
+    leaves = buf("leaves", (n_loc, ncols_total)) if want_leaves else None
+    digests = buf("digests", (max(ndig_loc, 1), 4))
+    cap_local = buf("cap_local", (ncap_loc, 4))
+    engine.merkle_colmajor(lde_rows, cap_height - glog, hash_kind, leaves, digests, cap_local)
+    # 5. everyone gets the whole cap
+    cap = buf("cap", (1 << cap_height, 4))
+    if G > 1:
+        dist.all_gather_into_tensor(cap, cap_local, group=group)
+    else:
+        cap.copy_(cap_local)
+    return ShardedBatch(coeffs, leaves, digests[:ndig_loc], cap, g, G)

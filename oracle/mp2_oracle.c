@@ -135,35 +135,54 @@ static void pos_init(void) {
 static const uint64_t POS_CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 static const uint64_t POS_DIAG[12] = {8, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-static inline uint64_t sbox7(uint64_t x) {
-  uint64_t x2 = gl_mul(x, x), x4 = gl_mul(x2, x2), x3 = gl_mul(x, x2);
-  return gl_mul(x3, x4);
+/* loose arithmetic (values in [0,2^64), canonicalised once per permutation) keeps the CPU baseline
+ * honest: this is the same lazy-reduction discipline plonky2's scalar code uses */
+static inline uint64_t gl_reduce128_loose(u128 x) {
+  uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
+  uint64_t hh = hi >> 32, hl = hi & GL_EPS;
+  uint64_t t0 = lo - hh;
+  if (lo < hh) t0 -= GL_EPS;
+  uint64_t t1 = hl * GL_EPS;
+  uint64_t r = t0 + t1;
+  if (r < t0) r += GL_EPS;
+  return r;
 }
+static inline uint64_t gl_mul_loose(uint64_t a, uint64_t b) { return gl_reduce128_loose((u128)a * b); }
+static inline uint64_t sbox7_loose(uint64_t x) {
+  uint64_t x2 = gl_mul_loose(x, x), x4 = gl_mul_loose(x2, x2), x3 = gl_mul_loose(x, x2);
+  return gl_mul_loose(x3, x4);
+}
+static inline uint64_t sbox7(uint64_t x) { return orc_gl_canon(sbox7_loose(x)); }
 
-/* out[r] = sum_i state[(i+r)%12] * CIRC[i] + state[r] * DIAG[r]   (mds_row_shf) */
-static inline void pos_mds(uint64_t s[12]) {
-  uint64_t o[12];
+/* out[r] = sum_i state[(i+r)%12] * CIRC[i] + state[r] * DIAG[r] + rc[r]   (mds_row_shf) */
+static inline void pos_mds_rc(uint64_t s[12], const uint64_t *rc) {
+  uint64_t d[24], o[12];
+  memcpy(d, s, 96);
+  memcpy(d + 12, s, 96);
   for (int r = 0; r < 12; r++) {
-    u128 acc = (u128)s[r] * POS_DIAG[r];
-    for (int i = 0; i < 12; i++) acc += (u128)s[(i + r) % 12] * POS_CIRC[i];
-    o[r] = gl_reduce128(acc);
+    u128 acc = (u128)rc[r] + (u128)s[r] * POS_DIAG[r];
+    for (int i = 0; i < 12; i++) acc += (u128)d[i + r] * POS_CIRC[i];
+    o[r] = gl_reduce128_loose(acc);
   }
   memcpy(s, o, sizeof o);
 }
 
+static const uint64_t POS_ZERO_RC[12] = {0};
+
 void orc_poseidon_permute(uint64_t s[12]) {
   pos_init();
-  for (int i = 0; i < 12; i++) s[i] = orc_gl_canon(s[i]);
-  int rc = 0;
+  /* round r: +RC[r], S-box, MDS.  The constants of round r+1 are added right after the MDS of
+   * round r (same values, fewer passes over the state). */
+  for (int i = 0; i < 12; i++) s[i] = gl_add(orc_gl_canon(s[i]), POS_RC[i]);
   for (int round = 0; round < 30; round++) {
-    for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], POS_RC[rc++]);
     if (round < 4 || round >= 26) {
-      for (int i = 0; i < 12; i++) s[i] = sbox7(s[i]);
+      for (int i = 0; i < 12; i++) s[i] = sbox7_loose(s[i]);
     } else {
-      s[0] = sbox7(s[0]);
+      s[0] = sbox7_loose(s[0]);
     }
-    pos_mds(s);
+    pos_mds_rc(s, round < 29 ? POS_RC + 12 * (round + 1) : POS_ZERO_RC);
   }
+  for (int i = 0; i < 12; i++) s[i] = orc_gl_canon(s[i]);
 }
 
 /* ------------------------------------------------------------------------- */
