@@ -74,8 +74,9 @@ inline u64 h_root_of_unity(u32 log_n) {
 // ---- device tables, cached per device (tables.cu) ----
 // W[m] = w_T^m for m < T = 2^log_t (T >= 1)
 Status table_roots(u32 log_t, cudaStream_t st, const u64 **out);
-// pow7[j] = 7^j for j < 2^log_n
-Status table_shift_powers(u32 log_n, cudaStream_t st, const u64 **out);
+// scale[(k << log_n) + j] = (7 * w_N^k)^j for k < 2^rate_bits, j < 2^log_n, N = 2^(log_n + rate_bits):
+// the coset pre-scaling of PolynomialCoeffs::coset_fft (shift = MULTIPLICATIVE_GROUP_GENERATOR = 7)
+Status table_coset_scale(u32 log_n, u32 rate_bits, cudaStream_t st, const u64 **out);
 
 // ---- transforms (ntt.cu) ----
 Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_stride, size_t ncols,

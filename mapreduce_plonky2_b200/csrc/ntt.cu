@@ -5,17 +5,25 @@
 // folds plonky2_util::{transpose, reverse_index_bits_in_place}'s row permutation into the transform:
 //
 //   * the LDE on the coset 7*<w_N>, N = n*2^r, is computed as 2^r independent size-n transforms
-//     (coset k: coefficients scaled by (7*w_N^k)^j) -- the zero-padded top r stages never run;
+//     (coset k: coefficients scaled by (7*w_N^k)^j, a precomputed table) -- the zero-padded top r
+//     stages never run;
 //   * each size-n transform is a decimation-in-frequency network (natural in, bit-reversed out), and
 //     leaf index L = (bitrev_r(k) << log n) | bitrev_n(m) is exactly the position the value
 //     P(7*w_N^(k + 2^r m)) has in plonky2's bit-reversed leaf order -- so the network's raw output,
 //     written to block bitrev_r(k), IS the leaf order: no separate bit-reversal pass exists;
 //   * output is column-major over leaves (column c contiguous), which is what the leaf-hash kernel
-//     wants for coalesced loads; the row-major `leaves` copy is produced by that kernel.
+//     wants for coalesced loads; the row-major `leaves` copy is produced by that kernel;
+//   * the inverse transform is the forward one with the output index reversed (coeffs[i] =
+//     fft[(n-i)%n] / n, as plonky2's ifft does), so only forward root tables exist.
 //
-// n <= 2^14 : one pass, the whole line lives in shared memory (128 KB at 2^14).
-// n >  2^14 : two passes (n = n1*n2, four-step), each pass a shared-memory transform on a tile of
-//             adjacent lines so that every global access is a >= 128-byte run.
+// The network runs radix-8 passes held in registers: a pass is an 8-point DFT whose internal twiddles
+// are the 8th roots of unity -- in Goldilocks w_8 = -2^24, w_4 = 2^48 (2^96 = -1), i.e. shifts, no
+// multiplier -- followed by ONE general twiddle multiplication per element.  14 stages = 5 shared
+// memory round trips and ~4.4 general multiplications per element instead of 14 and 7.
+//
+// n <= 2^14 : one pass over global memory, the whole line lives in shared memory (128 KB at 2^14).
+// n >  2^14 : two passes (n = n1*n2, four-step), each a shared-memory transform on a tile of adjacent
+//             lines so that every global access is a >= 64-byte run.
 #include "internal.h"
 #include "gl.cuh"
 
@@ -32,78 +40,162 @@ struct LdeMap {  // (column c, leaf L) -> offset in the leaf-ordered, column-maj
   }
 };
 
-// W[m] = w_T^m, T = 2^log_t.  Twiddle of stage `stage` (butterfly span 2^stage), index t:
-// w_{2^(stage+1)}^t = W[t << (log_t - stage - 1)];  the inverse transform uses W[T - idx].
-struct Roots {
-  const u64 *W;
-  u32 log_t;
-  GL_DEV u64 get(size_t idx, bool inverse) const {
-    size_t mask = ((size_t)1 << log_t) - 1;
-    idx &= mask;
-    if (inverse) idx = (((size_t)1 << log_t) - idx) & mask;
-    return W[idx];
-  }
+// ---- multiplications by the powers of two that are roots of unity ---------------------------------
+// x * 2^24: an 88-bit value {w0, w1, w2}
+GL_DEV u64 gl_mul_2_24(u64 x) {
+  u32 x0 = lo32(x), x1 = hi32(x);
+  return gl_reduce128w(x0 << 24, __funnelshift_l(x0, x1, 24), x1 >> 8, 0u);
+}
+// x * 2^48: a 112-bit value {0, w1, w2, w3}
+GL_DEV u64 gl_mul_2_48(u64 x) {
+  u32 x0 = lo32(x), x1 = hi32(x);
+  return gl_reduce128w(0u, x0 << 16, __funnelshift_l(x0, x1, 16), x1 >> 16);
+}
+// x * 2^72 = w2*2^64 + w3*2^96 + w4*2^128 with {w2,w3,w4} = x << 8;  2^64 = eps, 2^96 = -1,
+// 2^128 = -2^32:   r = w2*eps - {w3, w4}   (a borrow is folded as -eps; the wrapped value is huge)
+GL_DEV u64 gl_mul_2_72(u64 x) {
+  u32 x0 = lo32(x), x1 = hi32(x);
+  u32 w2 = x0 << 8, w3 = __funnelshift_l(x0, x1, 8), w4 = x1 >> 24;
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 t0, t1, m;\n\t"
+      "sub.cc.u32 t0, 0, %2;\n\tsubc.u32 t1, %2, 0;\n\t"                       // {t0,t1} = w2*eps
+      "sub.cc.u32 %0, t0, %3;\n\tsubc.cc.u32 %1, t1, %4;\n\tsubc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(w2), "r"(w3), "r"(w4));
+  return pack64(r0, r1);
+}
+
+// ---- small DFTs with shift twiddles; output position j holds frequency bitrev(j) -------------------
+GL_DEV void dft2(u64 (&x)[2]) {
+  u64 a = gl_add(x[0], x[1]), b = gl_sub(x[0], x[1]);
+  x[0] = a;
+  x[1] = b;
+}
+GL_DEV void dft4(u64 (&x)[4]) {  // w_4 = 2^48
+  u64 a0 = gl_add(x[0], x[2]), a1 = gl_add(x[1], x[3]);
+  u64 b0 = gl_sub(x[0], x[2]), b1 = gl_mul_2_48(gl_sub(x[1], x[3]));
+  x[0] = gl_add(a0, a1);
+  x[1] = gl_sub(a0, a1);
+  x[2] = gl_add(b0, b1);
+  x[3] = gl_sub(b0, b1);
+}
+GL_DEV void dft8(u64 (&x)[8]) {  // w_8 = -2^24, w_8^2 = 2^48, w_8^3 = -2^72
+  u64 a0 = gl_add(x[0], x[4]), a1 = gl_add(x[1], x[5]), a2 = gl_add(x[2], x[6]), a3 = gl_add(x[3], x[7]);
+  u64 b0 = gl_sub(x[0], x[4]);
+  u64 b1 = gl_mul_2_24(gl_sub(x[5], x[1]));
+  u64 b2 = gl_mul_2_48(gl_sub(x[2], x[6]));
+  u64 b3 = gl_mul_2_72(gl_sub(x[7], x[3]));
+  u64 c0 = gl_add(a0, a2), c1 = gl_add(a1, a3), d0 = gl_sub(a0, a2), d1 = gl_mul_2_48(gl_sub(a1, a3));
+  u64 e0 = gl_add(b0, b2), e1 = gl_add(b1, b3), f0 = gl_sub(b0, b2), f1 = gl_mul_2_48(gl_sub(b1, b3));
+  x[0] = gl_add(c0, c1);
+  x[1] = gl_sub(c0, c1);
+  x[2] = gl_add(d0, d1);
+  x[3] = gl_sub(d0, d1);
+  x[4] = gl_add(e0, e1);
+  x[5] = gl_sub(e0, e1);
+  x[6] = gl_add(f0, f1);
+  x[7] = gl_sub(f0, f1);
+}
+template <int RHO>
+struct Dft;
+template <>
+struct Dft<1> {
+  static GL_DEV void run(u64 (&x)[2]) { dft2(x); }
+};
+template <>
+struct Dft<2> {
+  static GL_DEV void run(u64 (&x)[4]) { dft4(x); }
+};
+template <>
+struct Dft<3> {
+  static GL_DEV void run(u64 (&x)[8]) { dft8(x); }
 };
 
-// Decimation-in-frequency network over LINES = 2^lines_log independent lines of S = 2^s points held
-// as sm[p*LINES + l]: consecutive threads take consecutive lines of the same butterfly, so shared
-// memory accesses are conflict-free and the twiddle is a broadcast.  Leaves X[bitrev_s(p)] at p.
-GL_DEV void smem_dif(u64 *sm, u32 s, u32 lines_log, Roots roots, bool inverse) {
-  const u32 total = 1u << (s + lines_log - 1);  // butterflies per stage (s >= 1)
-  const u32 lmask = (1u << lines_log) - 1;
-  for (int stage = (int)s - 1; stage >= 0; stage--) {
-    const u32 half = 1u << stage;
-    for (u32 b = threadIdx.x; b < total; b += blockDim.x) {
-      u32 l = b & lmask, bb = b >> lines_log;
-      u32 t = bb & (half - 1);
-      u32 i = ((bb >> stage) << (stage + 1)) + t;
-      u64 *pi = sm + (((size_t)i << lines_log) + l);
-      u64 *pj = pi + ((size_t)half << lines_log);
-      u64 u = *pi, v = *pj;
-      *pi = gl_add(u, v);
-      u64 d = gl_sub(u, v);
-      *pj = t ? gl_mul(d, roots.get((size_t)t << (roots.log_t - stage - 1), inverse)) : d;
+// One radix-2^RHO decimation-in-frequency pass over LINES = 2^lines_log lines of 2^s points held as
+// sm[p*LINES + l].  The current sub-transform length is L = 2^ell; a work item is the R points
+// p = blk*L + j*(L/R) + lo.  After the DFT, the output of frequency r (stored at j = bitrev(r)) is
+// multiplied by w_L^(r*lo) = W[r*lo << (s - ell)], W the root table of the line size 2^s.
+template <int RHO>
+GL_DEV void ntt_pass(u64 *sm, u32 ell, u32 s, u32 lines_log, const u64 *__restrict__ W) {
+  constexpr int R = 1 << RHO;
+  const u32 sub_log = ell - RHO;
+  const u32 items = 1u << (s - RHO + lines_log);
+  const u32 lmask = (1u << lines_log) - 1, lomask = (1u << sub_log) - 1;
+  const size_t jstride = (size_t)1 << (sub_log + lines_log);
+  for (u32 w = threadIdx.x; w < items; w += blockDim.x) {
+    const u32 l = w & lmask, q = w >> lines_log;
+    const u32 lo = q & lomask, blk = q >> sub_log;
+    u64 *base = sm + ((((size_t)blk << ell) + lo) << lines_log) + l;
+    u64 x[R];
+#pragma unroll
+    for (int j = 0; j < R; j++) x[j] = base[j * jstride];
+    Dft<RHO>::run(x);
+    if (sub_log) {  // lo == 0 for the last pass: all twiddles are 1
+      const u32 e1 = lo << (s - ell);
+#pragma unroll
+      for (int j = 1; j < R; j++) {
+        const u32 r = __brev((u32)j) >> (32 - RHO);
+        x[j] = gl_mul(x[j], __ldg(W + r * e1));
+      }
     }
-    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < R; j++) base[j * jstride] = x[j];
+  }
+  __syncthreads();
+}
+
+// Full network on a tile: passes of 3 stages while possible; a remainder of 4 is split 2+2.
+GL_DEV void smem_ntt(u64 *sm, u32 s, u32 lines_log, const u64 *__restrict__ W) {
+  u32 ell = s;
+  while (ell) {
+    if (ell == 4 || ell == 2) {
+      ntt_pass<2>(sm, ell, s, lines_log, W);
+      ell -= 2;
+    } else if (ell >= 3) {
+      ntt_pass<3>(sm, ell, s, lines_log, W);
+      ell -= 3;
+    } else {
+      ntt_pass<1>(sm, ell, s, lines_log, W);
+      ell -= 1;
+    }
   }
 }
 
-// ---- single pass: lines are columns ------------------------------------------------------------
-// grid.x = ceil(ncols / LINES); inverse transform, natural-order output scaled by n^-1
-__global__ void k_intt_single(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out,
-                              size_t out_stride, u32 ncols, u32 s, u32 lines_log, Roots roots, u64 n_inv) {
+// ---- single pass over global memory: lines are columns ------------------------------------------
+// grid.x = ceil(ncols / LINES); forward network + index reversal = inverse transform, scaled by n^-1
+__global__ void __launch_bounds__(1024)
+k_intt_single(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, u32 ncols,
+              u32 s, u32 lines_log, const u64 *__restrict__ W, u64 n_inv) {
   extern __shared__ u64 sm[];
-  const u32 S = 1u << s, LINES = 1u << lines_log, c0 = blockIdx.x * LINES;
+  const u32 S = 1u << s, c0 = blockIdx.x << lines_log;
   for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
     u32 p = e & (S - 1), l = e >> s, c = c0 + l;
     sm[((size_t)p << lines_log) + l] = c < ncols ? in[(size_t)c * in_stride + p] : 0;
   }
   __syncthreads();
-  if (s) smem_dif(sm, s, lines_log, roots, true);
+  smem_ntt(sm, s, lines_log, W);
   for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
-    u32 k = e & (S - 1), l = e >> s, c = c0 + l;
+    u32 i = e & (S - 1), l = e >> s, c = c0 + l;
+    u32 k = (S - i) & (S - 1);  // coeffs[i] = fft[(n - i) % n] / n
     if (c < ncols)
-      out[(size_t)c * out_stride + k] = gl_canon(gl_mul(sm[((size_t)brev_bits(k, s) << lines_log) + l], n_inv));
+      out[(size_t)c * out_stride + i] = gl_canon(gl_mul(sm[((size_t)brev_bits(k, s) << lines_log) + l], n_inv));
   }
 }
 
 // grid = (ceil(ncols / LINES), 2^r cosets): coset-scaled forward transform, leaf-ordered output
-__global__ void k_lde_single(const u64 *__restrict__ coeffs, size_t in_stride, u64 *__restrict__ lde, LdeMap map,
-                             u32 ncols, u32 s, u32 lines_log, u32 rate_bits, Roots roots,
-                             const u64 *__restrict__ pow7) {
+__global__ void __launch_bounds__(1024)
+k_lde_single(const u64 *__restrict__ coeffs, size_t in_stride, u64 *__restrict__ lde, LdeMap map, u32 ncols, u32 s,
+             u32 lines_log, u32 rate_bits, const u64 *__restrict__ W, const u64 *__restrict__ scale) {
   extern __shared__ u64 sm[];
-  const u32 S = 1u << s, LINES = 1u << lines_log, c0 = blockIdx.x * LINES, k = blockIdx.y;
+  const u32 S = 1u << s, c0 = blockIdx.x << lines_log, k = blockIdx.y;
+  const u64 *sc = scale + ((size_t)k << s);  // (7*w_N^k)^j
   for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
     u32 p = e & (S - 1), l = e >> s, c = c0 + l;
-    u64 v = 0;
-    if (c < ncols) {
-      v = coeffs[(size_t)c * in_stride + p];
-      v = gl_mul(v, gl_mul(pow7[p], roots.get((size_t)k * p, false)));  // (7*w_N^k)^p
-    }
-    sm[((size_t)p << lines_log) + l] = v;
+    sm[((size_t)p << lines_log) + l] = c < ncols ? gl_mul(coeffs[(size_t)c * in_stride + p], __ldg(sc + p)) : 0;
   }
   __syncthreads();
-  if (s) smem_dif(sm, s, lines_log, roots, false);
+  smem_ntt(sm, s, lines_log, W);
   const size_t block_base = (size_t)brev_bits(k, rate_bits) << s;
   for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
     u32 p = e & (S - 1), l = e >> s, c = c0 + l;
@@ -121,28 +213,29 @@ struct TwoPass {
 };
 
 // pass 1: tile = LINES adjacent j2; size-n1 transform over j1 (stride n2); then the four-step
-// twiddle rho^(j2*k1).  grid = (n2 / LINES, ncols, cosets)
-__global__ void k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride,
-                        LdeMap map, TwoPass tp, Roots roots, const u64 *__restrict__ pow7) {
+// twiddle w_n^(j2*k1).  grid = (n2 / LINES, ncols, cosets)
+__global__ void __launch_bounds__(1024)
+k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
+        TwoPass tp, const u64 *__restrict__ W1, const u64 *__restrict__ Wn, const u64 *__restrict__ scale) {
   extern __shared__ u64 sm[];
   const u32 LINES = 1u << tp.lines_log, S = 1u << tp.a;
   const size_t n2 = (size_t)1 << tp.b;
   const size_t c = blockIdx.y, k = blockIdx.z, q0 = (size_t)blockIdx.x * LINES;
+  const u64 *sc = tp.inverse ? nullptr : scale + (k << tp.n_log);
   for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
     u32 l = e & (LINES - 1), p = e >> tp.lines_log;
     size_t j = (size_t)p * n2 + q0 + l;
     u64 v = in[c * in_stride + j];
-    if (!tp.inverse) v = gl_mul(v, gl_mul(pow7[j], roots.get(k * j, false)));
+    if (!tp.inverse) v = gl_mul(v, __ldg(sc + j));
     sm[e] = v;  // == sm[p*LINES + l]
   }
   __syncthreads();
-  smem_dif(sm, tp.a, tp.lines_log, roots, tp.inverse);
+  smem_ntt(sm, tp.a, tp.lines_log, W1);
   const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
   for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
     u32 l = e & (LINES - 1), p = e >> tp.lines_log;
     size_t j2 = q0 + l, k1 = brev_bits(p, tp.a);
-    u64 w = roots.get((j2 * k1) << (roots.log_t - tp.n_log), tp.inverse);
-    u64 v = gl_mul(sm[e], w);
+    u64 v = gl_mul(sm[e], __ldg(Wn + j2 * k1));  // j2*k1 < n
     if (tp.inverse) out[c * out_stride + k1 * n2 + j2] = v;       // row k1 (natural)
     else out[map(block_base + (size_t)p * n2 + j2, c)] = v;       // row bitrev(k1) = p
   }
@@ -150,11 +243,12 @@ __global__ void k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__res
 
 // pass 2: tile = LINES adjacent rows; size-n2 transform along each (contiguous) row.
 // grid = (n1 / LINES, ncols, cosets)
-__global__ void k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride,
-                        LdeMap map, TwoPass tp, Roots roots) {
+__global__ void __launch_bounds__(1024)
+k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
+        TwoPass tp, const u64 *__restrict__ W2) {
   extern __shared__ u64 sm[];
   const u32 LINES = 1u << tp.lines_log, S = 1u << tp.b;
-  const size_t n1 = (size_t)1 << tp.a, n2 = (size_t)1 << tp.b;
+  const size_t n = (size_t)1 << tp.n_log, n1 = (size_t)1 << tp.a, n2 = (size_t)1 << tp.b;
   const size_t c = blockIdx.y, k = blockIdx.z, r0 = (size_t)blockIdx.x * LINES;
   const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
   for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
@@ -164,12 +258,12 @@ __global__ void k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__res
         tp.inverse ? in[c * in_stride + row * n2 + p] : in[map(block_base + row * n2 + p, c)];
   }
   __syncthreads();
-  smem_dif(sm, tp.b, tp.lines_log, roots, tp.inverse);
+  smem_ntt(sm, tp.b, tp.lines_log, W2);
   if (tp.inverse) {
     for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
       u32 l = e & (LINES - 1), p = e >> tp.lines_log;
-      size_t k1 = r0 + l, k2 = brev_bits(p, tp.b);
-      out[c * out_stride + k1 + n1 * k2] = gl_canon(gl_mul(sm[e], tp.n_inv));
+      size_t kk = (r0 + l) + n1 * brev_bits(p, tp.b);  // forward frequency k = k1 + n1*k2
+      out[c * out_stride + ((n - kk) & (n - 1))] = gl_canon(gl_mul(sm[e], tp.n_inv));
     }
   } else {
     for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
@@ -194,8 +288,9 @@ static u32 ceil_log2(size_t x) {
   return l;
 }
 static u32 threads_for(u32 tile_log) {
-  u32 t = tile_log >= 1 ? 1u << (tile_log - 1) : 1;  // one butterfly per thread...
-  if (t > 1024) t = 1024;                            // ...up to a full CTA
+  u32 t = tile_log >= 3 ? 1u << (tile_log - 3) : 1;  // one radix-8 item per thread and pass...
+  if (tile_log >= 13) t = 1u << (tile_log - 4);      // ...two on the big tiles (<= 1024 threads)
+  if (t > 1024) t = 1024;
   if (t < 32) t = 32;
   return t;
 }
@@ -228,18 +323,16 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
   if (ncols == 0) return "";
   if (n_log > 32) return "n_log exceeds the field's two-adicity (32)";
   const u64 n_inv = h_inv((u64)1 << n_log);
-  Roots roots;
-  roots.log_t = n_log;
-  MP2_TRY(table_roots(n_log, st, &roots.W));
   LdeMap none = {0, 0, 0};
   if (n_log <= kMaxSingleLog) {
+    const u64 *W;
+    MP2_TRY(table_roots(n_log, st, &W));
     u32 lines_log = n_log >= kTileLog ? 0 : std::min(kTileLog - n_log, ceil_log2(ncols));
     u32 tile_log = n_log + lines_log;
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_intt_single, smem));
     unsigned grid = (unsigned)((ncols + ((size_t)1 << lines_log) - 1) >> lines_log);
-    { ProfScope _p("k_intt_single", st); k_intt_single<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, coeffs, out_stride, (u32)ncols,
-                                                              n_log, lines_log, roots, n_inv); }
+    { ProfScope _p("k_intt_single", st); k_intt_single<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, coeffs, out_stride, (u32)ncols, n_log, lines_log, W, n_inv); }
     MP2_LAUNCH_CHECK();
     return "";
   }
@@ -248,6 +341,10 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
   tp.rate_bits = 0;
   tp.inverse = 1;
   tp.n_inv = n_inv;
+  const u64 *W1, *W2, *Wn;
+  MP2_TRY(table_roots(tp.a, st, &W1));
+  MP2_TRY(table_roots(tp.b, st, &W2));
+  MP2_TRY(table_roots(n_log, st, &Wn));
   const size_t n = (size_t)1 << n_log;
   u64 *tmp = nullptr;
   MP2_CUDA(cudaMallocAsync(&tmp, sizeof(u64) * n * ncols, st));
@@ -256,7 +353,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass1, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.b) >> tp.lines_log), (unsigned)ncols, 1);
-    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, tmp, n, none, tp, roots, nullptr); }
+    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, tmp, n, none, tp, W1, Wn, nullptr); }
     MP2_LAUNCH_CHECK();
   }
   {
@@ -267,7 +364,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, 1);
-    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, tp2, roots); }
+    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, tp2, W2); }
     MP2_LAUNCH_CHECK();
   }
   MP2_CUDA(cudaFreeAsync(tmp, st));
@@ -281,21 +378,19 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
   if (N_log > 32) return "n_log + rate_bits exceeds the field's two-adicity (32)";
   if (shard_log > N_log) return "shard_log larger than log2(number of leaves)";
   if (rate_bits > 15) return "rate_bits too large";
-  Roots roots;
-  roots.log_t = N_log;
-  MP2_TRY(table_roots(N_log, st, &roots.W));
-  const u64 *pow7 = nullptr;
-  MP2_TRY(table_shift_powers(n_log, st, &pow7));
+  const u64 *scale = nullptr;
+  MP2_TRY(table_coset_scale(n_log, rate_bits, st, &scale));
   LdeMap map = {N_log - shard_log, shard_log ? shard_stride : 0, lde_stride};
   const unsigned cosets = 1u << rate_bits;
   if (n_log <= kMaxSingleLog) {
+    const u64 *W;
+    MP2_TRY(table_roots(n_log, st, &W));
     u32 lines_log = n_log >= kTileLog ? 0 : std::min(kTileLog - n_log, ceil_log2(ncols));
     u32 tile_log = n_log + lines_log;
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_lde_single, smem));
     dim3 grid((unsigned)((ncols + ((size_t)1 << lines_log) - 1) >> lines_log), cosets, 1);
-    { ProfScope _p("k_lde_single", st); k_lde_single<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, map, (u32)ncols, n_log,
-                                                             lines_log, rate_bits, roots, pow7); }
+    { ProfScope _p("k_lde_single", st); k_lde_single<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, map, (u32)ncols, n_log, lines_log, rate_bits, W, scale); }
     MP2_LAUNCH_CHECK();
     return "";
   }
@@ -304,12 +399,16 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
   tp.rate_bits = rate_bits;
   tp.inverse = 0;
   tp.n_inv = 1;
+  const u64 *W1, *W2, *Wn;
+  MP2_TRY(table_roots(tp.a, st, &W1));
+  MP2_TRY(table_roots(tp.b, st, &W2));
+  MP2_TRY(table_roots(n_log, st, &Wn));
   {
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass1, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.b) >> tp.lines_log), (unsigned)ncols, cosets);
-    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, 0, map, tp, roots, pow7); }
+    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, 0, map, tp, W1, Wn, scale); }
     MP2_LAUNCH_CHECK();
   }
   {
@@ -320,7 +419,7 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     size_t smem = sizeof(u64) << tile_log;
     MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, cosets);
-    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(lde, 0, lde, 0, map, tp2, roots); }
+    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(lde, 0, lde, 0, map, tp2, W2); }
     MP2_LAUNCH_CHECK();
   }
   return "";

@@ -3,6 +3,7 @@
 // PolynomialBatch::from_values, which the GPU path ignores -- SURVEY.md 8(b) "Threading").
 #include <map>
 #include <mutex>
+#include <vector>
 
 #include "gl.cuh"
 #include "internal.h"
@@ -12,6 +13,12 @@ namespace mp2 {
 __global__ void k_fill_powers(u64 *out, u64 base, size_t count) {
   size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m < count) out[m] = gl_canon(gl_pow(base, m));
+}
+
+// out[(k << log_n) + j] = bases[k]^j
+__global__ void k_fill_coset_scale(u64 *out, const u64 *bases, u32 log_n, size_t count) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m < count) out[m] = gl_canon(gl_pow(bases[m >> log_n], m & (((size_t)1 << log_n) - 1)));
 }
 
 namespace {
@@ -54,8 +61,35 @@ Status get_table(int kind, u32 log, u64 base, cudaStream_t st, const u64 **out) 
 Status table_roots(u32 log_t, cudaStream_t st, const u64 **out) {
   return get_table(0, log_t, h_root_of_unity(log_t), st, out);
 }
-Status table_shift_powers(u32 log_n, cudaStream_t st, const u64 **out) {
-  return get_table(1, log_n, 7 /* coset_shift() = MULTIPLICATIVE_GROUP_GENERATOR */, st, out);
+Status table_coset_scale(u32 log_n, u32 rate_bits, cudaStream_t st, const u64 **out) {
+  int dev = 0;
+  MP2_CUDA(cudaGetDevice(&dev));
+  Key key = {dev, 2 + (int)rate_bits, log_n};
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_tables.find(key);
+  if (it != g_tables.end()) {
+    *out = it->second;
+    return "";
+  }
+  const size_t cosets = (size_t)1 << rate_bits, count = cosets << log_n;
+  std::vector<u64> bases(cosets);
+  const u64 wN = h_root_of_unity(log_n + rate_bits);
+  u64 wk = 1;
+  for (size_t k = 0; k < cosets; k++) {
+    bases[k] = h_mul(7 /* coset_shift() = MULTIPLICATIVE_GROUP_GENERATOR */, wk);
+    wk = h_mul(wk, wN);
+  }
+  u64 *d = nullptr, *d_bases = nullptr;
+  MP2_CUDA(cudaMalloc(&d, sizeof(u64) * count));
+  MP2_CUDA(cudaMalloc(&d_bases, sizeof(u64) * cosets));
+  MP2_CUDA(cudaMemcpyAsync(d_bases, bases.data(), sizeof(u64) * cosets, cudaMemcpyHostToDevice, st));
+  k_fill_coset_scale<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d, d_bases, log_n, count);
+  MP2_LAUNCH_CHECK();
+  MP2_CUDA(cudaStreamSynchronize(st));
+  MP2_CUDA(cudaFree(d_bases));
+  g_tables[key] = d;
+  *out = d;
+  return "";
 }
 
 }  // namespace mp2
