@@ -30,6 +30,7 @@ static __constant__ u64 c_pos_rc[MP2_POSEIDON_RC_LEN] = {MP2_POSEIDON_RC_LIST};
 static __constant__ u32 c_pos_rc3[MP2_POSEIDON_RC3_LEN] = {MP2_POSEIDON_RC3_LIST};
 static __constant__ u64 c_p2_rc[MP2_POSEIDON2_RC_LEN] = {MP2_POSEIDON2_RC_LIST};
 static __constant__ u64 c_p2_diag[MP2_POSEIDON2_DIAG_LEN] = {MP2_POSEIDON2_DIAG_LIST};
+static __constant__ u32 c_p2_rc3[MP2_POSEIDON2_RC3_LEN] = {MP2_POSEIDON2_RC3_LIST};
 
 // ------------------------------------------------------------------------------------------------
 // Poseidon: MDS = circ(17,15,41,16,2,28,13,13,39,18,34,20) + diag(8,0,...,0)
@@ -125,7 +126,24 @@ GL_DEV void pos_mds_rc(u64 (&s)[12], const u32 *rc3) {
   for (int i = 0; i < 12; i++) s[i] = pos_merge3(o0[i], o1[i], o2[i]);
 }
 
+// Carry-propagates the three plane outputs (each < 2^31) of one lane back into limbs that may enter
+// the next MDS: l0 < 2^22, l1 < 2^21.6, l2 < 2^21.  The bits above 2^64 (ov <= 2^10) are folded with
+// 2^64 = 2^32 - 1: +ov*2^10 on limb 1 (2^32 = 2^10 * 2^22) and -ov on limb 0, borrowing 2^22 from
+// limb 1 (which is >= ov*2^10 >= 1 whenever ov > 0) if limb 0 would go negative.
+GL_DEV void pos_renorm3(u32 o0, u32 o1, u32 o2, u32 &l0, u32 &l1, u32 &l2) {
+  const u32 t1 = o1 + (o0 >> 22);
+  const u32 t2 = o2 + (t1 >> 21);
+  const u32 ov = t2 >> 21;
+  l2 = t2 & 0x1FFFFFu;
+  const u32 d = (o0 & 0x3FFFFFu) - ov;
+  const u32 neg = (u32)((int)d >> 31);  // all ones if d < 0
+  l0 = d + (neg & 0x400000u);
+  l1 = (t1 & 0x1FFFFFu) + (ov << 10) + neg;
+}
+
 // Naive schedule (A.6): 30 x { +RC ; S-box (all lanes | lane 0) ; MDS }, 4 full + 22 partial + 4 full.
+// In the 22 partial rounds only lane 0 passes through the S-box, so lanes 1..11 stay in limb form
+// from one linear layer to the next (re-normalised, never merged) and only lane 0 is merged/split.
 template <bool SYNC>
 GL_DEV void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll
@@ -138,11 +156,28 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
     pos_mds_rc(s, c_pos_rc3 + 36 * (r + 1));
     MP2_ROUND_SYNC();
   }
+  {
+    u32 l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int i = 1; i < 12; i++) pos_split3(s[i], l0[i], l1[i], l2[i]);
+    u64 s0 = s[0];
 #pragma unroll 1
-  for (; r < 26; r++) {
-    s[0] = gl_pow7(s[0]);
-    pos_mds_rc(s, c_pos_rc3 + 36 * (r + 1));
-    MP2_ROUND_SYNC();
+    for (; r < 26; r++) {
+      s0 = gl_pow7(s0);
+      pos_split3(s0, l0[0], l1[0], l2[0]);
+      u32 o0[12], o1[12], o2[12];
+      const u32 *rc3 = c_pos_rc3 + 36 * (r + 1);
+      pos_mds_plane(l0, rc3, 3, o0);
+      pos_mds_plane(l1, rc3 + 1, 3, o1);
+      pos_mds_plane(l2, rc3 + 2, 3, o2);
+      s0 = pos_merge3(o0[0], o1[0], o2[0]);
+#pragma unroll
+      for (int i = 1; i < 12; i++) pos_renorm3(o0[i], o1[i], o2[i], l0[i], l1[i], l2[i]);
+      MP2_ROUND_SYNC();
+    }
+    s[0] = s0;
+#pragma unroll
+    for (int i = 1; i < 12; i++) s[i] = pos_merge3(l0[i], l1[i], l2[i]);
   }
 #pragma unroll 1
   for (; r < 30; r++) {
@@ -157,61 +192,79 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
 // Poseidon2 (Horizen-Labs Goldilocks t = 12):  M_E ; 4 x {+RC, S, M_E} ; 22 x {+rc on lane 0, S on
 // lane 0, M_I} ; 4 x {+RC, S, M_E}
 // ------------------------------------------------------------------------------------------------
-// M_E = circ(2*M4, M4, M4), M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]
-GL_DEV void p2_external(u64 (&s)[12]) {
+// M_E = circ(2*M4, M4, M4), M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]]; row sums <= 64, so the same
+// 22|21|21-bit limb planes as Poseidon's MDS apply: one plane is ~40 32-bit adds / shifted adds.
+GL_DEV void p2_ext_plane(const u32 (&x)[12], const u32 *rc, u32 (&y)[12]) {
+  u32 t[12];
 #pragma unroll
   for (int c = 0; c < 12; c += 4) {
-    u64 x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
-    u64 t0 = gl_add(x0, x1), t1 = gl_add(x2, x3);
-    u64 t2 = gl_add(gl_add(x1, x1), t1), t3 = gl_add(gl_add(x3, x3), t0);
-    u64 t1_2 = gl_add(t1, t1), t0_2 = gl_add(t0, t0);
-    u64 t4 = gl_add(gl_add(t1_2, t1_2), t3), t5 = gl_add(gl_add(t0_2, t0_2), t2);
-    s[c] = gl_add(t3, t5);
-    s[c + 1] = t5;
-    s[c + 2] = gl_add(t2, t4);
-    s[c + 3] = t4;
+    const u32 x0 = x[c], x1 = x[c + 1], x2 = x[c + 2], x3 = x[c + 3];
+    const u32 t0 = x0 + x1, t1 = x2 + x3;
+    const u32 t2 = (x1 << 1) + t1, t3 = (x3 << 1) + t0;
+    const u32 t4 = (t1 << 2) + t3, t5 = (t0 << 2) + t2;
+    t[c] = t3 + t5;
+    t[c + 1] = t5;
+    t[c + 2] = t2 + t4;
+    t[c + 3] = t4;
   }
-  u64 col[4];
 #pragma unroll
-  for (int l = 0; l < 4; l++) col[l] = gl_add(gl_add(s[l], s[4 + l]), s[8 + l]);
+  for (int l = 0; l < 4; l++) {
+    const u32 col = t[l] + t[4 + l] + t[8 + l];
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], col[i % 4]);
+    for (int k = 0; k < 3; k++) y[4 * k + l] = t[4 * k + l] + col + rc[3 * (4 * k + l)];
+  }
 }
 
-// M_I: out[i] = s[i]*mu_i + sum(s)
+// s <- M_E*s + constants of slot `slot` (see tools/gen_poseidon_constants.py)
+GL_DEV void p2_external_rc(u64 (&s)[12], int slot) {
+  u32 l0[12], l1[12], l2[12], o0[12], o1[12], o2[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) pos_split3(s[i], l0[i], l1[i], l2[i]);
+  const u32 *rc3 = c_p2_rc3 + 36 * slot;
+  p2_ext_plane(l0, rc3, o0);
+  p2_ext_plane(l1, rc3 + 1, o1);
+  p2_ext_plane(l2, rc3 + 2, o2);
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = pos_merge3(o0[i], o1[i], o2[i]);
+}
+
+// M_I: out[i] = s[i]*mu_i + sum(s).  The sum is accumulated in 96 bits and reduced once.
 GL_DEV void p2_internal(u64 (&s)[12]) {
-  u64 sum = s[0];
+  u32 a0 = lo32(s[0]), a1 = hi32(s[0]), a2 = 0;
 #pragma unroll
-  for (int i = 1; i < 12; i++) sum = gl_add(sum, s[i]);
+  for (int i = 1; i < 12; i++)
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
+        : "+r"(a0), "+r"(a1), "+r"(a2)
+        : "r"(lo32(s[i])), "r"(hi32(s[i])));
+  const u64 sum = gl_canon(gl_reduce128w(a0, a1, a2, 0u));  // canonical: one fold suffices below
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_add(gl_mul(s[i], c_p2_diag[i]), sum);
+  for (int i = 0; i < 12; i++) s[i] = gl_add_c(gl_mul(s[i], c_p2_diag[i]), sum);
 }
 
 template <bool SYNC>
 GL_DEV void poseidon2_permute(u64 (&s)[12]) {
-  p2_external(s);
-  const u64 *rc = c_p2_rc;
+  p2_external_rc(s, 0);
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_pow7(gl_add_c(s[i], rc[i]));
-    p2_external(s);
-    rc += 12;
+    for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+    p2_external_rc(s, r + 1);
     MP2_ROUND_SYNC();
   }
+  const u64 *rc = c_p2_rc + 48;
 #pragma unroll 1
   for (int r = 0; r < 22; r++) {
-    s[0] = gl_pow7(gl_add_c(s[0], rc[0]));
+    s[0] = gl_pow7(gl_add_c(s[0], rc[r]));
     p2_internal(s);
-    rc += 1;
     MP2_ROUND_SYNC();
   }
-#pragma unroll 1
-  for (int r = 0; r < 4; r++) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_pow7(gl_add_c(s[i], rc[i]));
-    p2_external(s);
-    rc += 12;
+  for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[22 + i]);
+#pragma unroll 1
+  for (int r = 4; r < 8; r++) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+    p2_external_rc(s, r + 1);
     MP2_ROUND_SYNC();
   }
 }
