@@ -274,6 +274,8 @@ static Status launch_leaf_hash(const u64 *in, size_t stride, u32 ncols, size_t n
   switch (env_int("MP2_HASH_BLOCK", MP2_HASH_BLOCK)) {
     case 64: return launch_leaf_hash_b<KIND, COLMAJOR, 64>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
     case 256: return launch_leaf_hash_b<KIND, COLMAJOR, 256>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
+    case 512: return launch_leaf_hash_b<KIND, COLMAJOR, 512>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
+    case 640: return launch_leaf_hash_b<KIND, COLMAJOR, 640>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
     default: return launch_leaf_hash_b<KIND, COLMAJOR, 128>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
   }
 }
