@@ -1,0 +1,58 @@
+"""NCCL run of the sharded commitment on real GPUs (needs >= 2 devices; skipped otherwise):
+column shards -> all-to-all -> row shards must reassemble to the oracle's single PolynomialBatch."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from util import field_elems
+
+    from mapreduce_plonky2_b200.sharded import CudaEngine, commit_sharded
+
+    cols = field_elems(0xBEEF, (ncols, 1 << n_log))
+    c_loc = ncols // world
+    mine = torch.from_numpy(cols[rank * c_loc:(rank + 1) * c_loc].view(np.int64).copy()).cuda()
+    res = commit_sharded(mine, ncols, rate_bits, cap_height, kind, CudaEngine())
+    torch.cuda.synchronize()
+    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), coeffs=res.coeffs.cpu().numpy().view(np.uint64),
+             leaves=res.leaves.cpu().numpy().view(np.uint64), digests=res.digests.cpu().numpy().view(np.uint64),
+             cap=res.cap.cpu().numpy().view(np.uint64))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ncols,n_log,kind", [(16, 12, 0), (6, 15, 1)])
+def test_sharded_nccl_equals_oracle(tmp_path, oracle, ncols, n_log, kind):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = 2
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from util import field_elems
+
+    port = 29600 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, ncols, n_log, 3, 4, kind, str(tmp_path)), nprocs=world, join=True)
+    cols = field_elems(0xBEEF, (ncols, 1 << n_log))
+    ref = oracle.commit(cols, 3, 4, kind)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    assert np.array_equal(np.concatenate([p["coeffs"] for p in parts]), ref["coeffs"])
+    assert np.array_equal(np.concatenate([p["leaves"] for p in parts]), ref["leaves"])
+    assert np.array_equal(np.concatenate([p["digests"] for p in parts]), ref["digests"])
+    for p in parts:
+        assert np.array_equal(p["cap"], ref["cap"])
