@@ -51,6 +51,11 @@ def parse_args():
     ap.add_argument("--rate-bits", type=int, default=3)
     ap.add_argument("--cap-height", type=int, default=4)
     ap.add_argument("--cpu-sample-log", type=int, default=15, help="rows (log2) of the CPU-baseline sample")
+    ap.add_argument("--workload", default="wide", choices=["wide", "trace"],
+                    help="wide: one 2^20 x 256 batch (BASELINE configs[2], the contract line); trace: mp2 leaf-proof "
+                         "commitment traces, independent proofs per GPU (configs[1]/[4])")
+    ap.add_argument("--proofs", type=int, default=64, help="trace workload: proofs per GPU per step")
+    ap.add_argument("--streams", type=int, default=4, help="trace workload: proofs in flight per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -393,9 +398,121 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
             "outputs": "coefficients + row-major leaves + digests + cap copied back to the host every step"}
 
 
+# ------------------------------------------------------------------------------------------------
+# proof-trace replay (map stage): independent proofs, one GPU each, no collective
+# ------------------------------------------------------------------------------------------------
+def cpu_trace_time(kind, threads):
+    """One leaf-proof trace on the CPU restatement (oracle/)."""
+    import oracle as O
+    from mapreduce_plonky2_b200 import trace as T
+
+    O.build()
+    t0 = time.perf_counter()
+    for i, op in enumerate(T.proof_ops()):
+        if op.kind == "merkle":
+            leaves = synthetic_columns(0x7000 + i, (1 << op.n_log, op.ncols))
+            O.merkle_new(leaves, min(T.CAP_HEIGHT, op.n_log), kind, nthreads=threads)
+        else:
+            cols = synthetic_columns(0x7000 + i, (op.ncols, 1 << op.n_log))
+            O.commit(cols, T.RATE_BITS, T.CAP_HEIGHT, kind, op.kind == "from_coeffs", nthreads=threads, want_leaves=True)
+    return time.perf_counter() - t0
+
+
+def run_trace(a):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    kind = 0 if a.hash == "poseidon" else 1
+    name = ("map stage: %d independent mp2-v1 leaf-proof commitment traces per GPU (prove() degrees 2^14, 2^13, 2^12 "
+            "ASSUMED; %s; trace replay = upper bound on proofs/s)") % (a.proofs, a.hash)
+    if a.impl == "reference":
+        if rank == 0:
+            import oracle as O
+            threads = O.max_threads()
+            dt = [cpu_trace_time(kind, threads) for _ in range(max(1, min(a.steps, 3)))]
+            v = len(dt) / sum(dt)
+            print(json.dumps({"impl": "reference", "metric": "mp2 leaf proofs/s (commitment trace)", "value": v,
+                              "unit": "proofs/s", "n_gpus": a.gpus, "steps": len(dt), "warmup": 0,
+                              "ms_per_step": 1e3 * sum(dt) / len(dt), "higher_is_better": True, "scaling": "weak",
+                              "vs_baseline": None, "dtype": "u64 (Goldilocks field)", "data": "synthetic",
+                              "config": {"workload": name, "sample": "one proof trace per step"},
+                              "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": threads, "kind": "port",
+                                               "sample": "one proof trace per step"},
+                              "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                              "gpu_launches": 0}), flush=True)
+        return
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import mapreduce_plonky2_b200 as G
+    from mapreduce_plonky2_b200 import trace as T
+
+    G.init(local_rank)
+    runner = T.TraceRunner(T.LEAF_PROOF_DEGREES, kind, a.streams)
+    launches0 = G.launch_count()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        runner.run(a.streams)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = G.launch_count()
+    e0.record()
+    for _ in range(a.steps):
+        runner.run(a.proofs)
+        for st in runner.streams:  # the default stream (and e1) waits for every in-flight proof
+            torch.cuda.current_stream().wait_stream(st)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / a.steps
+    value = world * a.proofs / (ms_step * 1e-3)
+    if rank == 0:
+        perms = runner.perms_per_proof
+        ip = __import__("mapreduce_plonky2_b200.device", fromlist=["x"]).int_pipe_peak()
+        mads = perms * a.proofs * PERM_MADS / (ms_step * 1e-3) / 1e12
+        line = {"metric": "mp2 leaf proofs/s (commitment trace)", "value": value, "unit": "proofs/s", "n_gpus": world,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
+                "config": {"workload": name, "parallelism": "replicas only (one proof stream set per GPU, no collective)",
+                           "streams_per_gpu": a.streams, "l2": "working set of %d concurrent proofs exceeds L2" % a.streams,
+                           "ops_per_proof": len(runner.ops), "perms_per_proof": perms,
+                           "lde_elems_per_proof": runner.lde_elems_per_proof},
+                "gpu_launches": int(G.launch_count() - launches0), "clocks": clocks,
+                "lde_gelems_per_s": world * a.proofs * runner.lde_elems_per_proof / (ms_step * 1e-3) / 1e9,
+                "roofline": {"kernel": "all Poseidon kernels of the trace (whole step)", "bound": "int_pipe",
+                             "achieved": mads, "peak": ip["t_imad_per_s"], "unit": "T imad/s (6700 credited per permutation)",
+                             "frac": mads / ip["t_imad_per_s"] if ip["t_imad_per_s"] else None, "traffic": None}}
+        if not a.no_cpu_baseline and world == 1:
+            import oracle as O
+            threads = O.max_threads()
+            dt = cpu_trace_time(kind, threads)
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
+                                    "sample": "one proof trace (%.1f s)" % dt}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
     rank = int(os.environ.get("RANK", "0"))
+    if a.workload == "trace":
+        run_trace(a)
+        return
     if a.impl == "reference":
         run_reference(a, rank)
         return

@@ -17,7 +17,8 @@ namespace {
 struct ThreadCtx {
   int device = 0;
   bool device_set = false;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute
+  cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute
   int stream_device = -1;
 };
 thread_local ThreadCtx t_ctx;
@@ -33,6 +34,7 @@ Status ctx_stream(cudaStream_t *out) {
   MP2_CUDA(cudaSetDevice(c.device));
   if (!c.stream || c.stream_device != c.device) {
     MP2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    MP2_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     c.stream_device = c.device;
     // keep freed blocks in the stream-ordered pool: commitments reuse the same sizes over and over
     cudaMemPool_t pool;
@@ -130,22 +132,47 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
   if (want_rows) MP2_TRY(d_leaves.alloc(ncols * N, st));
   MP2_TRY(d_dig.alloc(ndig * 4, st));
   MP2_TRY(d_cap.alloc(ncap * 4, st));
+  // The copy stream trails the compute stream: coefficients go back while the LDE runs, each block of
+  // leaf rows goes back while the next block is hashed.  PCIe, not HBM, bounds this entry point
+  // (SURVEY.md section 7), so hiding the copies behind the hashing is worth ~2x end to end.
+  cudaStream_t cp = t_ctx.copy_stream;
+  cudaEvent_t ev;
+  MP2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  struct EvGuard {
+    cudaEvent_t e;
+    ~EvGuard() { cudaEventDestroy(e); }
+  } ev_guard{ev};
   for (size_t c = 0; c < ncols; c++) {
     if (!cols[c]) return "null column pointer";
     MP2_CUDA(cudaMemcpyAsync(d_in.p + c * n, cols[c], n * sizeof(u64), cudaMemcpyHostToDevice, st));
   }
-  MP2_TRY(dev_commit(d_in.p, ncols, n_log, rate_bits, cap_height, hash_kind, from_coeffs, d_coeffs.p, d_lde.p,
-                     d_leaves.p, d_dig.p, d_cap.p, st));
-  if (coeffs_out)
+  if (from_coeffs) MP2_TRY(ntt_canonicalize(d_in.p, n, d_coeffs.p, n, ncols, n, st));
+  else MP2_TRY(ntt_intt(d_in.p, n, d_coeffs.p, n, ncols, n_log, st));
+  if (coeffs_out) {
+    MP2_CUDA(cudaEventRecord(ev, st));
+    MP2_CUDA(cudaStreamWaitEvent(cp, ev, 0));
     for (size_t c = 0; c < ncols; c++)
       if (coeffs_out[c])
-        MP2_CUDA(cudaMemcpyAsync(coeffs_out[c], d_coeffs.p + c * n, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+        MP2_CUDA(cudaMemcpyAsync(coeffs_out[c], d_coeffs.p + c * n, n * sizeof(u64), cudaMemcpyDeviceToHost, cp));
+  }
+  MP2_TRY(ntt_coset_lde(d_coeffs.p, n, d_lde.p, N, ncols, n_log, rate_bits, 0, 0, st));
+  const size_t nchunks = (leaves_out && N >= ((size_t)1 << 16)) ? 8 : 1;
+  for (size_t j = 0; j < nchunks; j++) {
+    const size_t lb = j * (N / nchunks), le = (j + 1) * (N / nchunks);
+    MP2_TRY(merkle_colmajor_leaves(d_lde.p, N, ncols, N, cap_height, hash_kind, lb, le, d_leaves.p, d_dig.p, d_cap.p, st));
+    if (leaves_out) {
+      MP2_CUDA(cudaEventRecord(ev, st));
+      MP2_CUDA(cudaStreamWaitEvent(cp, ev, 0));
+      MP2_CUDA(cudaMemcpyAsync(leaves_out + lb * ncols, d_leaves.p + lb * ncols, (le - lb) * ncols * sizeof(u64),
+                               cudaMemcpyDeviceToHost, cp));
+    }
+  }
+  MP2_TRY(merkle_levels(N, cap_height, hash_kind, d_dig.p, d_cap.p, st));
   MP2_CUDA(cudaMemcpyAsync(cap_out, d_cap.p, ncap * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
   if (digests_out && ndig)
     MP2_CUDA(cudaMemcpyAsync(digests_out, d_dig.p, ndig * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-  if (leaves_out)
-    MP2_CUDA(cudaMemcpyAsync(leaves_out, d_leaves.p, ncols * N * sizeof(u64), cudaMemcpyDeviceToHost, st));
   MP2_CUDA(cudaStreamSynchronize(st));
+  MP2_CUDA(cudaStreamSynchronize(cp));
   if (handle_out) {
     mp2gpu_batch *b = new mp2gpu_batch();
     MP2_CUDA(cudaGetDevice(&b->device));

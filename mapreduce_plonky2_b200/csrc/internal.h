@@ -90,6 +90,11 @@ Status ntt_canonicalize(const u64 *in, size_t in_stride, u64 *out, size_t out_st
 Status merkle_colmajor(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves,
                        u32 cap_height, u32 hash_kind, u64 *leaves_out, u64 *digests, u64 *cap,
                        cudaStream_t st);
+// the two halves of merkle_colmajor, for callers that pipeline leaf ranges against copies
+Status merkle_colmajor_leaves(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves, u32 cap_height,
+                              u32 hash_kind, size_t leaf_begin, size_t leaf_end, u64 *leaves_out, u64 *digests,
+                              u64 *cap, cudaStream_t st);
+Status merkle_levels(size_t nleaves, u32 cap_height, u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st);
 Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 cap_height,
                        u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st);
 // flat: concatenated leaves, offsets: nleaves+1 prefix sums (device)

@@ -45,11 +45,11 @@ GL_DEV u64 *leaf_digest_ptr(size_t L, u32 h, u64 *digests, u64 *cap) {
 // !COLMAJOR: element at in[L*stride + c] (row-major user leaves, FRI layers).
 template <u32 KIND, bool COLMAJOR, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
-k_leaf_hash(const u64 *__restrict__ in, size_t stride, u32 ncols, size_t nleaves, u32 h,
+k_leaf_hash(const u64 *__restrict__ in, size_t stride, u32 ncols, size_t leaf_begin, size_t leaf_end, u32 h,
             u64 *__restrict__ leaves_out, u64 *__restrict__ digests, u64 *__restrict__ cap) {
-  size_t L = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = L < nleaves;  // inactive threads still walk the rounds (block-wide barriers)
-  if (!active) L = nleaves - 1;
+  size_t L = leaf_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = L < leaf_end;  // inactive threads still walk the rounds (block-wide barriers)
+  if (!active) L = leaf_end - 1;
   u64 st[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) st[i] = 0;
@@ -258,25 +258,26 @@ static Status plan_hash_launch(K kernel, int block, size_t nthreads, int max_reg
 }
 
 template <u32 KIND, bool COLMAJOR, int BLOCK>
-static Status launch_leaf_hash_b(const u64 *in, size_t stride, u32 ncols, size_t nleaves, u32 h, u64 *leaves_out,
-                                 u64 *digests, u64 *cap, cudaStream_t st) {
+static Status launch_leaf_hash_b(const u64 *in, size_t stride, u32 ncols, size_t leaf_begin, size_t leaf_end, u32 h,
+                                 u64 *leaves_out, u64 *digests, u64 *cap, cudaStream_t st) {
   HashLaunch hl;
+  const size_t nleaves = leaf_end - leaf_begin;
   MP2_TRY(plan_hash_launch(k_leaf_hash<KIND, COLMAJOR, BLOCK>, BLOCK, nleaves, 0, &hl));
-  { ProfScope _p("k_leaf_hash", st); k_leaf_hash<KIND, COLMAJOR, BLOCK><<<grid_for(nleaves, BLOCK), BLOCK, hl.smem, st>>>(in, stride, ncols, nleaves, h,
+  { ProfScope _p("k_leaf_hash", st); k_leaf_hash<KIND, COLMAJOR, BLOCK><<<grid_for(nleaves, BLOCK), BLOCK, hl.smem, st>>>(in, stride, ncols, leaf_begin, leaf_end, h,
                                                                                       leaves_out, digests, cap); }
   MP2_LAUNCH_CHECK();
   return "";
 }
 
 template <u32 KIND, bool COLMAJOR>
-static Status launch_leaf_hash(const u64 *in, size_t stride, u32 ncols, size_t nleaves, u32 h, u64 *leaves_out,
-                               u64 *digests, u64 *cap, cudaStream_t st) {
+static Status launch_leaf_hash(const u64 *in, size_t stride, u32 ncols, size_t leaf_begin, size_t leaf_end, u32 h,
+                               u64 *leaves_out, u64 *digests, u64 *cap, cudaStream_t st) {
   switch (env_int("MP2_HASH_BLOCK", MP2_HASH_BLOCK)) {
-    case 64: return launch_leaf_hash_b<KIND, COLMAJOR, 64>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
-    case 256: return launch_leaf_hash_b<KIND, COLMAJOR, 256>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
-    case 512: return launch_leaf_hash_b<KIND, COLMAJOR, 512>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
-    case 640: return launch_leaf_hash_b<KIND, COLMAJOR, 640>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
-    default: return launch_leaf_hash_b<KIND, COLMAJOR, 128>(in, stride, ncols, nleaves, h, leaves_out, digests, cap, st);
+    case 64: return launch_leaf_hash_b<KIND, COLMAJOR, 64>(in, stride, ncols, leaf_begin, leaf_end, h, leaves_out, digests, cap, st);
+    case 256: return launch_leaf_hash_b<KIND, COLMAJOR, 256>(in, stride, ncols, leaf_begin, leaf_end, h, leaves_out, digests, cap, st);
+    case 512: return launch_leaf_hash_b<KIND, COLMAJOR, 512>(in, stride, ncols, leaf_begin, leaf_end, h, leaves_out, digests, cap, st);
+    case 640: return launch_leaf_hash_b<KIND, COLMAJOR, 640>(in, stride, ncols, leaf_begin, leaf_end, h, leaves_out, digests, cap, st);
+    default: return launch_leaf_hash_b<KIND, COLMAJOR, 128>(in, stride, ncols, leaf_begin, leaf_end, h, leaves_out, digests, cap, st);
   }
 }
 
@@ -300,17 +301,30 @@ static Status check_tree_args(size_t nleaves, u32 cap_height, u32 hash_kind, u32
   return "";
 }
 
-Status merkle_colmajor(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves, u32 cap_height,
-                       u32 hash_kind, u64 *leaves_out, u64 *digests, u64 *cap, cudaStream_t st) {
+Status merkle_colmajor_leaves(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves, u32 cap_height,
+                              u32 hash_kind, size_t leaf_begin, size_t leaf_end, u64 *leaves_out, u64 *digests,
+                              u64 *cap, cudaStream_t st) {
   u32 h;
   MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
   if (ncols == 0 || ncols > 0xFFFFFFFFu) return "bad number of columns";
+  if (leaf_begin >= leaf_end || leaf_end > nleaves) return "bad leaf range";
   if (hash_kind == MP2_HASH_POSEIDON2)
-    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON2, true>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap, st)));
-  else
-    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON, true>(lde, lde_stride, (u32)ncols, nleaves, h, leaves_out, digests, cap, st)));
+    return launch_leaf_hash<MP2_HASH_POSEIDON2, true>(lde, lde_stride, (u32)ncols, leaf_begin, leaf_end, h, leaves_out, digests, cap, st);
+  return launch_leaf_hash<MP2_HASH_POSEIDON, true>(lde, lde_stride, (u32)ncols, leaf_begin, leaf_end, h, leaves_out, digests, cap, st);
+}
+
+Status merkle_levels(size_t nleaves, u32 cap_height, u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st) {
+  u32 h;
+  MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
   return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
                                          : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
+}
+
+Status merkle_colmajor(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves, u32 cap_height,
+                       u32 hash_kind, u64 *leaves_out, u64 *digests, u64 *cap, cudaStream_t st) {
+  MP2_TRY(merkle_colmajor_leaves(lde, lde_stride, ncols, nleaves, cap_height, hash_kind, 0, nleaves, leaves_out, digests,
+                                 cap, st));
+  return merkle_levels(nleaves, cap_height, hash_kind, digests, cap, st);
 }
 
 Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 cap_height, u32 hash_kind,
@@ -319,9 +333,9 @@ Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 c
   MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
   if (leaf_len > 0xFFFFFFFFu) return "leaf too long";
   if (hash_kind == MP2_HASH_POSEIDON2)
-    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON2, false>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap, st)));
+    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON2, false>(leaves, leaf_len, (u32)leaf_len, 0, nleaves, h, nullptr, digests, cap, st)));
   else
-    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON, false>(leaves, leaf_len, (u32)leaf_len, nleaves, h, nullptr, digests, cap, st)));
+    MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON, false>(leaves, leaf_len, (u32)leaf_len, 0, nleaves, h, nullptr, digests, cap, st)));
   return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
                                          : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
 }
