@@ -1,0 +1,168 @@
+// mp2gpu_plonky2.hpp -- C++ host-side mirror of the plonky2 surface the reference reaches the hot path
+// through, written above the C ABI of mp2gpu.h (the reference's host language, Rust, has no toolchain in
+// this image; the Rust binding itself is in INTEGRATION.md).  Same names, argument meaning and failure
+// behaviour as plonky2 0.2.2:
+//
+//   PolynomialBatch::from_values / from_coeffs / get_lde_values   (plonky2 fri/oracle.rs; reached via
+//       circuit_data.prove at recursion-framework/src/circuit_builder.rs:308 and builder.build at :177)
+//   MerkleTree::new_ / prove / get, MerkleCap, MerkleProof          (plonky2 hash/merkle_tree.rs; called
+//       directly at recursion-framework/src/universal_verifier_gadget/circuit_set.rs:189, :216)
+//
+// Where Rust panics (MerkleTree::new with cap_height > log2(len), non power-of-two lengths) this throws
+// mp2gpu::Panic.  Header only; link with -lmp2gpu.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mp2gpu.h"
+
+namespace mp2gpu {
+
+using F = uint64_t;                 // GoldilocksField (repr(transparent) u64), canonical on output
+using HashOut = std::array<F, 4>;   // HashOut<F>
+
+struct Panic : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+inline void check(const char *err) {  // handle_c_result of gnark-utils/src/utils.rs:9-20
+  if (err) {
+    std::string msg(err);
+    mp2gpu_free_string(err);
+    throw Panic(msg);
+  }
+}
+
+enum class Hasher : uint32_t { Poseidon = MP2GPU_HASH_POSEIDON, Poseidon2 = MP2GPU_HASH_POSEIDON2 };
+
+inline void init(int device = 0) { check(mp2gpu_init(device)); }
+
+struct MerkleCap {
+  std::vector<HashOut> hashes;  // MerkleCap(pub Vec<H::Hash>)
+  size_t height() const {
+    size_t h = 0;
+    while ((size_t(1) << h) < hashes.size()) h++;
+    return h;
+  }
+  size_t len() const { return hashes.size(); }
+};
+
+struct MerkleProof {
+  std::vector<HashOut> siblings;  // bottom-up
+  size_t len() const { return siblings.size(); }
+};
+
+struct PolynomialValues {
+  std::vector<F> values;
+};
+struct PolynomialCoeffs {
+  std::vector<F> coeffs;
+};
+
+template <Hasher H>
+struct MerkleTree {
+  std::vector<std::vector<F>> leaves;
+  std::vector<HashOut> digests;
+  MerkleCap cap;
+
+  // MerkleTree::new(leaves, cap_height)
+  static MerkleTree new_(std::vector<std::vector<F>> leaves, size_t cap_height) {
+    MerkleTree t;
+    const size_t n = leaves.size();
+    std::vector<const uint64_t *> ptrs(n);
+    std::vector<size_t> lens(n);
+    for (size_t i = 0; i < n; i++) {
+      ptrs[i] = leaves[i].data();
+      lens[i] = leaves[i].size();
+    }
+    // sizes are validated by the library (it reports plonky2's assertion text); allocate defensively
+    const size_t ncap = cap_height < 63 ? size_t(1) << cap_height : 0;
+    t.digests.resize(n > ncap ? 2 * (n - ncap) : 0);
+    t.cap.hashes.resize(ncap ? ncap : 1);
+    check(mp2gpu_merkle_new_ragged(ptrs.data(), lens.data(), n, (uint32_t)cap_height, (uint32_t)H,
+                                   t.digests.empty() ? nullptr : t.digests[0].data(), t.cap.hashes[0].data()));
+    t.leaves = std::move(leaves);
+    return t;
+  }
+  const std::vector<F> &get(size_t i) const { return leaves[i]; }
+  // MerkleTree::prove(leaf_index)
+  MerkleProof prove(size_t leaf_index) const {
+    MerkleProof p;
+    size_t lg = 0;
+    while ((size_t(1) << lg) < leaves.size()) lg++;
+    p.siblings.resize(lg - cap.height() ? lg - cap.height() : 1);
+    size_t cnt = 0;
+    check(mp2gpu_merkle_prove(digests.empty() ? nullptr : digests[0].data(), leaves.size(), (uint32_t)cap.height(),
+                              leaf_index, p.siblings[0].data(), &cnt));
+    p.siblings.resize(cnt);
+    return p;
+  }
+};
+
+inline size_t reverse_bits(size_t x, size_t bits) {
+  size_t r = 0;
+  for (size_t i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+  return r;
+}
+
+template <Hasher H>
+struct PolynomialBatch {
+  std::vector<PolynomialCoeffs> polynomials;
+  MerkleTree<H> merkle_tree;
+  size_t degree_log = 0, rate_bits = 0;
+  bool blinding = false;
+
+  // PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table):
+  // timing / fft_root_table have no GPU counterpart (twiddles are device resident) and are omitted.
+  static PolynomialBatch from_values(const std::vector<PolynomialValues> &values, size_t rate_bits, bool blinding,
+                                     size_t cap_height) {
+    std::vector<const uint64_t *> cols(values.size());
+    for (size_t c = 0; c < values.size(); c++) cols[c] = values[c].values.data();
+    return commit(cols, values.empty() ? 0 : values[0].values.size(), rate_bits, blinding, cap_height, false);
+  }
+  static PolynomialBatch from_coeffs(const std::vector<PolynomialCoeffs> &polys, size_t rate_bits, bool blinding,
+                                     size_t cap_height) {
+    std::vector<const uint64_t *> cols(polys.size());
+    for (size_t c = 0; c < polys.size(); c++) cols[c] = polys[c].coeffs.data();
+    return commit(cols, polys.empty() ? 0 : polys[0].coeffs.size(), rate_bits, blinding, cap_height, true);
+  }
+  // get_lde_values(index, step): leaves[reverse_bits(index * step, degree_log + rate_bits)]
+  const std::vector<F> &get_lde_values(size_t index, size_t step) const {
+    return merkle_tree.leaves[reverse_bits(index * step, degree_log + rate_bits)];
+  }
+
+ private:
+  static PolynomialBatch commit(const std::vector<const uint64_t *> &cols, size_t n, size_t rate_bits, bool blinding,
+                                size_t cap_height, bool from_coeffs) {
+    if (blinding) throw Panic("blinding (salted) batches are not supported on the GPU path");
+    size_t n_log = 0;
+    while ((size_t(1) << n_log) < n) n_log++;
+    if (cols.empty() || n == 0 || (size_t(1) << n_log) != n) throw Panic("polynomial length must be a power of two");
+    const size_t N = n << rate_bits, ncols = cols.size(), ncap = size_t(1) << cap_height;
+    PolynomialBatch b;
+    b.degree_log = n_log;
+    b.rate_bits = rate_bits;
+    b.polynomials.resize(ncols);
+    std::vector<uint64_t *> coeff_ptrs(ncols);
+    for (size_t c = 0; c < ncols; c++) {
+      b.polynomials[c].coeffs.resize(n);
+      coeff_ptrs[c] = b.polynomials[c].coeffs.data();
+    }
+    std::vector<F> flat(N * ncols);
+    b.merkle_tree.digests.resize(N > ncap ? 2 * (N - ncap) : 0);
+    b.merkle_tree.cap.hashes.resize(ncap);
+    auto fn = from_coeffs ? mp2gpu_commit_from_coeffs : mp2gpu_commit_from_values;
+    check(fn(cols.data(), ncols, (uint32_t)n_log, (uint32_t)rate_bits, (uint32_t)cap_height, (uint32_t)H,
+             coeff_ptrs.data(), flat.data(),
+             b.merkle_tree.digests.empty() ? nullptr : b.merkle_tree.digests[0].data(),
+             b.merkle_tree.cap.hashes[0].data(), nullptr));
+    b.merkle_tree.leaves.resize(N);
+    for (size_t i = 0; i < N; i++) b.merkle_tree.leaves[i].assign(flat.begin() + i * ncols, flat.begin() + (i + 1) * ncols);
+    return b;
+  }
+};
+
+}  // namespace mp2gpu

@@ -43,8 +43,11 @@ GL_DEV u64 *leaf_digest_ptr(size_t L, u32 h, u64 *digests, u64 *cap) {
 // ---- K4: leaf sponge.  One thread per leaf; rate 8, overwrite absorb (A.5). ---------------------
 // COLMAJOR: element (column c, leaf L) at in[c*stride + L]  -> loads coalesce across the warp.
 // !COLMAJOR: element at in[L*stride + c] (row-major user leaves, FRI layers).
+#ifndef MP2_HASH_MIN_CTAS
+#define MP2_HASH_MIN_CTAS 1
+#endif
 template <u32 KIND, bool COLMAJOR, int BLOCK>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, BLOCK == 128 ? MP2_HASH_MIN_CTAS : 1)
 k_leaf_hash(const u64 *__restrict__ in, size_t stride, u32 ncols, size_t leaf_begin, size_t leaf_end, u32 h,
             u64 *__restrict__ leaves_out, u64 *__restrict__ digests, u64 *__restrict__ cap) {
   size_t L = leaf_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x;

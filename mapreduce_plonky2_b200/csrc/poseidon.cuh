@@ -141,6 +141,30 @@ GL_DEV void pos_renorm3(u32 o0, u32 o1, u32 o2, u32 &l0, u32 &l1, u32 &l2) {
   l1 = (t1 & 0x1FFFFFu) + (ov << 10) + neg;
 }
 
+// S-box on all 12 lanes.  Fully unrolled this is ~1000 instructions per round and the permutation
+// outgrows the instruction caches (ncu: `no_instruction` was the top stall); rolled up as 3 x 4 lanes
+// with a register rotation (24 moves per trip) it is a third of the code for 7 % more issue slots.
+#ifndef MP2_SBOX_ROLLED
+#define MP2_SBOX_ROLLED 1
+#endif
+GL_DEV void sbox_layer(u64 (&s)[12]) {
+#if MP2_SBOX_ROLLED
+#pragma unroll 1
+  for (int it = 0; it < 3; it++) {
+    const u64 t0 = gl_pow7(s[0]), t1 = gl_pow7(s[1]), t2 = gl_pow7(s[2]), t3 = gl_pow7(s[3]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+    s[8] = t0;
+    s[9] = t1;
+    s[10] = t2;
+    s[11] = t3;
+  }
+#else
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+#endif
+}
+
 // Naive schedule (A.6): 30 x { +RC ; S-box (all lanes | lane 0) ; MDS }, 4 full + 22 partial + 4 full.
 // In the 22 partial rounds only lane 0 passes through the S-box, so lanes 1..11 stay in limb form
 // from one linear layer to the next (re-normalised, never merged) and only lane 0 is merged/split.
@@ -151,8 +175,7 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
   int r = 0;
 #pragma unroll 1
   for (; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+    sbox_layer(s);
     pos_mds_rc(s, c_pos_rc3 + 36 * (r + 1));
     MP2_ROUND_SYNC();
   }
@@ -181,8 +204,7 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
   }
 #pragma unroll 1
   for (; r < 30; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+    sbox_layer(s);
     pos_mds_rc(s, c_pos_rc3 + 36 * (r + 1));
     MP2_ROUND_SYNC();
   }
@@ -246,8 +268,7 @@ GL_DEV void poseidon2_permute(u64 (&s)[12]) {
   p2_external_rc(s, 0);
 #pragma unroll 1
   for (int r = 0; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+    sbox_layer(s);
     p2_external_rc(s, r + 1);
     MP2_ROUND_SYNC();
   }
@@ -262,8 +283,7 @@ GL_DEV void poseidon2_permute(u64 (&s)[12]) {
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[22 + i]);
 #pragma unroll 1
   for (int r = 4; r < 8; r++) {
-#pragma unroll
-    for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
+    sbox_layer(s);
     p2_external_rc(s, r + 1);
     MP2_ROUND_SYNC();
   }

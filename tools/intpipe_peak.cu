@@ -19,6 +19,10 @@ __global__ void __launch_bounds__(1024) k(u64 *out, u64 *cycles, u32 seed) {
 #pragma unroll
   for (int i = 0; i < CHAINS; i++) acc[i] = (u64)a * (i + 3) + b;
   u32 x[CHAINS], y[CHAINS];
+  double dd[CHAINS];
+  const double dc = 1.0000001;
+#pragma unroll
+  for (int i = 0; i < CHAINS; i++) dd[i] = 1.0 + 1e-9 * (double)(threadIdx.x + i);
 #pragma unroll
   for (int i = 0; i < CHAINS; i++) { x[i] = a + i; y[i] = b - i; }
   __syncthreads();
@@ -67,6 +71,18 @@ __global__ void __launch_bounds__(1024) k(u64 *out, u64 *cycles, u32 seed) {
       } else if (MODE == 8) {  // 1 IMAD (lo) : 1 LOP3
         asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x[i]) : "r"(x[j]), "r"(b));
         asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(y[i]) : "r"(x[i]), "r"(y[j]));
+      } else if (MODE == 20) {  // DFMA
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dd[j]), "d"(dc));
+      } else if (MODE == 21) {  // DADD
+        asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(dd[i]) : "d"(dd[j]));
+      } else if (MODE == 22) {  // 1 DFMA : 1 LOP3 : 1 IMAD  (three pipes)
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dd[j]), "d"(dc));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(y[i]));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y[i]) : "r"(y[j]), "r"(b));
+      } else if (MODE == 23) {  // 1 DFMA : 2 LOP3
+        asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(dd[i]) : "d"(dd[j]), "d"(dc));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(x[j]), "r"(y[i]));
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(y[i]) : "r"(y[j]), "r"(b));
       } else if (MODE == 12) {  // IADD3 three-operand adds
         asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(x[i]) : "r"(x[j]), "r"(y[i]));
       }
@@ -75,7 +91,7 @@ __global__ void __launch_bounds__(1024) k(u64 *out, u64 *cycles, u32 seed) {
   long long t1 = clock64();
   u64 s = 0;
 #pragma unroll
-  for (int i = 0; i < CHAINS; i++) s += acc[i] + x[i] + y[i];
+  for (int i = 0; i < CHAINS; i++) s += acc[i] + x[i] + y[i] + (u64)__double_as_longlong(dd[i]);
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cycles[blockIdx.x] = (u64)(t1 - t0);
 }
@@ -109,6 +125,10 @@ int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   int nsm = p.multiProcessorCount;
   printf("device %s, %d SMs\n", p.name, nsm);
+  run<20>("DFMA", 1, nsm);
+  run<21>("DADD", 1, nsm);
+  run<22>("1 DFMA : 1 LOP3 : 1 IMAD", 3, nsm);
+  run<23>("1 DFMA : 2 LOP3", 3, nsm);
   run<0>("IMAD.WIDE.U32 (acc-dependent)", 1, nsm);
   run<13>("mul.wide.u32", 1, nsm);
   run<14>("IMAD.WIDE (indep. multiplicands) + LOP3", 2, nsm);
