@@ -363,6 +363,21 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
             call()
         dt = (time.perf_counter() - t0) / steps
         api = "mp2gpu_commit_from_values (C ABI, pinned host buffers)"
+
+        # variant: the leaves stay on the device behind a batch handle (get_lde_values fetches rows on demand)
+        handle = C.c_void_p(None)
+
+        def call_resident():
+            _lib.call("mp2gpu_commit_from_values", ptrs(cols_h), a.ncols, a.n_log, a.rate_bits, a.cap_height, kind,
+                      ptrs(coeffs_h), None, C.cast(dig_h.data_ptr(), u64p), C.cast(cap_h.data_ptr(), u64p),
+                      C.byref(handle))
+            _lib.load().mp2gpu_batch_free(handle)
+
+        call_resident()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call_resident()
+        dt_res = (time.perf_counter() - t0) / steps
     else:
         cols_h = torch.empty((c_loc, n), dtype=torch.int64, pin_memory=True)
         cols_h.random_(0, 1 << 62)
@@ -393,9 +408,15 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         dt = float(t.item())
         api = "sharded.commit_sharded with pinned host shards (H2D + D2H per rank)"
     elems = a.ncols * N
-    return {"value": elems / dt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "ms_per_step": dt * 1e3, "steps": steps, "api": api,
-            "outputs": "coefficients + row-major leaves + digests + cap copied back to the host every step"}
+    out = {"value": elems / dt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": dt * 1e3, "steps": steps, "api": api,
+           "outputs": "coefficients + row-major leaves + digests + cap copied back to the host every step"}
+    if world == 1:
+        out["leaves_resident"] = {"value": elems / dt_res / 1e9, "unit": "Gelem/s", "ms_per_step": dt_res * 1e3,
+                                  "d2h_bytes_per_step": d2h - 8 * a.ncols * N,
+                                  "note": "same call with leaves_out = NULL + handle_out: leaves stay in HBM behind "
+                                          "mp2gpu_batch_fetch_rows (get_lde_values)"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -172,41 +172,41 @@ template <bool SYNC>
 GL_DEV void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pos_rc[i]);
-  int r = 0;
+  // The two groups of four full rounds share ONE copy of the full-round code (phase loop): with
+  // separate copies the three loop bodies (2 x 14 KB + 8 KB) no longer fit the 32 KB instruction cache
+  // level when the resident CTAs are in different parts of the permutation.
 #pragma unroll 1
-  for (; r < 4; r++) {
-    sbox_layer(s);
-    pos_mds_rc(s, c_pos_rc3 + 36 * (r + 1));
-    MP2_ROUND_SYNC();
-  }
-  {
-    u32 l0[12], l1[12], l2[12];
-#pragma unroll
-    for (int i = 1; i < 12; i++) pos_split3(s[i], l0[i], l1[i], l2[i]);
-    u64 s0 = s[0];
+  for (int phase = 0; phase < 2; phase++) {
+    const int r0 = phase ? 26 : 0;
 #pragma unroll 1
-    for (; r < 26; r++) {
-      s0 = gl_pow7(s0);
-      pos_split3(s0, l0[0], l1[0], l2[0]);
-      u32 o0[12], o1[12], o2[12];
-      const u32 *rc3 = c_pos_rc3 + 36 * (r + 1);
-      pos_mds_plane(l0, rc3, 3, o0);
-      pos_mds_plane(l1, rc3 + 1, 3, o1);
-      pos_mds_plane(l2, rc3 + 2, 3, o2);
-      s0 = pos_merge3(o0[0], o1[0], o2[0]);
-#pragma unroll
-      for (int i = 1; i < 12; i++) pos_renorm3(o0[i], o1[i], o2[i], l0[i], l1[i], l2[i]);
+    for (int k = 0; k < 4; k++) {
+      sbox_layer(s);
+      pos_mds_rc(s, c_pos_rc3 + 36 * (r0 + k + 1));
       MP2_ROUND_SYNC();
     }
-    s[0] = s0;
+    if (phase == 0) {
+      u32 l0[12], l1[12], l2[12];
 #pragma unroll
-    for (int i = 1; i < 12; i++) s[i] = pos_merge3(l0[i], l1[i], l2[i]);
-  }
+      for (int i = 1; i < 12; i++) pos_split3(s[i], l0[i], l1[i], l2[i]);
+      u64 s0 = s[0];
 #pragma unroll 1
-  for (; r < 30; r++) {
-    sbox_layer(s);
-    pos_mds_rc(s, c_pos_rc3 + 36 * (r + 1));
-    MP2_ROUND_SYNC();
+      for (int r = 4; r < 26; r++) {
+        s0 = gl_pow7(s0);
+        pos_split3(s0, l0[0], l1[0], l2[0]);
+        u32 o0[12], o1[12], o2[12];
+        const u32 *rc3 = c_pos_rc3 + 36 * (r + 1);
+        pos_mds_plane(l0, rc3, 3, o0);
+        pos_mds_plane(l1, rc3 + 1, 3, o1);
+        pos_mds_plane(l2, rc3 + 2, 3, o2);
+        s0 = pos_merge3(o0[0], o1[0], o2[0]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) pos_renorm3(o0[i], o1[i], o2[i], l0[i], l1[i], l2[i]);
+        MP2_ROUND_SYNC();
+      }
+      s[0] = s0;
+#pragma unroll
+      for (int i = 1; i < 12; i++) s[i] = pos_merge3(l0[i], l1[i], l2[i]);
+    }
   }
 }
 
@@ -266,26 +266,25 @@ GL_DEV void p2_internal(u64 (&s)[12]) {
 template <bool SYNC>
 GL_DEV void poseidon2_permute(u64 (&s)[12]) {
   p2_external_rc(s, 0);
-#pragma unroll 1
-  for (int r = 0; r < 4; r++) {
-    sbox_layer(s);
-    p2_external_rc(s, r + 1);
-    MP2_ROUND_SYNC();
-  }
   const u64 *rc = c_p2_rc + 48;
 #pragma unroll 1
-  for (int r = 0; r < 22; r++) {
-    s[0] = gl_pow7(gl_add_c(s[0], rc[r]));
-    p2_internal(s);
-    MP2_ROUND_SYNC();
-  }
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[22 + i]);
+  for (int phase = 0; phase < 2; phase++) {  // one copy of the external-round code, see poseidon_permute
 #pragma unroll 1
-  for (int r = 4; r < 8; r++) {
-    sbox_layer(s);
-    p2_external_rc(s, r + 1);
-    MP2_ROUND_SYNC();
+    for (int k = 0; k < 4; k++) {
+      sbox_layer(s);
+      p2_external_rc(s, 4 * phase + k + 1);  // slots 1..4, then 5..8 (tools/gen_poseidon_constants.py)
+      MP2_ROUND_SYNC();
+    }
+    if (phase == 0) {
+#pragma unroll 1
+      for (int r = 0; r < 22; r++) {
+        s[0] = gl_pow7(gl_add_c(s[0], rc[r]));
+        p2_internal(s);
+        MP2_ROUND_SYNC();
+      }
+#pragma unroll
+      for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], rc[22 + i]);
+    }
   }
 }
 
