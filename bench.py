@@ -56,6 +56,8 @@ def parse_args():
                          "commitment traces, independent proofs per GPU (configs[1]/[4])")
     ap.add_argument("--proofs", type=int, default=64, help="trace workload: proofs per GPU per step")
     ap.add_argument("--streams", type=int, default=4, help="trace workload: proofs in flight per GPU")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: peer = LDE kernel stores into the peers' buffers over NVLink; nccl = all_to_all_single")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -209,7 +211,8 @@ def run_ours(a):
 
     def step():
         if world > 1:
-            return S.commit_sharded(cols, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch)
+            return S.commit_sharded(cols, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
+                                    exchange=a.exchange)
         return commit_solo()
 
     solo_bufs = D.CommitBuffers(a.ncols, a.n_log, a.rate_bits, a.cap_height, True) if world == 1 else None
@@ -298,7 +301,8 @@ def run_ours(a):
             "metric": "Merkle-committed LDE Gelem/s", "value": value, "unit": "Gelem/s", "n_gpus": world,
             "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
-            "config": {"workload": workload_name(a), "parallelism": "columns/%d -> all-to-all -> rows/%d" % (world, world)
+            "config": {"workload": workload_name(a), "parallelism": "columns/%d -> %s -> rows/%d" % (
+                           world, "peer stores from the LDE kernel (NVLink)" if a.exchange == "peer" else "NCCL all-to-all", world)
                        if world > 1 else "single GPU", "l2": "inputs (%.1f GB) and LDE (%.1f GB) exceed the 126 MB L2" % (
                            8 * a.ncols * n / 1e9, 8 * elems / 1e9),
                        "timing": "CUDA events on the launching stream, max over ranks"},
@@ -389,7 +393,8 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
 
         def call():
             cols_d.copy_(cols_h, non_blocking=True)
-            r = S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch)
+            r = S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
+                                 exchange=a.exchange)
             coeffs_h.copy_(r.coeffs, non_blocking=True)
             leaves_h.copy_(r.leaves, non_blocking=True)
             dig_h.copy_(r.digests, non_blocking=True)

@@ -134,6 +134,15 @@ const char *mp2gpu_dev_coset_lde(const uint64_t *coeffs, size_t in_stride, uint6
                                  size_t lde_stride, size_t ncols, uint32_t n_log,
                                  uint32_t rate_bits, uint32_t shard_log, size_t shard_stride,
                                  void *stream);
+/* The same transform with the row-shard exchange fused into its store: shard g (the leaves owned by
+ * rank g) is written straight to shard_bases[g] + c*lde_stride -- pointers into the other ranks' HBM
+ * mapped over NVLink/NVSwitch (peer or symmetric memory), so no all-to-all follows.  shard_bases is a
+ * HOST array of 2^shard_log (<= 16) device pointers.  Callers order the kernel against the peers with
+ * their own barrier (sharded.py: symmetric-memory barrier before and after). */
+const char *mp2gpu_dev_coset_lde_peer(const uint64_t *coeffs, size_t in_stride,
+                                      uint64_t *const *shard_bases, size_t lde_stride, size_t ncols,
+                                      uint32_t n_log, uint32_t rate_bits, uint32_t shard_log,
+                                      void *stream);
 /* Leaf-ordered column-major LDE (column c at lde + c*lde_stride, nleaves elements) -> optional
  * row-major leaves (nleaves x ncols), digests and cap of a tree with `nleaves` leaves.  A rank of a
  * G-way row-sharded batch passes nleaves = N/G and cap_height - log2(G): its digests/cap are the

@@ -529,6 +529,18 @@ const char *mp2gpu_dev_coset_lde(const uint64_t *coeffs, size_t in_stride, uint6
   });
 }
 
+const char *mp2gpu_dev_coset_lde_peer(const uint64_t *coeffs, size_t in_stride, uint64_t *const *shard_bases,
+                                      size_t lde_stride, size_t ncols, uint32_t n_log, uint32_t rate_bits,
+                                      uint32_t shard_log, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    if (!shard_bases) return "null shard_bases";
+    return ntt_coset_lde((const u64 *)coeffs, in_stride, nullptr, lde_stride, ncols, n_log, rate_bits, shard_log, 0, st,
+                         (u64 *const *)shard_bases);
+  });
+}
+
 const char *mp2gpu_dev_merkle_colmajor(const uint64_t *lde, size_t lde_stride, size_t ncols, size_t nleaves,
                                        uint32_t cap_height, uint32_t hash_kind, uint64_t *leaves_out,
                                        uint64_t *digests_out, uint64_t *cap_out, void *stream) {

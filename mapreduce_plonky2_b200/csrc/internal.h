@@ -81,8 +81,11 @@ Status table_coset_scale(u32 log_n, u32 rate_bits, cudaStream_t st, const u64 **
 // ---- transforms (ntt.cu) ----
 Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_stride, size_t ncols,
                 u32 n_log, cudaStream_t st);
+// peer_bases (optional, host array of 2^shard_log device pointers): shard g is written to peer_bases[g]
+// (column c at + c*lde_stride) instead of lde + g*shard_stride -- the exchange fused into the store.
 Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols,
-                     u32 n_log, u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st);
+                     u32 n_log, u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st,
+                     u64 *const *peer_bases = nullptr);
 Status ntt_canonicalize(const u64 *in, size_t in_stride, u64 *out, size_t out_stride, size_t ncols,
                         size_t n, cudaStream_t st);
 

@@ -32,11 +32,19 @@ namespace mp2 {
 static const u32 kMaxSingleLog = 14;  // 2^14 * 8 B = 128 KB of the 227 KB shared memory
 static const u32 kTileLog = 13;       // target tile (elements) when several lines share a CTA
 
-struct LdeMap {  // (column c, leaf L) -> offset in the leaf-ordered, column-major, shardable buffer
+struct LdeMap {  // (column c, leaf L) -> address in the leaf-ordered, column-major, shardable buffer
   u32 ls_log;    // log2(leaves per shard)
   size_t shard_stride, col_stride;
+  // peer mode: shard g of the output starts at bases[g] -- a buffer in rank g's HBM, mapped over NVLink
+  // (the exchange of the sharded commitment happens in the store of the LDE kernel itself)
+  u32 peer;
+  u64 *bases[16];
   GL_DEV size_t operator()(size_t L, size_t c) const {
     return (L >> ls_log) * shard_stride + c * col_stride + (L & (((size_t)1 << ls_log) - 1));
+  }
+  GL_DEV u64 *ptr(u64 *local, size_t L, size_t c) const {
+    if (peer) return bases[L >> ls_log] + c * col_stride + (L & (((size_t)1 << ls_log) - 1));
+    return local + (*this)(L, c);
   }
 };
 
@@ -228,7 +236,7 @@ k_lde_single(const u64 *__restrict__ coeffs, size_t in_stride, u64 *__restrict__
   const size_t block_base = (size_t)brev_bits(k, rate_bits) << s;
   for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
     u32 p = e & (S - 1), l = e >> s, c = c0 + l;
-    if (c < ncols) lde[map(block_base + p, c)] = gl_canon(sm[sidx(((size_t)p << lines_log) + l)]);
+    if (c < ncols) *map.ptr(lde, block_base + p, c) = gl_canon(sm[sidx(((size_t)p << lines_log) + l)]);
   }
 }
 
@@ -274,7 +282,7 @@ k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, siz
 // grid = (n1 / LINES, ncols, cosets)
 __global__ void __launch_bounds__(1024)
 k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
-        TwoPass tp, const u64 *__restrict__ W2) {
+        LdeMap out_map, TwoPass tp, const u64 *__restrict__ W2) {
   extern __shared__ u64 sm[];
   const u32 LINES = 1u << tp.lines_log, S = 1u << tp.b;
   const size_t n = (size_t)1 << tp.n_log, n1 = (size_t)1 << tp.a, n2 = (size_t)1 << tp.b;
@@ -297,7 +305,7 @@ k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, siz
   } else {
     for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
       u32 p = e & (S - 1), l = e >> tp.b;
-      out[map(block_base + (r0 + l) * n2 + p, c)] = gl_canon(sm[sidx(((size_t)p << tp.lines_log) + l)]);
+      *out_map.ptr(out, block_base + (r0 + l) * n2 + p, c) = gl_canon(sm[sidx(((size_t)p << tp.lines_log) + l)]);
     }
   }
 }
@@ -352,7 +360,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
   if (ncols == 0) return "";
   if (n_log > 32) return "n_log exceeds the field's two-adicity (32)";
   const u64 n_inv = h_inv((u64)1 << n_log);
-  LdeMap none = {0, 0, 0};
+  LdeMap none = {};
   if (n_log <= kMaxSingleLog) {
     const u64 *W;
     MP2_TRY(table_roots(n_log, st, &W));
@@ -393,7 +401,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     size_t smem = smem_bytes_for(tile_log);
     MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, 1);
-    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, tp2, W2); }
+    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, none, tp2, W2); }
     MP2_LAUNCH_CHECK();
   }
   MP2_CUDA(cudaFreeAsync(tmp, st));
@@ -401,7 +409,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
 }
 
 Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols, u32 n_log,
-                     u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st) {
+                     u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st, u64 *const *peer_bases) {
   if (ncols == 0) return "";
   const u32 N_log = n_log + rate_bits;
   if (N_log > 32) return "n_log + rate_bits exceeds the field's two-adicity (32)";
@@ -409,7 +417,15 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
   if (rate_bits > 15) return "rate_bits too large";
   const u64 *scale = nullptr;
   MP2_TRY(table_coset_scale(n_log, rate_bits, st, &scale));
-  LdeMap map = {N_log - shard_log, shard_log ? shard_stride : 0, lde_stride};
+  LdeMap map = {};
+  map.ls_log = N_log - shard_log;
+  map.shard_stride = shard_log ? shard_stride : 0;
+  map.col_stride = lde_stride;
+  if (peer_bases) {
+    if (shard_log > 4) return "peer exchange supports at most 16 ranks";
+    map.peer = 1;
+    for (u32 g = 0; g < (1u << shard_log); g++) map.bases[g] = peer_bases[g];
+  }
   const unsigned cosets = 1u << rate_bits;
   if (n_log <= kMaxSingleLog) {
     const u64 *W;
@@ -432,12 +448,23 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
   MP2_TRY(table_roots(tp.a, st, &W1));
   MP2_TRY(table_roots(tp.b, st, &W2));
   MP2_TRY(table_roots(n_log, st, &Wn));
+  // the four-step intermediate stays local: in place in the output buffer, or (peer mode, where the
+  // output lives in other ranks' HBM) in a scratch buffer of the same shape
+  LdeMap mid_map = map;
+  u64 *mid = lde;
+  if (map.peer) {
+    const size_t N = (size_t)1 << N_log;
+    mid_map = LdeMap{};
+    mid_map.ls_log = N_log;
+    mid_map.col_stride = N;
+    MP2_CUDA(cudaMallocAsync(&mid, sizeof(u64) * N * ncols, st));
+  }
   {
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);
     MP2_TRY(allow_smem(k_pass1, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.b) >> tp.lines_log), (unsigned)ncols, cosets);
-    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, lde, 0, map, tp, W1, Wn, scale); }
+    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, mid, 0, mid_map, tp, W1, Wn, scale); }
     MP2_LAUNCH_CHECK();
   }
   {
@@ -448,9 +475,10 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     size_t smem = smem_bytes_for(tile_log);
     MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, cosets);
-    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(lde, 0, lde, 0, map, tp2, W2); }
+    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(mid, 0, lde, 0, mid_map, map, tp2, W2); }
     MP2_LAUNCH_CHECK();
   }
+  if (map.peer) MP2_CUDA(cudaFreeAsync(mid, st));
   return "";
 }
 

@@ -82,6 +82,18 @@ def coset_lde(coeffs: torch.Tensor, lde: torch.Tensor, rate_bits: int, shard_log
               n.bit_length() - 1, rate_bits, shard_log, shard_stride, _stream_ptr())
 
 
+def coset_lde_peer(coeffs: torch.Tensor, shard_ptrs, n_loc: int, rate_bits: int) -> None:
+    """coeffs (ncols, n) -> LDE whose shard g is stored at device address ``shard_ptrs[g]`` (column c at
+    + c*n_loc elements): the peers' receive buffers, i.e. the all-to-all happens in the kernel's store."""
+    import ctypes as C
+
+    ncols, n = coeffs.shape
+    G = len(shard_ptrs)
+    arr = (C.c_void_p * G)(*[C.c_void_p(int(p)) for p in shard_ptrs])
+    _lib.call("mp2gpu_dev_coset_lde_peer", _chk(coeffs, "coeffs"), n, arr, n_loc, ncols, n.bit_length() - 1,
+              rate_bits, G.bit_length() - 1, _stream_ptr())
+
+
 def merkle_colmajor(lde: torch.Tensor, cap_height: int, hash_kind: int, leaves: Optional[torch.Tensor],
                     digests: torch.Tensor, cap: torch.Tensor) -> None:
     """lde (ncols, nleaves) leaf-ordered column-major -> row-major leaves (optional), digests, cap."""

@@ -45,8 +45,33 @@ class CudaEngine:
     def coset_lde(self, coeffs, lde, rate_bits, shard_log):
         self.d.coset_lde(coeffs, lde, rate_bits, shard_log)
 
+    def coset_lde_peer(self, coeffs, shard_ptrs, n_loc, rate_bits):
+        self.d.coset_lde_peer(coeffs, shard_ptrs, n_loc, rate_bits)
+
     def merkle_colmajor(self, lde, cap_height, hash_kind, leaves, digests, cap):
         self.d.merkle_colmajor(lde, cap_height, hash_kind, leaves, digests, cap)
+
+
+class PeerExchange:
+    """Receive buffer of this rank in symmetric memory, mapped into every peer over NVLink/NVSwitch.
+
+    With it the column-shard -> row-shard exchange is not a separate collective: every rank's LDE kernel
+    stores shard ``g`` of its output directly into rank ``g``'s receive buffer (``mp2gpu_dev_coset_lde_peer``),
+    bracketed by two device-side barriers on the compute stream.  NCCL stays for the 512-byte cap gather."""
+
+    def __init__(self, G: int, c_loc: int, n_loc: int, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.recv = symm.empty((G, c_loc, n_loc), dtype=torch.int64, device=dev)
+        self.hdl = symm.rendezvous(self.recv, group if group is not None else dist.group.WORLD)
+        block_bytes = c_loc * n_loc * 8
+        # where MY block (my columns) lands inside rank g's receive buffer
+        self.shard_ptrs = [int(self.hdl.buffer_ptrs[g]) + self.hdl.rank * block_bytes for g in range(G)]
+        self.shape = (G, c_loc, n_loc)
+
+    def barrier(self):
+        self.hdl.barrier()
 
 
 @dataclass
@@ -69,12 +94,14 @@ def _log2(x: int) -> int:
 
 def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, cap_height: int, hash_kind: int,
                    engine, group=None, from_coeffs: bool = False, want_leaves: bool = True,
-                   scratch: Optional[dict] = None) -> ShardedBatch:
+                   scratch: Optional[dict] = None, exchange: str = "nccl") -> ShardedBatch:
     """PolynomialBatch::from_values / from_coeffs of one (ncols_total x n) batch over ``group``.
 
     ``cols_local``: this rank's columns, shape (ncols_total / G, n).  Requirements: G is a power of two,
     G divides ncols_total, and G <= 2^cap_height (every rank owns whole cap subtrees).
-    ``scratch`` may hold reusable buffers (keys: coeffs, send, recv, leaves, digests, cap_local, cap)."""
+    ``scratch`` may hold reusable buffers (keys: coeffs, send, recv, leaves, digests, cap_local, cap).
+    ``exchange``: "nccl" = LDE into a send buffer + ``all_to_all_single``; "peer" = the LDE kernel stores
+    straight into the peers' receive buffers (symmetric memory over NVLink), no all-to-all."""
     G = dist.get_world_size(group)
     g = dist.get_rank(group)
     glog = _log2(G)
@@ -103,15 +130,26 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
         engine.canonical_copy(cols_local, coeffs)
     else:
         engine.intt(cols_local, coeffs)
-    # 2. LDE written leaf-ordered and blocked by destination rank: send[s] = (c_loc, n_loc) block for rank s
-    send = buf("send", (G, c_loc, n_loc))
-    engine.coset_lde(coeffs, send, rate_bits, glog)
-    # 3. the one exchange of the path
-    if G > 1:
-        recv = buf("recv", (G, c_loc, n_loc))
-        dist.all_to_all_single(recv, send, group=group)
+    if exchange == "peer" and G > 1:
+        # 2+3 fused: every rank's LDE kernel writes block s of its output into rank s's receive buffer
+        ex = sc.get("peer_exchange")
+        if ex is None or ex.shape != (G, c_loc, n_loc):
+            ex = PeerExchange(G, c_loc, n_loc, group)
+            sc["peer_exchange"] = ex
+        ex.barrier()   # peers are done reading what the previous step put into my buffer
+        engine.coset_lde_peer(coeffs, ex.shard_ptrs, n_loc, rate_bits)
+        ex.barrier()   # every block of my receive buffer has landed
+        recv = ex.recv
     else:
-        recv = send
+        # 2. LDE written leaf-ordered and blocked by destination rank: send[s] = (c_loc, n_loc) block for rank s
+        send = buf("send", (G, c_loc, n_loc))
+        engine.coset_lde(coeffs, send, rate_bits, glog)
+        # 3. the one exchange of the path
+        if G > 1:
+            recv = buf("recv", (G, c_loc, n_loc))
+            dist.all_to_all_single(recv, send, group=group)
+        else:
+            recv = send
     # recv[s][j] is column s*c_loc + j restricted to my leaves: a (ncols_total, n_loc) column-major LDE
     lde_rows = recv.view(ncols_total, n_loc)
     # 4. my leaves, my subtrees

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_dir):
+def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_dir, exchange):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -27,7 +27,7 @@ def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_di
     cols = field_elems(0xBEEF, (ncols, 1 << n_log))
     c_loc = ncols // world
     mine = torch.from_numpy(cols[rank * c_loc:(rank + 1) * c_loc].view(np.int64).copy()).cuda()
-    res = commit_sharded(mine, ncols, rate_bits, cap_height, kind, CudaEngine())
+    res = commit_sharded(mine, ncols, rate_bits, cap_height, kind, CudaEngine(), exchange=exchange)
     torch.cuda.synchronize()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), coeffs=res.coeffs.cpu().numpy().view(np.uint64),
              leaves=res.leaves.cpu().numpy().view(np.uint64), digests=res.digests.cpu().numpy().view(np.uint64),
@@ -36,8 +36,9 @@ def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_di
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
 @pytest.mark.parametrize("ncols,n_log,kind", [(16, 12, 0), (6, 15, 1)])
-def test_sharded_nccl_equals_oracle(tmp_path, oracle, ncols, n_log, kind):
+def test_sharded_nccl_equals_oracle(tmp_path, oracle, ncols, n_log, kind, exchange):
     import torch
     import torch.multiprocessing as mp
 
@@ -47,7 +48,7 @@ def test_sharded_nccl_equals_oracle(tmp_path, oracle, ncols, n_log, kind):
     from util import field_elems
 
     port = 29600 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, ncols, n_log, 3, 4, kind, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, ncols, n_log, 3, 4, kind, str(tmp_path), exchange), nprocs=world, join=True)
     cols = field_elems(0xBEEF, (ncols, 1 << n_log))
     ref = oracle.commit(cols, 3, 4, kind)
     parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
