@@ -56,7 +56,7 @@ def parse_args():
                          "commitment traces, independent proofs per GPU (configs[1]/[4])")
     ap.add_argument("--proofs", type=int, default=64, help="trace workload: proofs per GPU per step")
     ap.add_argument("--streams", type=int, default=4, help="trace workload: proofs in flight per GPU")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
                     help="N > 1: peer = LDE kernel stores into the peers' buffers over NVLink; nccl = all_to_all_single")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -226,12 +226,14 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi is started before the warm-up so that its start-up (it takes driver locks) cannot land
+    # inside the timed region; it keeps sampling through it
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         step()
     barrier()
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream, max over ranks ----
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     D.profile_enable(True)
     D.profile_report()  # drop warm-up records
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -486,10 +488,10 @@ def run_trace(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(max(a.warmup, 3)):
         runner.run(a.streams)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = G.launch_count()
     e0.record()
