@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--workload", default="wide", choices=["wide", "trace"],
                     help="wide: one 2^20 x 256 batch (BASELINE configs[2], the contract line); trace: mp2 leaf-proof "
                          "commitment traces, independent proofs per GPU (configs[1]/[4])")
+    ap.add_argument("--trace", default="leaf", choices=["leaf", "aggregation"],
+                    help="leaf: mp2-v1 values-extraction leaf proof (configs[1]); aggregation: 2-proof universal-verifier "
+                         "aggregation (configs[3])")
     ap.add_argument("--proofs", type=int, default=64, help="trace workload: proofs per GPU per step")
     ap.add_argument("--streams", type=int, default=4, help="trace workload: proofs in flight per GPU")
     ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
@@ -429,14 +432,14 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
 # ------------------------------------------------------------------------------------------------
 # proof-trace replay (map stage): independent proofs, one GPU each, no collective
 # ------------------------------------------------------------------------------------------------
-def cpu_trace_time(kind, threads):
-    """One leaf-proof trace on the CPU restatement (oracle/)."""
+def cpu_trace_time(kind, threads, degrees):
+    """One proof trace on the CPU restatement (oracle/)."""
     import oracle as O
     from mapreduce_plonky2_b200 import trace as T
 
     O.build()
     t0 = time.perf_counter()
-    for i, op in enumerate(T.proof_ops()):
+    for i, op in enumerate(T.proof_ops(degrees)):
         if op.kind == "merkle":
             leaves = synthetic_columns(0x7000 + i, (1 << op.n_log, op.ncols))
             O.merkle_new(leaves, min(T.CAP_HEIGHT, op.n_log), kind, nthreads=threads)
@@ -454,15 +457,20 @@ def run_trace(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     kind = 0 if a.hash == "poseidon" else 1
-    name = ("map stage: %d independent mp2-v1 leaf-proof commitment traces per GPU (prove() degrees 2^14, 2^13, 2^12 "
-            "ASSUMED; %s; trace replay = upper bound on proofs/s)") % (a.proofs, a.hash)
+    from mapreduce_plonky2_b200 import trace as T0
+
+    degrees = T0.LEAF_PROOF_DEGREES if a.trace == "leaf" else T0.AGGREGATION_DEGREES
+    name = ("map stage: %d independent %s commitment traces per GPU (prove() degrees %s ASSUMED; %s; trace replay = "
+            "upper bound on proofs/s)") % (a.proofs, "mp2-v1 leaf-proof" if a.trace == "leaf" else
+                                           "2-proof universal-verifier aggregation",
+                                           ", ".join("2^%d" % d for d in degrees), a.hash)
     if a.impl == "reference":
         if rank == 0:
             import oracle as O
             threads = O.max_threads()
-            dt = [cpu_trace_time(kind, threads) for _ in range(max(1, min(a.steps, 3)))]
+            dt = [cpu_trace_time(kind, threads, degrees) for _ in range(max(1, min(a.steps, 3)))]
             v = len(dt) / sum(dt)
-            print(json.dumps({"impl": "reference", "metric": "mp2 leaf proofs/s (commitment trace)", "value": v,
+            print(json.dumps({"impl": "reference", "metric": "mp2 proofs/s (commitment trace)", "value": v,
                               "unit": "proofs/s", "n_gpus": a.gpus, "steps": len(dt), "warmup": 0,
                               "ms_per_step": 1e3 * sum(dt) / len(dt), "higher_is_better": True, "scaling": "weak",
                               "vs_baseline": None, "dtype": "u64 (Goldilocks field)", "data": "synthetic",
@@ -480,7 +488,7 @@ def run_trace(a):
     from mapreduce_plonky2_b200 import trace as T
 
     G.init(local_rank)
-    runner = T.TraceRunner(T.LEAF_PROOF_DEGREES, kind, a.streams)
+    runner = T.TraceRunner(degrees, kind, a.streams)
     launches0 = G.launch_count()
 
     def barrier():
@@ -511,7 +519,7 @@ def run_trace(a):
         perms = runner.perms_per_proof
         ip = __import__("mapreduce_plonky2_b200.device", fromlist=["x"]).int_pipe_peak()
         mads = perms * a.proofs * PERM_MADS / (ms_step * 1e-3) / 1e12
-        line = {"metric": "mp2 leaf proofs/s (commitment trace)", "value": value, "unit": "proofs/s", "n_gpus": world,
+        line = {"metric": "mp2 proofs/s (commitment trace)", "value": value, "unit": "proofs/s", "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u64 (Goldilocks field, integer)", "data": "synthetic",
                 "config": {"workload": name, "parallelism": "replicas only (one proof stream set per GPU, no collective)",
@@ -526,7 +534,7 @@ def run_trace(a):
         if not a.no_cpu_baseline and world == 1:
             import oracle as O
             threads = O.max_threads()
-            dt = cpu_trace_time(kind, threads)
+            dt = cpu_trace_time(kind, threads, degrees)
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
                                     "sample": "one proof trace (%.1f s)" % dt}
         print(json.dumps(line), flush=True)
