@@ -202,15 +202,13 @@ static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n
 
 
 // ---- leaf-hash launch shape ----------------------------------------------------------------------
-// A leaf is an indivisible unit (a sequential sponge of ceil(ncols/8) permutations), so with T
-// resident threads per SM the kernel takes ceil(nleaves / (nSM*T)) "waves".  2^17 leaves on 148 SMs
-// are 885.6 leaves per SM: T = 640 (what the register budget allows) needs two waves at 69 %
-// efficiency, T = 448 needs two at 99 %.  We therefore pick the block size and cap the resident CTAs
-// per SM (by asking for dynamic shared memory we never touch) to minimise ceil(waves)*T.
+// 128-thread CTAs (4 warps kept in step by the per-round barrier), as many resident as the register
+// file allows (5-6).  A leaf is an indivisible unit, so 2^17 leaves on 148 SMs quantise into 1.4 "waves";
+// capping the resident CTAs to even that out was measured to change nothing (the SM's throughput scales
+// with its resident warps), so the only knob left is MP2_HASH_CTAS for experiments: it caps the resident
+// CTAs per SM by requesting dynamic shared memory that is never touched.
 struct HashLaunch {
-  int block;        // threads per CTA
-  int ctas_per_sm;  // resident CTAs per SM we want
-  size_t smem;      // dynamic shared memory that enforces it (0 = no cap)
+  size_t smem;  // dynamic shared memory that enforces the cap (0 = none)
 };
 
 static int env_int(const char *name, int dflt) {
@@ -219,42 +217,16 @@ static int env_int(const char *name, int dflt) {
 }
 
 template <typename K>
-static Status plan_hash_launch(K kernel, int block, size_t nthreads, int max_regs_ctas, HashLaunch *out) {
-  int dev = 0, nsm = 0;
-  MP2_CUDA(cudaGetDevice(&dev));
-  MP2_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  int kmax = 0;
-  MP2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&kmax, kernel, block, 0));
-  if (kmax < 1) return "leaf-hash kernel cannot be resident";
-  if (max_regs_ctas > 0 && kmax > max_regs_ctas) kmax = max_regs_ctas;
-  int forced = env_int("MP2_HASH_CTAS", 0);
-  int best_k = kmax;
-  if (forced > 0) {
-    best_k = forced < kmax ? forced : kmax;
-  } else {
-    // fewer than ~12 warps per SM no longer hides the arithmetic latency: do not go below that
-    int kmin = (384 + block - 1) / block;
-    if (kmin > kmax) kmin = kmax;
-    double best_cost = 1e300;
-    for (int k = kmax; k >= kmin; k--) {
-      double per_wave = (double)nsm * k * block;
-      double waves = (double)((nthreads + (size_t)per_wave - 1) / (size_t)per_wave);
-      double cost = waves * k * block;  // ~ time, if an SM's throughput does not depend on k
-      if (cost < best_cost * 0.97) {    // prefer more resident warps unless the gain is real
-        best_cost = cost;
-        best_k = k;
-      }
-    }
-  }
-  out->block = block;
-  out->ctas_per_sm = best_k;
+static Status plan_hash_launch(K kernel, int block, size_t nthreads, int, HashLaunch *out) {
+  (void)block;
+  (void)nthreads;
   out->smem = 0;
-  if (best_k < kmax) {
-    size_t per = (size_t)(228 * 1024) / best_k - 1024;  // each CTA also reserves 1 KB
+  const int forced = env_int("MP2_HASH_CTAS", 0);
+  if (forced > 0) {
+    size_t per = (size_t)(228 * 1024) / forced - 1024;  // each CTA also reserves 1 KB
     per &= ~(size_t)127;
     if (per > 227 * 1024) per = 227 * 1024;
     MP2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per));
-    MP2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     out->smem = per;
   }
   return "";
