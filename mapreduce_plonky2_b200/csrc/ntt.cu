@@ -30,7 +30,15 @@
 namespace mp2 {
 
 static const u32 kMaxSingleLog = 14;  // 2^14 * 8 B = 128 KB of the 227 KB shared memory
-static const u32 kTileLog = 13;       // target tile (elements) when several lines share a CTA
+// Tile = 2^12 elements (32 KB) and 256 threads: 4 resident CTAs per SM whose load / transform / store
+// phases interleave.  2^13-element tiles (2 resident CTAs) were 8 % slower on the 2^20 four-step path.
+#ifndef MP2_NTT_TILE_LOG
+#define MP2_NTT_TILE_LOG 12
+#endif
+#ifndef MP2_NTT_THREADS_SHIFT
+#define MP2_NTT_THREADS_SHIFT 4  // threads = tile >> shift on the big tiles (2 radix-8 items per thread and pass)
+#endif
+static const u32 kTileLog = MP2_NTT_TILE_LOG;  // target tile (elements) when several lines share a CTA
 
 struct LdeMap {  // (column c, leaf L) -> address in the leaf-ordered, column-major, shardable buffer
   u32 ls_log;    // log2(leaves per shard)
@@ -52,6 +60,13 @@ struct LdeMap {  // (column c, leaf L) -> address in the leaf-ordered, column-ma
 // at the end of the network have 8-way bank conflicts (half of all wavefronts) and the twiddle loads show up
 // as long_scoreboard stalls, yet removing either changes the run time by < 4 % on B200 (measured, all four
 // combinations): the transform is bound by the alu pipe (62-75 % busy), so both stay off.
+// Staging batch: every global->shared staging loop first issues MP2_NTT_BATCH independent global loads per
+// thread (data, coset scale, four-step twiddle) and only then consumes them.  ncu's source view of the first
+// two-pass kernels showed 33 % (pass 1) / 25 % (pass 2) of all stall samples on the first consumer of those
+// loads: one load in flight per thread leaves the DRAM/L2 latency exposed.
+#ifndef MP2_NTT_BATCH
+#define MP2_NTT_BATCH 4
+#endif
 #ifndef MP2_NTT_SKEW
 #define MP2_NTT_SKEW 0
 #endif
@@ -206,9 +221,19 @@ k_intt_single(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ ou
               u32 s, u32 lines_log, const u64 *__restrict__ W, u64 n_inv) {
   extern __shared__ u64 sm[];
   const u32 S = 1u << s, c0 = blockIdx.x << lines_log;
-  for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
-    u32 p = e & (S - 1), l = e >> s, c = c0 + l;
-    sm[sidx(((size_t)p << lines_log) + l)] = c < ncols ? in[(size_t)c * in_stride + p] : 0;
+  const u32 total = S << lines_log, nthr = blockDim.x;
+  for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
+    u64 v[MP2_NTT_BATCH];
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> s, c = c0 + l;
+      v[b] = (e < total && c < ncols) ? in[(size_t)c * in_stride + p] : 0;
+    }
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> s;
+      if (e < total) sm[sidx(((size_t)p << lines_log) + l)] = v[b];
+    }
   }
   __syncthreads();
   smem_ntt(sm, s, lines_log, W);
@@ -227,9 +252,21 @@ k_lde_single(const u64 *__restrict__ coeffs, size_t in_stride, u64 *__restrict__
   extern __shared__ u64 sm[];
   const u32 S = 1u << s, c0 = blockIdx.x << lines_log, k = blockIdx.y;
   const u64 *sc = scale + ((size_t)k << s);  // (7*w_N^k)^j
-  for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
-    u32 p = e & (S - 1), l = e >> s, c = c0 + l;
-    sm[sidx(((size_t)p << lines_log) + l)] = c < ncols ? gl_mul(coeffs[(size_t)c * in_stride + p], __ldg(sc + p)) : 0;
+  const u32 total = S << lines_log, nthr = blockDim.x;
+  for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
+    u64 v[MP2_NTT_BATCH], f[MP2_NTT_BATCH];
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> s, c = c0 + l;
+      const bool ok = e < total && c < ncols;
+      v[b] = ok ? coeffs[(size_t)c * in_stride + p] : 0;
+      f[b] = ok ? __ldg(sc + p) : 0;
+    }
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> s;
+      if (e < total) sm[sidx(((size_t)p << lines_log) + l)] = gl_mul(v[b], f[b]);
+    }
   }
   __syncthreads();
   smem_ntt(sm, s, lines_log, W);
@@ -259,22 +296,41 @@ k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, siz
   const size_t n2 = (size_t)1 << tp.b;
   const size_t c = blockIdx.y, k = blockIdx.z, q0 = (size_t)blockIdx.x * LINES;
   const u64 *sc = tp.inverse ? nullptr : scale + (k << tp.n_log);
-  for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
-    u32 l = e & (LINES - 1), p = e >> tp.lines_log;
-    size_t j = (size_t)p * n2 + q0 + l;
-    u64 v = in[c * in_stride + j];
-    if (!tp.inverse) v = gl_mul(v, __ldg(sc + j));
-    sm[sidx(e)] = v;  // element p*LINES + l
+  const u32 total = S << tp.lines_log, nthr = blockDim.x;
+  for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
+    u64 v[MP2_NTT_BATCH], f[MP2_NTT_BATCH];
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, l = e & (LINES - 1), p = e >> tp.lines_log;
+      size_t j = (size_t)p * n2 + q0 + l;
+      v[b] = e < total ? in[c * in_stride + j] : 0;
+      f[b] = (e < total && !tp.inverse) ? __ldg(sc + j) : 1;
+    }
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr;
+      if (e < total) sm[sidx(e)] = tp.inverse ? v[b] : gl_mul(v[b], f[b]);  // element p*LINES + l
+    }
   }
   __syncthreads();
   smem_ntt(sm, tp.a, tp.lines_log, W1);
   const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
-  for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
-    u32 l = e & (LINES - 1), p = e >> tp.lines_log;
-    size_t j2 = q0 + l, k1 = brev_bits(p, tp.a);
-    u64 v = gl_mul(sm[sidx(e)], __ldg(Wn + j2 * k1));  // j2*k1 < n
-    if (tp.inverse) out[c * out_stride + k1 * n2 + j2] = v;       // row k1 (natural)
-    else out[map(block_base + (size_t)p * n2 + j2, c)] = v;       // row bitrev(k1) = p
+  for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
+    u64 w[MP2_NTT_BATCH];
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, l = e & (LINES - 1), p = e >> tp.lines_log;
+      w[b] = e < total ? __ldg(Wn + (q0 + l) * (size_t)brev_bits(p, tp.a)) : 0;  // w_n^(j2*k1), j2*k1 < n
+    }
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, l = e & (LINES - 1), p = e >> tp.lines_log;
+      if (e >= total) continue;
+      size_t j2 = q0 + l, k1 = brev_bits(p, tp.a);
+      u64 v = gl_mul(sm[sidx(e)], w[b]);
+      if (tp.inverse) out[c * out_stride + k1 * n2 + j2] = v;       // row k1 (natural)
+      else out[map(block_base + (size_t)p * n2 + j2, c)] = v;       // row bitrev(k1) = p
+    }
   }
 }
 
@@ -288,11 +344,20 @@ k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, siz
   const size_t n = (size_t)1 << tp.n_log, n1 = (size_t)1 << tp.a, n2 = (size_t)1 << tp.b;
   const size_t c = blockIdx.y, k = blockIdx.z, r0 = (size_t)blockIdx.x * LINES;
   const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
-  for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
-    u32 p = e & (S - 1), l = e >> tp.b;
-    size_t row = r0 + l;
-    sm[sidx(((size_t)p << tp.lines_log) + l)] =
-        tp.inverse ? in[c * in_stride + row * n2 + p] : in[map(block_base + row * n2 + p, c)];
+  const u32 total = S << tp.lines_log, nthr = blockDim.x;
+  for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
+    u64 v[MP2_NTT_BATCH];
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> tp.b;
+      size_t row = r0 + l;
+      v[b] = e >= total ? 0 : tp.inverse ? in[c * in_stride + row * n2 + p] : in[map(block_base + row * n2 + p, c)];
+    }
+#pragma unroll
+    for (int b = 0; b < MP2_NTT_BATCH; b++) {
+      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> tp.b;
+      if (e < total) sm[sidx(((size_t)p << tp.lines_log) + l)] = v[b];
+    }
   }
   __syncthreads();
   smem_ntt(sm, tp.b, tp.lines_log, W2);
@@ -326,7 +391,7 @@ static u32 ceil_log2(size_t x) {
 }
 static u32 threads_for(u32 tile_log) {
   u32 t = tile_log >= 3 ? 1u << (tile_log - 3) : 1;  // one radix-8 item per thread and pass...
-  if (tile_log >= 13) t = 1u << (tile_log - 4);      // ...two on the big tiles (<= 1024 threads)
+  if (tile_log >= 12) t = 1u << (tile_log - MP2_NTT_THREADS_SHIFT);  // ...more on the big tiles (<= 1024 threads)
   if (t > 1024) t = 1024;
   if (t < 32) t = 32;
   return t;
