@@ -116,6 +116,33 @@ const char *mp2gpu_batch_shape(const mp2gpu_batch *b, size_t *ncols, uint32_t *n
                                uint32_t *rate_bits, uint32_t *cap_height, uint32_t *hash_kind);
 void mp2gpu_batch_free(mp2gpu_batch *b);
 
+/* ---- FRI commit phase (plonky2 fri/prover.rs fri_committed_trees; runs inside every prove(), e.g.
+ *      recursion-framework/src/circuit_builder.rs:308) -- device-resident loop state --------------------
+ * Extension elements (D = 2, mp2-common/src/lib.rs:36) are interleaved pairs [a0, a1].  Usage, per proof:
+ *   mp2gpu_fri_begin(final_poly coefficients, degree_log, rate_bits, cap_height, hash_kind, &f);
+ *   for arity_bits in fri_params.reduction_arity_bits:
+ *       mp2gpu_fri_commit_layer(f, arity_bits, cap);   // MerkleTree::new(chunked values, cap_height)
+ *       challenger.observe_cap(cap); beta = challenger.get_extension_challenge();   // host, tiny
+ *       mp2gpu_fri_fold(f, beta);                       // reduce_with_powers + coset_fft(shift^arity)
+ *   mp2gpu_fri_finish(f, final_coeffs, &len);           // already truncated by rate_bits
+ * The layer trees stay on the device for the query phase (mp2gpu_fri_fetch_layer).  The values of the first
+ * layer are computed here from the coefficients (plonky2 passes both; they are the same function of them). */
+typedef struct mp2gpu_fri mp2gpu_fri;
+/* coeffs_ext: 2^n_log extension coefficients (the non-padded final polynomial; its lde(rate_bits) is implied). */
+const char *mp2gpu_fri_begin(const uint64_t *coeffs_ext, uint32_t n_log, uint32_t rate_bits,
+                             uint32_t cap_height, uint32_t hash_kind, mp2gpu_fri **out);
+/* cap_out: 2^cap_height x 4. */
+const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t *cap_out);
+const char *mp2gpu_fri_fold(mp2gpu_fri *f, const uint64_t beta[2]);
+const char *mp2gpu_fri_layer_shape(const mp2gpu_fri *f, uint32_t layer, size_t *nleaves, size_t *leaf_len,
+                                   size_t *ndigests, size_t *ncap);
+/* Any output may be NULL; sizes from mp2gpu_fri_layer_shape. */
+const char *mp2gpu_fri_fetch_layer(const mp2gpu_fri *f, uint32_t layer, uint64_t *leaves_out,
+                                   uint64_t *digests_out, uint64_t *cap_out);
+/* final_coeffs_out: *len_out extension coefficients (interleaved); may be NULL to query the length. */
+const char *mp2gpu_fri_finish(mp2gpu_fri *f, uint64_t *final_coeffs_out, size_t *len_out);
+void mp2gpu_fri_free(mp2gpu_fri *f);
+
 /* ---- device-pointer stages (inputs already resident in HBM; asynchronous on `stream`, a
  *      cudaStream_t passed as void*: NULL is CUDA's legacy default stream, MP2GPU_STREAM_THREAD the
  *      calling thread's private library stream).  These are what the multi-GPU driver and bench.py's

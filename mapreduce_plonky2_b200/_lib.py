@@ -45,6 +45,13 @@ SIGNATURES = {
     "mp2gpu_batch_fetch": (_ERR, [C.c_void_p, u64pp, u64p, u64p, u64p]),
     "mp2gpu_batch_shape": (_ERR, [C.c_void_p, size_p, u32p, u32p, u32p, u32p]),
     "mp2gpu_batch_free": (None, [C.c_void_p]),
+    "mp2gpu_fri_begin": (_ERR, [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "mp2gpu_fri_commit_layer": (_ERR, [C.c_void_p, C.c_uint32, u64p]),
+    "mp2gpu_fri_fold": (_ERR, [C.c_void_p, u64p]),
+    "mp2gpu_fri_layer_shape": (_ERR, [C.c_void_p, C.c_uint32, size_p, size_p, size_p, size_p]),
+    "mp2gpu_fri_fetch_layer": (_ERR, [C.c_void_p, C.c_uint32, u64p, u64p, u64p]),
+    "mp2gpu_fri_finish": (_ERR, [C.c_void_p, u64p, size_p]),
+    "mp2gpu_fri_free": (None, [C.c_void_p]),
     "mp2gpu_dev_intt": (_ERR, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]),
     "mp2gpu_dev_coset_lde": (_ERR, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p]),

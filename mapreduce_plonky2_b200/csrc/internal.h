@@ -74,9 +74,11 @@ inline u64 h_root_of_unity(u32 log_n) {
 // ---- device tables, cached per device (tables.cu) ----
 // W[m] = w_T^m for m < T = 2^log_t (T >= 1)
 Status table_roots(u32 log_t, cudaStream_t st, const u64 **out);
-// scale[(k << log_n) + j] = (7 * w_N^k)^j for k < 2^rate_bits, j < 2^log_n, N = 2^(log_n + rate_bits):
-// the coset pre-scaling of PolynomialCoeffs::coset_fft (shift = MULTIPLICATIVE_GROUP_GENERATOR = 7)
-Status table_coset_scale(u32 log_n, u32 rate_bits, cudaStream_t st, const u64 **out);
+// scale[(k << log_n) + j] = (shift * w_N^k)^j for k < 2^rate_bits, j < 2^log_n, N = 2^(log_n + rate_bits):
+// the coset pre-scaling of PolynomialCoeffs::coset_fft (shift = MULTIPLICATIVE_GROUP_GENERATOR = 7 for the
+// polynomial batches; 7^(arity^i) for FRI layer i)
+static const u64 kCosetShift = 7;
+Status table_coset_scale(u32 log_n, u32 rate_bits, u64 shift, cudaStream_t st, const u64 **out);
 
 // ---- transforms (ntt.cu) ----
 Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_stride, size_t ncols,
@@ -85,7 +87,16 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
 // (column c at + c*lde_stride) instead of lde + g*shard_stride -- the exchange fused into the store.
 Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols,
                      u32 n_log, u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st,
-                     u64 *const *peer_bases = nullptr);
+                     u64 *const *peer_bases = nullptr, u64 shift = kCosetShift);
+
+// ---- FRI commit phase (fri.cu) ----
+// coeffs' = chunks(2^arity_bits) reduced with powers of beta; ext polys are component-major (2 x len)
+Status fri_fold(const u64 *coeffs, size_t in_stride, u64 *out, size_t out_stride, size_t out_len, u32 arity_bits,
+                u64 beta0, u64 beta1, cudaStream_t st);
+// out[2*pos + comp] = vals[comp*stride + pos]: leaf-ordered ext values -> flattened FRI leaves
+Status fri_interleave(const u64 *vals, size_t stride, u64 *out, size_t len, cudaStream_t st);
+// inverse: interleaved host layout -> component-major (canonicalised)
+Status fri_deinterleave(const u64 *in, u64 *out, size_t stride, size_t len, cudaStream_t st);
 Status ntt_canonicalize(const u64 *in, size_t in_stride, u64 *out, size_t out_stride, size_t ncols,
                         size_t n, cudaStream_t st);
 

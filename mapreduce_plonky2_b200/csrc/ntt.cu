@@ -474,14 +474,15 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
 }
 
 Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols, u32 n_log,
-                     u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st, u64 *const *peer_bases) {
+                     u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st, u64 *const *peer_bases,
+                     u64 shift) {
   if (ncols == 0) return "";
   const u32 N_log = n_log + rate_bits;
   if (N_log > 32) return "n_log + rate_bits exceeds the field's two-adicity (32)";
   if (shard_log > N_log) return "shard_log larger than log2(number of leaves)";
   if (rate_bits > 15) return "rate_bits too large";
   const u64 *scale = nullptr;
-  MP2_TRY(table_coset_scale(n_log, rate_bits, st, &scale));
+  MP2_TRY(table_coset_scale(n_log, rate_bits, shift, st, &scale));
   LdeMap map = {};
   map.ls_log = N_log - shard_log;
   map.shard_stride = shard_log ? shard_stride : 0;

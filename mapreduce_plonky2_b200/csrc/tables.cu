@@ -24,12 +24,14 @@ __global__ void k_fill_coset_scale(u64 *out, const u64 *bases, u32 log_n, size_t
 namespace {
 struct Key {
   int device;
-  int kind;  // 0 roots, 1 shift powers
+  int kind;  // 0 roots, 2 + rate_bits coset scale
   u32 log;
+  u64 shift;  // coset shift of a scale table (0 for root tables)
   bool operator<(const Key &o) const {
     if (device != o.device) return device < o.device;
     if (kind != o.kind) return kind < o.kind;
-    return log < o.log;
+    if (log != o.log) return log < o.log;
+    return shift < o.shift;
   }
 };
 std::mutex g_mu;
@@ -38,7 +40,7 @@ std::map<Key, u64 *> g_tables;
 Status get_table(int kind, u32 log, u64 base, cudaStream_t st, const u64 **out) {
   int dev = 0;
   MP2_CUDA(cudaGetDevice(&dev));
-  Key key = {dev, kind, log};
+  Key key = {dev, kind, log, 0};
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_tables.find(key);
   if (it != g_tables.end()) {
@@ -61,10 +63,10 @@ Status get_table(int kind, u32 log, u64 base, cudaStream_t st, const u64 **out) 
 Status table_roots(u32 log_t, cudaStream_t st, const u64 **out) {
   return get_table(0, log_t, h_root_of_unity(log_t), st, out);
 }
-Status table_coset_scale(u32 log_n, u32 rate_bits, cudaStream_t st, const u64 **out) {
+Status table_coset_scale(u32 log_n, u32 rate_bits, u64 shift, cudaStream_t st, const u64 **out) {
   int dev = 0;
   MP2_CUDA(cudaGetDevice(&dev));
-  Key key = {dev, 2 + (int)rate_bits, log_n};
+  Key key = {dev, 2 + (int)rate_bits, log_n, shift};
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_tables.find(key);
   if (it != g_tables.end()) {
@@ -76,7 +78,7 @@ Status table_coset_scale(u32 log_n, u32 rate_bits, cudaStream_t st, const u64 **
   const u64 wN = h_root_of_unity(log_n + rate_bits);
   u64 wk = 1;
   for (size_t k = 0; k < cosets; k++) {
-    bases[k] = h_mul(7 /* coset_shift() = MULTIPLICATIVE_GROUP_GENERATOR */, wk);
+    bases[k] = h_mul(shift, wk);
     wk = h_mul(wk, wN);
   }
   u64 *d = nullptr, *d_bases = nullptr;

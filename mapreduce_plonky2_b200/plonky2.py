@@ -297,3 +297,77 @@ class PolynomialBatch:
             self.free()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------
+# FRI commit phase (plonky2 fri/prover.rs fri_committed_trees)
+# ------------------------------------------------------------------------------------------------
+class FriCommitPhase:
+    """Device-resident state of one ``fri_committed_trees`` loop (extension elements are [a0, a1] pairs).
+
+    ``final_poly_coeffs``: (n, 2) coefficients of the batched opening polynomial *before* ``lde(rate_bits)``
+    (the zero padding is implied).  Per reduction layer: :meth:`commit_layer` = ``MerkleTree::new(chunked
+    values, cap_height)``, then the caller's challenger yields ``beta``, then :meth:`fold` =
+    ``reduce_with_powers`` per chunk + ``coset_fft(shift^arity)``."""
+
+    def __init__(self, final_poly_coeffs, rate_bits: int, cap_height: int, hash_kind: int = POSEIDON2):
+        c = _arr(final_poly_coeffs, 2)
+        n = c.shape[0]
+        n_log = int(n).bit_length() - 1
+        if c.shape[1] != 2 or n == 0 or (1 << n_log) != n:
+            raise Mp2GpuError("final polynomial must be (2^k, 2) extension coefficients")
+        self.hash_kind, self.cap_height, self.rate_bits = hash_kind, cap_height, rate_bits
+        self._h = C.c_void_p(None)
+        self.num_layers = 0
+        _lib.call("mp2gpu_fri_begin", _ptr(c), n_log, rate_bits, cap_height, hash_kind, C.byref(self._h))
+
+    def commit_layer(self, arity_bits: int) -> MerkleCap:
+        cap = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
+        _lib.call("mp2gpu_fri_commit_layer", self._h, arity_bits, _ptr(cap))
+        self.num_layers += 1
+        return MerkleCap(cap)
+
+    def fold(self, beta) -> None:
+        b = _arr(beta).reshape(2)
+        _lib.call("mp2gpu_fri_fold", self._h, _ptr(b))
+
+    def layer(self, i: int) -> MerkleTree:
+        nl, ll, nd, nc = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        _lib.call("mp2gpu_fri_layer_shape", self._h, i, C.byref(nl), C.byref(ll), C.byref(nd), C.byref(nc))
+        leaves = np.zeros((nl.value, ll.value), dtype=np.uint64)
+        digests = np.zeros((nd.value, 4), dtype=np.uint64)
+        cap = np.zeros((nc.value, 4), dtype=np.uint64)
+        _lib.call("mp2gpu_fri_fetch_layer", self._h, i, _ptr(leaves), _ptr(digests) if nd.value else None, _ptr(cap))
+        return MerkleTree(leaves, digests, MerkleCap(cap), self.hash_kind)
+
+    def finish(self) -> np.ndarray:
+        ln = C.c_size_t(0)
+        _lib.call("mp2gpu_fri_finish", self._h, None, C.byref(ln))
+        out = np.zeros((ln.value, 2), dtype=np.uint64)
+        _lib.call("mp2gpu_fri_finish", self._h, _ptr(out), C.byref(ln))
+        return out
+
+    def free(self) -> None:
+        if self._h:
+            _lib.load().mp2gpu_fri_free(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def fri_committed_trees(final_poly_coeffs, reduction_arity_bits, betas, rate_bits: int, cap_height: int,
+                        hash_kind: int = POSEIDON2):
+    """The whole commit phase with the challenger's betas given up front (tests / trace replay).
+    Returns ``(trees, final_coeffs)`` like plonky2's function."""
+    ph = FriCommitPhase(final_poly_coeffs, rate_bits, cap_height, hash_kind)
+    try:
+        for ab, beta in zip(reduction_arity_bits, betas):
+            ph.commit_layer(ab)
+            ph.fold(beta)
+        return [ph.layer(i) for i in range(ph.num_layers)], ph.finish()
+    finally:
+        ph.free()

@@ -546,6 +546,59 @@ int orc_commit(const uint64_t *const *cols, size_t ncols, uint32_t log_n, uint32
   return rc;
 }
 
+/* ------------------------------------------------------------------------- */
+/* a10 / 8(f).2: FRI commit phase pieces (plonky2 fri/prover.rs, restated)      */
+/* ------------------------------------------------------------------------- */
+void orc_ext_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]) { /* X^2 = W = 7 */
+  uint64_t a0 = orc_gl_canon(a[0]), a1 = orc_gl_canon(a[1]), b0 = orc_gl_canon(b[0]), b1 = orc_gl_canon(b[1]);
+  uint64_t c0 = gl_add(gl_mul(a0, b0), gl_mul(7, gl_mul(a1, b1)));
+  uint64_t c1 = gl_add(gl_mul(a0, b1), gl_mul(a1, b0));
+  out[0] = c0;
+  out[1] = c1;
+}
+
+void orc_fri_fold(const uint64_t *coeffs, size_t m, uint32_t arity_bits, const uint64_t beta[2], uint64_t *out) {
+  size_t arity = (size_t)1 << arity_bits;
+  for (size_t j = 0; j < m >> arity_bits; j++) {
+    uint64_t acc[2] = {0, 0}; /* reduce_with_powers: Horner from the last term */
+    for (size_t t = arity; t-- > 0;) {
+      uint64_t prod[2];
+      orc_ext_mul(acc, beta, prod);
+      acc[0] = gl_add(prod[0], orc_gl_canon(coeffs[2 * ((j << arity_bits) + t)]));
+      acc[1] = gl_add(prod[1], orc_gl_canon(coeffs[2 * ((j << arity_bits) + t) + 1]));
+    }
+    out[2 * j] = acc[0];
+    out[2 * j + 1] = acc[1];
+  }
+}
+
+/* the extension's roots of unity of order <= 2^32 are the base field's (EXT_POWER_OF_TWO_GENERATOR^2 =
+ * POWER_OF_TWO_GENERATOR), so the transform acts on the two components separately */
+void orc_coset_fft_ext(const uint64_t *coeffs, uint32_t log_m, uint64_t shift, uint64_t *values) {
+  size_t m = (size_t)1 << log_m;
+  uint64_t *tmp = (uint64_t *)malloc(sizeof(uint64_t) * m);
+  for (int comp = 0; comp < 2; comp++) {
+    uint64_t pw = 1;
+    for (size_t j = 0; j < m; j++) {
+      tmp[j] = gl_mul(coeffs[2 * j + comp], pw);
+      pw = gl_mul(pw, shift);
+    }
+    orc_fft(tmp, log_m);
+    for (size_t j = 0; j < m; j++) values[2 * j + comp] = tmp[j];
+  }
+  free(tmp);
+}
+
+void orc_fri_layer_leaves(const uint64_t *values, uint32_t log_m, uint32_t arity_bits, uint64_t *leaves) {
+  size_t m = (size_t)1 << log_m;
+  for (size_t i = 0; i < m; i++) { /* leaf i>>ab, slot i & (arity-1): value bitrev(i), flattened [a0,a1] */
+    size_t src = bitrev(i, log_m);
+    leaves[2 * i] = orc_gl_canon(values[2 * src]);
+    leaves[2 * i + 1] = orc_gl_canon(values[2 * src + 1]);
+  }
+  (void)arity_bits; /* consecutive groups of 2^arity_bits pairs are the leaves */
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

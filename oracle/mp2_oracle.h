@@ -93,6 +93,17 @@ int orc_commit(const uint64_t *const *cols, size_t ncols, uint32_t log_n, uint32
                uint32_t cap_height, uint32_t hash_kind, int from_coeffs, uint64_t *coeffs_out,
                uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out, int nthreads);
 
+/* ---- FRI commit phase (a10; plonky2 fri/prover.rs fri_committed_trees) -- "next" row 8(f).2 --------
+ * Extension field GF(p^2) = F[X]/(X^2 - 7) (QuadraticExtension<GoldilocksField>, D = 2 at
+ * mp2-common/src/lib.rs:36); elements are interleaved pairs [a0, a1]. */
+void orc_ext_mul(const uint64_t a[2], const uint64_t b[2], uint64_t out[2]);
+/* coeffs' = chunks_exact(2^arity_bits).map(|c| reduce_with_powers(c, beta)):  out[j] = sum_t in[(j<<ab)+t]*beta^t */
+void orc_fri_fold(const uint64_t *coeffs, size_t m, uint32_t arity_bits, const uint64_t beta[2], uint64_t *out);
+/* PolynomialCoeffs<F::Extension>::coset_fft(shift): values[i] = P(shift * w_m^i), natural order */
+void orc_coset_fft_ext(const uint64_t *coeffs, uint32_t log_m, uint64_t shift, uint64_t *values);
+/* reverse_index_bits_in_place(values); chunks(2^arity_bits).map(flatten): (m >> ab) leaves of (2 << ab) elements */
+void orc_fri_layer_leaves(const uint64_t *values, uint32_t log_m, uint32_t arity_bits, uint64_t *leaves);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

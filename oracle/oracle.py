@@ -70,6 +70,10 @@ def lib():
         L.orc_commit.restype = C.c_int
         L.orc_commit.argtypes = [C.POINTER(_u64p), C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
                                  C.c_uint32, C.c_int, _u64p, _u64p, _u64p, _u64p, C.c_int]
+        L.orc_ext_mul.argtypes = [_u64p, _u64p, _u64p]
+        L.orc_fri_fold.argtypes = [_u64p, C.c_size_t, C.c_uint32, _u64p, _u64p]
+        L.orc_coset_fft_ext.argtypes = [_u64p, C.c_uint32, C.c_uint64, _u64p]
+        L.orc_fri_layer_leaves.argtypes = [_u64p, C.c_uint32, C.c_uint32, _u64p]
         L.orc_max_threads.restype = C.c_int
     return _lib
 
@@ -236,3 +240,47 @@ def commit(cols, rate_bits, cap_height, hash_kind=POSEIDON, from_coeffs=False, n
     if rc != 0:
         raise ValueError("commit: bad arguments")
     return {"coeffs": coeffs, "leaves": leaves, "digests": digests, "cap": cap}
+
+
+# ---- FRI commit phase (ext elements as (m, 2) arrays of [a0, a1]) ----
+def ext_mul(a, b) -> np.ndarray:
+    a, b = _arr(a), _arr(b)
+    out = np.zeros(2, dtype=np.uint64)
+    lib().orc_ext_mul(_p(a), _p(b), _p(out))
+    return out
+
+
+def fri_fold(coeffs, arity_bits, beta) -> np.ndarray:
+    c = _arr(coeffs).reshape(-1, 2)
+    out = np.zeros((c.shape[0] >> arity_bits, 2), dtype=np.uint64)
+    lib().orc_fri_fold(_p(c), c.shape[0], arity_bits, _p(_arr(beta)), _p(out))
+    return out
+
+
+def coset_fft_ext(coeffs, shift) -> np.ndarray:
+    c = _arr(coeffs).reshape(-1, 2)
+    out = np.zeros_like(c)
+    lib().orc_coset_fft_ext(_p(c), int(c.shape[0]).bit_length() - 1, shift, _p(out))
+    return out
+
+
+def fri_layer_leaves(values, arity_bits) -> np.ndarray:
+    v = _arr(values).reshape(-1, 2)
+    out = np.zeros_like(v)
+    lib().orc_fri_layer_leaves(_p(v), int(v.shape[0]).bit_length() - 1, arity_bits, _p(out))
+    return out.reshape(v.shape[0] >> arity_bits, 2 << arity_bits)
+
+
+def fri_committed_trees(coeffs, values, arity_bits_list, betas, cap_height, hash_kind=POSEIDON, rate_bits=3):
+    """plonky2 fri_committed_trees with the challenger's betas supplied by the caller.
+    Returns ([(leaves, digests, cap) per layer], final_coeffs truncated by rate_bits)."""
+    coeffs, values = _arr(coeffs).reshape(-1, 2), _arr(values).reshape(-1, 2)
+    shift, trees = 7, []
+    for ab, beta in zip(arity_bits_list, betas):
+        leaves = fri_layer_leaves(values, ab)
+        digests, cap = merkle_new(leaves, min(cap_height, int(leaves.shape[0]).bit_length() - 1), hash_kind)
+        trees.append((leaves, digests, cap))
+        coeffs = fri_fold(coeffs, ab, beta)
+        shift = gl_pow(shift, 1 << ab)
+        values = coset_fft_ext(coeffs, shift)
+    return trees, coeffs[:coeffs.shape[0] >> rate_bits]

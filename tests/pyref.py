@@ -253,3 +253,55 @@ def commit(cols, rate_bits, cap_height, kind=0, from_coeffs=False):
     leaves = [[lde[c][bitrev(i, bits)] for c in range(len(cols))] for i in range(N)]
     digests, cap, _ = merkle_new(leaves, cap_height, kind)
     return {"coeffs": coeffs, "leaves": leaves, "digests": digests, "cap": cap}
+
+
+# ---------------- FRI commit phase (plonky2 fri_committed_trees), by definition ----------------
+def ext_mul(a, b):
+    """GF(p^2) = F[X]/(X^2 - 7)."""
+    return ((a[0] * b[0] + 7 * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def ext_pow(a, e):
+    r = (1, 0)
+    while e:
+        if e & 1:
+            r = ext_mul(r, a)
+        a = ext_mul(a, a)
+        e >>= 1
+    return r
+
+
+def ext_horner(coeffs, x):
+    acc = (0, 0)
+    for c in reversed(coeffs):
+        acc = ext_mul(acc, x)
+        acc = ((acc[0] + c[0]) % P, (acc[1] + c[1]) % P)
+    return acc
+
+
+def fri_committed_trees(coeffs, arity_bits_list, betas, cap_height, kind=0, rate_bits=3):
+    """coeffs: list of ext pairs (zero-padded LDE length).  Every layer is computed from the definition:
+    values[i] = P(shift * w^i) by Horner in the extension field; the fold is
+    P(x) = sum_i x^i P_i(x^r)  ->  sum_i beta^i P_i(x)."""
+    shift, out = 7, []
+    for ab, beta in zip(arity_bits_list, betas):
+        m = len(coeffs)
+        bits = m.bit_length() - 1
+        w = root_of_unity(bits)
+        values = [ext_horner(coeffs, (shift * pow(w, i, P) % P, 0)) for i in range(m)]
+        rev = [values[bitrev(i, bits)] for i in range(m)]
+        arity = 1 << ab
+        leaves = [[x for v in rev[i:i + arity] for x in v] for i in range(0, m, arity)]
+        digests, cap, _ = merkle_new(leaves, min(cap_height, (m >> ab).bit_length() - 1), kind)
+        out.append({"leaves": leaves, "digests": digests, "cap": cap})
+        folded = []
+        for j in range(m >> ab):
+            acc, bp = (0, 0), (1, 0)
+            for t in range(arity):
+                term = ext_mul(coeffs[(j << ab) + t], bp)
+                acc = ((acc[0] + term[0]) % P, (acc[1] + term[1]) % P)
+                bp = ext_mul(bp, beta)
+            folded.append(acc)
+        coeffs = folded
+        shift = pow(shift, arity, P)
+    return out, coeffs[:len(coeffs) >> rate_bits]

@@ -135,3 +135,25 @@ def test_config1_sibling_caps_regression(oracle, case):
                         want_leaves=False)
     assert hexlist(res["cap"]) == case["cap"]
     assert hexlist(np.bitwise_xor.reduce(res["digests"], axis=0)) == case["digest_xor"]
+
+
+def test_fri_commit_phase_oracle_vs_definition(oracle):
+    """oracle.fri_committed_trees (FFT-based) == pyref (Horner in GF(p^2), explicit fold), two layers."""
+    rng = random.Random(9)
+    n_log, r = 6, 3
+    m = 1 << (n_log + r)
+    coeffs = [(rng.randrange(P), rng.randrange(P)) if j < (1 << n_log) else (0, 0) for j in range(m)]
+    arities = [4, 2]
+    betas = [(rng.randrange(P), rng.randrange(P)) for _ in arities]
+    for kind in (0, 1):
+        ref_trees, ref_final = R.fri_committed_trees(coeffs, arities, betas, 2, kind, r)
+        c = np.array(coeffs, dtype=np.uint64)
+        trees, final = oracle.fri_committed_trees(c, oracle.coset_fft_ext(c, 7), arities,
+                                                  np.array(betas, dtype=np.uint64), 2, kind, r)
+        for (lv, dg, cap), rt in zip(trees, ref_trees):
+            assert lv.tolist() == rt["leaves"] and dg.tolist() == rt["digests"] and cap.tolist() == rt["cap"]
+        assert final.tolist() == [list(x) for x in ref_final]
+    # the extension's generator of the 2^33 subgroup squares to the base field's 2-adic generator, so
+    # FFTs commute with the field inclusion (QuadraticExtension<GoldilocksField>::EXT_POWER_OF_TWO_GENERATOR)
+    g = (0, 15659105665374529263)
+    assert R.ext_mul(g, g) == (1753635133440165772, 0)
