@@ -143,6 +143,16 @@ const char *mp2gpu_fri_fetch_layer(const mp2gpu_fri *f, uint32_t layer, uint64_t
 const char *mp2gpu_fri_finish(mp2gpu_fri *f, uint64_t *final_coeffs_out, size_t *len_out);
 void mp2gpu_fri_free(mp2gpu_fri *f);
 
+/* fri_proof_of_work (plonky2 fri/prover.rs): duplex_state = the challenger's sponge state with its pending
+ * inputs already written (12 elements), witness_pos = challenger.input_buffer.len().  Finds the SMALLEST
+ * candidate c such that, with state[witness_pos] = c, permute(state)[7] has >= min_leading_zeros leading zero
+ * bits in canonical form (min_leading_zeros = proof_of_work_bits + 64 - 64 = 16 under
+ * standard_recursion_config).  plonky2 accepts any witness (rayon find_any); the smallest one is the
+ * deterministic rule that makes proofs byte-comparable. */
+const char *mp2gpu_fri_proof_of_work(const uint64_t *duplex_state, uint32_t witness_pos,
+                                     uint32_t min_leading_zeros, uint32_t hash_kind,
+                                     uint64_t *witness_out);
+
 /* ---- device-pointer stages (inputs already resident in HBM; asynchronous on `stream`, a
  *      cudaStream_t passed as void*: NULL is CUDA's legacy default stream, MP2GPU_STREAM_THREAD the
  *      calling thread's private library stream).  These are what the multi-GPU driver and bench.py's

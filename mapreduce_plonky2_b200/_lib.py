@@ -52,6 +52,7 @@ SIGNATURES = {
     "mp2gpu_fri_fetch_layer": (_ERR, [C.c_void_p, C.c_uint32, u64p, u64p, u64p]),
     "mp2gpu_fri_finish": (_ERR, [C.c_void_p, u64p, size_p]),
     "mp2gpu_fri_free": (None, [C.c_void_p]),
+    "mp2gpu_fri_proof_of_work": (_ERR, [u64p, C.c_uint32, C.c_uint32, C.c_uint32, u64p]),
     "mp2gpu_dev_intt": (_ERR, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]),
     "mp2gpu_dev_coset_lde": (_ERR, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p]),

@@ -421,6 +421,28 @@ const char *mp2gpu_permute_batch(uint64_t *states, size_t count, uint32_t hash_k
   });
 }
 
+const char *mp2gpu_fri_proof_of_work(const uint64_t *duplex_state, uint32_t witness_pos, uint32_t min_leading_zeros,
+                                     uint32_t hash_kind, uint64_t *witness_out) {
+  return guarded([&]() -> Status {
+    if (!duplex_state || !witness_out) return "null state / witness_out";
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    if (min_leading_zeros > 40) return "proof_of_work_bits too large";
+    // expected 2^min_lz candidates; batches of 2^20 (one wave of the hash kernel is ~10^5 threads)
+    const u64 batch = (u64)1 << 20;
+    for (u64 start = 0; start < kP; start += batch) {
+      u64 found = ~(u64)0;
+      u64 count = kP - start < batch ? kP - start : batch;
+      MP2_TRY(pow_search((const u64 *)duplex_state, witness_pos, min_leading_zeros, hash_kind, start, count, &found, st));
+      if (found != ~(u64)0) {
+        *witness_out = found;
+        return "";
+      }
+    }
+    return "Proof of work failed. This is highly unlikely!";
+  });
+}
+
 // ---- handle ---------------------------------------------------------------------------------
 const char *mp2gpu_batch_shape(const mp2gpu_batch *b, size_t *ncols, uint32_t *n_log, uint32_t *rate_bits,
                                uint32_t *cap_height, uint32_t *hash_kind) {

@@ -119,6 +119,9 @@ Status hash_no_pad_batch(const u64 *inputs, size_t count, size_t input_len, u32 
 Status two_to_one_batch(const u64 *a, const u64 *b, size_t count, u32 hash_kind, u64 *out,
                         cudaStream_t st);
 Status permute_batch(u64 *states, size_t count, u32 hash_kind, cudaStream_t st);
+// smallest c in [start, start + count) with clz(canon(permute(state | state[pos] = c)[7])) >= min_lz, else ~0
+Status pow_search(const u64 *state12_host, u32 pos, u32 min_lz, u32 hash_kind, u64 start, u64 count, u64 *found,
+                  cudaStream_t st);
 Status gather_rows(const u64 *leaves_rowmajor, const u64 *lde_colmajor, size_t lde_stride,
                    size_t ncols, const u64 *row_idx, size_t nrows, u64 *out, cudaStream_t st);
 

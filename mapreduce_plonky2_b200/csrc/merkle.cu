@@ -187,6 +187,23 @@ k_hash_no_pad(const u64 *__restrict__ in, size_t count, size_t len, u64 *__restr
   if (active) store_digest(out + 4 * t, st);
 }
 
+// fri_proof_of_work: one candidate per thread, smallest hit wins
+struct PowState {
+  u64 s[12];
+};
+template <u32 KIND>
+__global__ void __launch_bounds__(MP2_HASH_BLOCK)
+k_pow_search(PowState init, u32 pos, u32 min_lz, u64 start, u64 count, u64 *__restrict__ best) {
+  const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 cand = start + (t < count ? t : count - 1);
+  u64 st[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) st[i] = (u32)i == pos ? cand : init.s[i];
+  permute<KIND, true>(st);
+  const u64 v = gl_canon(st[7]);  // duplex_state.squeeze().iter().last(), RATE = 8
+  if (t < count && (u32)__clzll((long long)v) >= min_lz) atomicMin(best, cand);
+}
+
 // get_lde_values: out[r][c] = leaf row row_idx[r]
 __global__ void k_gather_rows(const u64 *__restrict__ rowmajor, const u64 *__restrict__ colmajor,
                               size_t stride, u32 ncols, const u64 *__restrict__ row_idx, size_t nrows,
@@ -357,6 +374,25 @@ Status permute_batch(u64 *states, size_t count, u32 hash_kind, cudaStream_t st) 
   if (hash_kind == MP2_HASH_POSEIDON2) { ProfScope _p("k_permute", st); k_permute<MP2_HASH_POSEIDON2><<<g, MP2_HASH_BLOCK, 0, st>>>(states, count); }
   else { ProfScope _p("k_permute", st); k_permute<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(states, count); }
   MP2_LAUNCH_CHECK();
+  return "";
+}
+
+Status pow_search(const u64 *state12_host, u32 pos, u32 min_lz, u32 hash_kind, u64 start, u64 count, u64 *found,
+                  cudaStream_t st) {
+  if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
+  if (pos >= 8) return "witness position must be inside the sponge rate";
+  PowState init;
+  for (int i = 0; i < 12; i++) init.s[i] = state12_host[i];
+  u64 *d_best = nullptr;
+  MP2_CUDA(cudaMallocAsync(&d_best, sizeof(u64), st));
+  MP2_CUDA(cudaMemsetAsync(d_best, 0xFF, sizeof(u64), st));
+  unsigned g = grid_for(count, MP2_HASH_BLOCK);
+  if (hash_kind == MP2_HASH_POSEIDON2) { ProfScope _p("k_pow_search", st); k_pow_search<MP2_HASH_POSEIDON2><<<g, MP2_HASH_BLOCK, 0, st>>>(init, pos, min_lz, start, count, d_best); }
+  else { ProfScope _p("k_pow_search", st); k_pow_search<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(init, pos, min_lz, start, count, d_best); }
+  MP2_LAUNCH_CHECK();
+  MP2_CUDA(cudaMemcpyAsync(found, d_best, sizeof(u64), cudaMemcpyDeviceToHost, st));
+  MP2_CUDA(cudaFreeAsync(d_best, st));
+  MP2_CUDA(cudaStreamSynchronize(st));
   return "";
 }
 

@@ -371,3 +371,11 @@ def fri_committed_trees(final_poly_coeffs, reduction_arity_bits, betas, rate_bit
         return [ph.layer(i) for i in range(ph.num_layers)], ph.finish()
     finally:
         ph.free()
+
+
+def fri_proof_of_work(duplex_state, witness_pos: int, min_leading_zeros: int = 16, hash_kind: int = POSEIDON2) -> int:
+    """``fri_proof_of_work``: smallest PoW witness for the challenger's intermediate duplex state."""
+    st = _arr(duplex_state).reshape(12)
+    w = np.zeros(1, dtype=np.uint64)
+    _lib.call("mp2gpu_fri_proof_of_work", _ptr(st), witness_pos, min_leading_zeros, hash_kind, _ptr(w))
+    return int(w[0])

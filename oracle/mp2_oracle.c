@@ -599,6 +599,23 @@ void orc_fri_layer_leaves(const uint64_t *values, uint32_t log_m, uint32_t arity
   (void)arity_bits; /* consecutive groups of 2^arity_bits pairs are the leaves */
 }
 
+int orc_fri_pow(uint32_t kind, const uint64_t state[12], uint32_t pos, uint32_t min_lz, uint64_t start,
+                uint64_t limit, uint64_t *witness) {
+  for (uint64_t c = start; c < limit; c++) {
+    uint64_t st[12];
+    memcpy(st, state, sizeof st);
+    st[pos] = c;
+    orc_permute(kind, st);
+    uint64_t v = orc_gl_canon(st[7]); /* duplex_state.squeeze().iter().last() with RATE = 8 */
+    uint32_t lz = v ? (uint32_t)__builtin_clzll(v) : 64;
+    if (lz >= min_lz) {
+      *witness = c;
+      return 0;
+    }
+  }
+  return -1;
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

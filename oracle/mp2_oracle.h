@@ -104,6 +104,13 @@ void orc_coset_fft_ext(const uint64_t *coeffs, uint32_t log_m, uint64_t shift, u
 /* reverse_index_bits_in_place(values); chunks(2^arity_bits).map(flatten): (m >> ab) leaves of (2 << ab) elements */
 void orc_fri_layer_leaves(const uint64_t *values, uint32_t log_m, uint32_t arity_bits, uint64_t *leaves);
 
+/* fri_proof_of_work: smallest candidate c >= start such that, with state[pos] = c, permute(state)[7] (the
+ * last squeezed rate element) has >= min_leading_zeros leading zero bits in canonical form.  plonky2 searches
+ * with rayon find_any (any witness is valid); "smallest" is the deterministic rule both sides use here
+ * (SURVEY.md 0.7).  Returns 0 and *witness, or -1 if none below `limit`. */
+int orc_fri_pow(uint32_t hash_kind, const uint64_t state[12], uint32_t pos, uint32_t min_leading_zeros,
+                uint64_t start, uint64_t limit, uint64_t *witness);
+
 int orc_max_threads(void);
 
 #ifdef __cplusplus

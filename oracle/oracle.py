@@ -74,6 +74,8 @@ def lib():
         L.orc_fri_fold.argtypes = [_u64p, C.c_size_t, C.c_uint32, _u64p, _u64p]
         L.orc_coset_fft_ext.argtypes = [_u64p, C.c_uint32, C.c_uint64, _u64p]
         L.orc_fri_layer_leaves.argtypes = [_u64p, C.c_uint32, C.c_uint32, _u64p]
+        L.orc_fri_pow.restype = C.c_int
+        L.orc_fri_pow.argtypes = [C.c_uint32, _u64p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _u64p]
         L.orc_max_threads.restype = C.c_int
     return _lib
 
@@ -284,3 +286,12 @@ def fri_committed_trees(coeffs, values, arity_bits_list, betas, cap_height, hash
         shift = gl_pow(shift, 1 << ab)
         values = coset_fft_ext(coeffs, shift)
     return trees, coeffs[:coeffs.shape[0] >> rate_bits]
+
+
+def fri_pow(state, pos, min_leading_zeros, hash_kind=POSEIDON, start=0, limit=1 << 40):
+    st = _arr(state)
+    w = np.zeros(1, dtype=np.uint64)
+    rc = lib().orc_fri_pow(hash_kind, _p(st), pos, min_leading_zeros, start, limit, _p(w))
+    if rc != 0:
+        raise ValueError("no proof-of-work witness below the limit")
+    return int(w[0])

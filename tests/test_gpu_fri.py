@@ -54,3 +54,19 @@ def test_fri_errors():
     ph.free()
     with pytest.raises(G.Mp2GpuError):
         G.FriCommitPhase(np.ones((6, 2), dtype=np.uint64), 3, 4, 0)
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_fri_proof_of_work_smallest_witness(oracle, kind):
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    for seed, pos, bits in ((1, 0, 8), (2, 3, 12), (3, 7, 16)):
+        state = field_elems(0x90 + seed, (12,))
+        w = G.fri_proof_of_work(state, pos, bits, kind)
+        assert w == oracle.fri_pow(state, pos, bits, kind)
+        # the response really has the leading zeros
+        st = state.copy()
+        st[pos] = w
+        resp = int(oracle.permute(st, kind)[7])
+        assert resp < 1 << (64 - bits)
