@@ -109,6 +109,11 @@ const char *mp2gpu_batch_fetch_rows(const mp2gpu_batch *b, const uint64_t *row_i
 /* MerkleTree::prove on the device-resident digests. */
 const char *mp2gpu_batch_prove(const mp2gpu_batch *b, size_t leaf_index, uint64_t *siblings_out,
                                size_t *nsiblings_out);
+/* Query-phase openings (fri_prover_query_round reads MerkleTree::get + MerkleTree::prove from every oracle
+ * for each of the 28 query indices): rows_out[q] = leaf row leaf_idx[q] (ncols elements), siblings_out[q] =
+ * its (log2 N - cap_height) x 4 sibling digests, bottom-up; gathered on the device, two copies back. */
+const char *mp2gpu_batch_open(const mp2gpu_batch *b, const uint64_t *leaf_idx, size_t count,
+                              uint64_t *rows_out, uint64_t *siblings_out);
 /* Any of the outputs may be NULL. Sizes as for mp2gpu_commit_from_values. */
 const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_out,
                                uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out);
@@ -134,6 +139,9 @@ const char *mp2gpu_fri_begin(const uint64_t *coeffs_ext, uint32_t n_log, uint32_
 /* cap_out: 2^cap_height x 4. */
 const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t *cap_out);
 const char *mp2gpu_fri_fold(mp2gpu_fri *f, const uint64_t beta[2]);
+/* The same for a FRI layer tree (leaves_out[q] = 2 << arity_bits elements). */
+const char *mp2gpu_fri_open_layer(const mp2gpu_fri *f, uint32_t layer, const uint64_t *leaf_idx,
+                                  size_t count, uint64_t *leaves_out, uint64_t *siblings_out);
 const char *mp2gpu_fri_layer_shape(const mp2gpu_fri *f, uint32_t layer, size_t *nleaves, size_t *leaf_len,
                                    size_t *ndigests, size_t *ncap);
 /* Any output may be NULL; sizes from mp2gpu_fri_layer_shape. */

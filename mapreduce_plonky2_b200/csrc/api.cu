@@ -498,6 +498,20 @@ const char *mp2gpu_batch_prove(const mp2gpu_batch *b, size_t leaf_index, uint64_
   });
 }
 
+const char *mp2gpu_batch_open(const mp2gpu_batch *b, const uint64_t *leaf_idx, size_t count, uint64_t *rows_out,
+                              uint64_t *siblings_out) {
+  return guarded([&]() -> Status {
+    if (!b) return "null batch handle";
+    if (count && !leaf_idx) return "null leaf_idx";
+    t_ctx.device = b->device;
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    const size_t N = ((size_t)1 << b->n_log) << b->rate_bits;
+    return merkle_open(b->leaves, b->lde, N, b->ncols, b->digests, N, b->cap_height, (const u64 *)leaf_idx, count,
+                       (u64 *)rows_out, (u64 *)siblings_out, st);
+  });
+}
+
 const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_out, uint64_t *leaves_out,
                                uint64_t *digests_out, uint64_t *cap_out) {
   return guarded([&]() -> Status {

@@ -233,6 +233,21 @@ const char *mp2gpu_fri_fetch_layer(const mp2gpu_fri *f, uint32_t layer, uint64_t
   });
 }
 
+const char *mp2gpu_fri_open_layer(const mp2gpu_fri *f, uint32_t layer, const uint64_t *leaf_idx, size_t count,
+                                  uint64_t *leaves_out, uint64_t *siblings_out) {
+  return guard([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(use_device(f, &st));
+    if (layer >= f->layers.size()) return "no such FRI layer";
+    if (count && !leaf_idx) return "null leaf_idx";
+    const mp2gpu_fri::Layer &L = f->layers[layer];
+    u32 cap_h = 0;
+    while (((size_t)1 << cap_h) < L.ncap) cap_h++;
+    return merkle_open(L.leaves, nullptr, 0, L.leaf_len, L.digests, L.nleaves, cap_h, (const u64 *)leaf_idx, count,
+                       (u64 *)leaves_out, (u64 *)siblings_out, st);
+  });
+}
+
 const char *mp2gpu_fri_layer_shape(const mp2gpu_fri *f, uint32_t layer, size_t *nleaves, size_t *leaf_len,
                                    size_t *ndigests, size_t *ncap) {
   return guard([&]() -> Status {

@@ -125,6 +125,12 @@ Status pow_search(const u64 *state12_host, u32 pos, u32 min_lz, u32 hash_kind, u
 Status gather_rows(const u64 *leaves_rowmajor, const u64 *lde_colmajor, size_t lde_stride,
                    size_t ncols, const u64 *row_idx, size_t nrows, u64 *out, cudaStream_t st);
 
+// Query-time openings (MerkleTree::get + MerkleTree::prove for a list of leaf indices): rows and sibling
+// digests are gathered on the device and copied back in two transfers.  idx / outputs are HOST pointers.
+Status merkle_open(const u64 *leaves_rowmajor, const u64 *lde_colmajor, size_t lde_stride, size_t leaf_len,
+                   const u64 *digests, size_t nleaves, u32 cap_height, const u64 *idx_host, size_t count,
+                   u64 *rows_out_host, u64 *siblings_out_host, cudaStream_t st);
+
 inline int log2_exact(size_t n) {
   if (n == 0 || (n & (n - 1))) return -1;
   int l = 0;

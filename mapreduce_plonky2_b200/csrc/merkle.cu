@@ -10,6 +10,7 @@
 // subtree of 2^h leaves.  Inside a chunk, node m of layer i (layer 0 = leaf digests, i < h) lives
 // at digest index 2*(((m>>1) << (i+1)) + (1<<i) - 1) + (m&1).  The subtree roots form the cap.
 #include <cstdlib>
+#include <vector>
 
 #include "internal.h"
 #include "poseidon.cuh"
@@ -215,6 +216,14 @@ __global__ void k_gather_rows(const u64 *__restrict__ rowmajor, const u64 *__res
   out[t] = rowmajor ? rowmajor[L * ncols + c] : colmajor[c * stride + L];
 }
 
+// out[t] = digests[slot[t]] (4 x u64 each)
+__global__ void k_gather_digests(const u64 *__restrict__ digests, const u64 *__restrict__ slot, size_t n,
+                                 u64 *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * n) return;
+  out[t] = digests[4 * slot[t >> 2] + (t & 3)];
+}
+
 static inline unsigned grid_for(size_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
 
 
@@ -404,4 +413,48 @@ Status gather_rows(const u64 *rowmajor, const u64 *colmajor, size_t stride, size
   return "";
 }
 
+}  // namespace mp2
+
+namespace mp2 {
+Status merkle_open(const u64 *rowmajor, const u64 *colmajor, size_t stride, size_t leaf_len, const u64 *digests,
+                   size_t nleaves, u32 cap_height, const u64 *idx_host, size_t count, u64 *rows_out,
+                   u64 *sib_out, cudaStream_t st) {
+  if (count == 0) return "";
+  int lg = log2_exact(nleaves);
+  if (lg < 0 || (int)cap_height > lg) return "MerkleTree::prove: bad tree shape";
+  const u32 h = (u32)lg - cap_height;
+  const size_t per = 2 * (((size_t)1 << h) - 1);
+  std::vector<u64> slots(count * (h ? h : 1));
+  for (size_t q = 0; q < count; q++) {
+    const size_t leaf = idx_host[q];
+    if (leaf >= nleaves) return "MerkleTree::prove: leaf_index out of range";
+    size_t pair_index = leaf & (((size_t)1 << h) - 1);
+    const size_t base = (leaf >> h) * per;
+    for (u32 i = 0; i < h; i++) {  // closed-form sibling slots
+      size_t parity = pair_index & 1;
+      pair_index >>= 1;
+      slots[q * h + i] = base + 2 * ((pair_index << (i + 1)) + ((size_t)1 << i) - 1) + (1 - parity);
+    }
+  }
+  u64 *d_idx = nullptr, *d_rows = nullptr, *d_slots = nullptr, *d_sib = nullptr;
+  MP2_CUDA(cudaMallocAsync(&d_idx, sizeof(u64) * count, st));
+  MP2_CUDA(cudaMemcpyAsync(d_idx, idx_host, sizeof(u64) * count, cudaMemcpyHostToDevice, st));
+  if (rows_out && leaf_len) {
+    MP2_CUDA(cudaMallocAsync(&d_rows, sizeof(u64) * count * leaf_len, st));
+    MP2_TRY(gather_rows(rowmajor, colmajor, stride, leaf_len, d_idx, count, d_rows, st));
+    MP2_CUDA(cudaMemcpyAsync(rows_out, d_rows, sizeof(u64) * count * leaf_len, cudaMemcpyDeviceToHost, st));
+  }
+  if (sib_out && h) {
+    MP2_CUDA(cudaMallocAsync(&d_slots, sizeof(u64) * count * h, st));
+    MP2_CUDA(cudaMallocAsync(&d_sib, sizeof(u64) * 4 * count * h, st));
+    MP2_CUDA(cudaMemcpyAsync(d_slots, slots.data(), sizeof(u64) * count * h, cudaMemcpyHostToDevice, st));
+    { ProfScope _p("k_gather_digests", st); k_gather_digests<<<grid_for(4 * count * h, 256), 256, 0, st>>>(digests, d_slots, count * h, d_sib); }
+    MP2_LAUNCH_CHECK();
+    MP2_CUDA(cudaMemcpyAsync(sib_out, d_sib, sizeof(u64) * 4 * count * h, cudaMemcpyDeviceToHost, st));
+  }
+  MP2_CUDA(cudaStreamSynchronize(st));
+  for (u64 *p : {d_idx, d_rows, d_slots, d_sib})
+    if (p) MP2_CUDA(cudaFreeAsync(p, st));
+  return "";
+}
 }  // namespace mp2

@@ -287,6 +287,17 @@ class PolynomialBatch:
         _lib.call("mp2gpu_batch_prove", self._handle, leaf_index, _ptr(sib), C.byref(cnt))
         return MerkleProof(sib[:cnt.value])
 
+    def open(self, leaf_indices: Sequence[int]):
+        """Query-phase openings from the device-resident batch: (rows (q, ncols), siblings (q, h, 4))."""
+        if self._handle is None:
+            raise Mp2GpuError("batch was not kept on the device")
+        idx = _arr(leaf_indices, 1)
+        h = self.degree_log + self.rate_bits - self.merkle_tree.cap.height()
+        rows = np.empty((idx.size, self.polynomials.shape[0]), dtype=np.uint64)
+        sib = np.empty((idx.size, h, 4), dtype=np.uint64)
+        _lib.call("mp2gpu_batch_open", self._handle, _ptr(idx), idx.size, _ptr(rows), _ptr(sib) if h else None)
+        return rows, sib
+
     def free(self) -> None:
         if self._handle is not None:
             _lib.load().mp2gpu_batch_free(self._handle)
@@ -339,6 +350,17 @@ class FriCommitPhase:
         cap = np.zeros((nc.value, 4), dtype=np.uint64)
         _lib.call("mp2gpu_fri_fetch_layer", self._h, i, _ptr(leaves), _ptr(digests) if nd.value else None, _ptr(cap))
         return MerkleTree(leaves, digests, MerkleCap(cap), self.hash_kind)
+
+    def open_layer(self, i: int, leaf_indices):
+        """(leaves (q, leaf_len), siblings (q, h, 4)) of layer ``i`` for the query rounds."""
+        nl, ll, nd, nc = C.c_size_t(0), C.c_size_t(0), C.c_size_t(0), C.c_size_t(0)
+        _lib.call("mp2gpu_fri_layer_shape", self._h, i, C.byref(nl), C.byref(ll), C.byref(nd), C.byref(nc))
+        idx = _arr(leaf_indices, 1)
+        h = (nl.value.bit_length() - 1) - (nc.value.bit_length() - 1)
+        leaves = np.empty((idx.size, ll.value), dtype=np.uint64)
+        sib = np.empty((idx.size, h, 4), dtype=np.uint64)
+        _lib.call("mp2gpu_fri_open_layer", self._h, i, _ptr(idx), idx.size, _ptr(leaves), _ptr(sib) if h else None)
+        return leaves, sib
 
     def finish(self) -> np.ndarray:
         ln = C.c_size_t(0)

@@ -39,6 +39,22 @@ def test_fri_committed_trees_matches_oracle(oracle, kind, degree_bits):
         G.verify_merkle_proof_to_cap(t0.get(i), i, t0.cap, t0.prove(i), kind)
 
 
+def test_fri_layer_openings(oracle):
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    coeffs = field_elems(0x0FE2, (1 << 10, 2))
+    ph = G.FriCommitPhase(coeffs, 3, 4, 1)
+    ph.commit_layer(4)
+    tree = ph.layer(0)
+    idx = [0, 5, 511, 300]
+    leaves, sib = ph.open_layer(0, idx)
+    assert np.array_equal(leaves, tree.leaves[idx])
+    for j, i in enumerate(idx):
+        assert np.array_equal(sib[j], oracle.merkle_prove(tree.digests, 512, 4, i))
+    ph.free()
+
+
 def test_fri_errors():
     import mapreduce_plonky2_b200 as G
 

@@ -221,6 +221,12 @@ def test_device_resident_handle(G, oracle):
         assert np.array_equal(pb.prove_on_device(i).siblings, oracle.merkle_prove(ref["digests"], 1 << 13, 4, i))
     with pytest.raises(G.Mp2GpuError):
         pb.fetch_rows([1 << 13])
+    # query-phase openings: 28 indices at once, rows + proofs gathered on the device
+    q = [int(x) for x in field_elems(3, (28,)) % np.uint64(1 << 13)]
+    got_rows, got_sib = pb.open(q)
+    assert np.array_equal(got_rows, ref["leaves"][q])
+    for j, i in enumerate(q):
+        assert np.array_equal(got_sib[j], oracle.merkle_prove(ref["digests"], 1 << 13, 4, i))
     pb.free()
 
 
