@@ -190,6 +190,52 @@ class MerkleTree:
         return MerkleProof(sib[:cnt.value])
 
 
+# ---- wire format -------------------------------------------------------------------------------------
+# plonky2 util/serialization Buffer::{write,read}_merkle_tree, used by the reference to (de)serialize the
+# circuit-set tree (mp2-common/src/serialization/circuit_data_serialization.rs:74-89, tested at :344-370).
+# Layout as recalled from plonky2 0.2.2 -- NOT yet confirmed against a real dump:
+#   usize = u64 LE; leaves.len(), then per leaf: len + canonical u64 LE elements;
+#   digests.len() + 4 x u64 LE each; cap height; 2^height cap hashes.
+def write_merkle_tree(tree: MerkleTree) -> bytes:
+    import struct
+
+    out = [struct.pack("<Q", len(tree.leaves))]
+    for leaf in tree.leaves:
+        leaf = _arr(leaf).reshape(-1)
+        out.append(struct.pack("<Q", leaf.size))
+        out.append(leaf.astype("<u8").tobytes())
+    out.append(struct.pack("<Q", int(tree.digests.shape[0])))
+    out.append(np.ascontiguousarray(tree.digests).astype("<u8").tobytes())
+    out.append(struct.pack("<Q", tree.cap.height()))
+    out.append(np.ascontiguousarray(tree.cap.hashes).astype("<u8").tobytes())
+    return b"".join(out)
+
+
+def read_merkle_tree(data: bytes, hash_kind: int = POSEIDON2) -> MerkleTree:
+    import struct
+
+    off = 0
+
+    def usize():
+        nonlocal off
+        v = struct.unpack_from("<Q", data, off)[0]
+        off += 8
+        return v
+
+    def elems(n):
+        nonlocal off
+        a = np.frombuffer(data, dtype="<u8", count=n, offset=off).astype(np.uint64)
+        off += 8 * n
+        return a
+
+    leaves = [elems(usize()) for _ in range(usize())]
+    digests = elems(4 * usize()).reshape(-1, 4)
+    cap = elems(4 << usize()).reshape(-1, 4)
+    if len({l.size for l in leaves}) == 1:
+        leaves = np.stack(leaves)
+    return MerkleTree(leaves, digests, MerkleCap(cap), hash_kind)
+
+
 def verify_merkle_proof_to_cap(leaf_data, leaf_index: int, cap: MerkleCap, proof: MerkleProof,
                                hash_kind: int = POSEIDON2) -> None:
     """plonky2's ``verify_merkle_proof_to_cap`` (native twin of the gadget used at

@@ -63,3 +63,23 @@ def test_error_strings_are_freed_and_pure_host_entry_points_work():
     with pytest.raises(P2.Mp2GpuError, match="out of range"):
         mt.prove(64)
     assert ctypes.c_char_p(P2._lib.load().mp2gpu_version()).value.startswith(b"0.")
+
+
+@pytest.mark.parametrize("n,cap", [(16, 0), (32, 3), (8, 3)])
+def test_merkle_tree_wire_format_round_trip(n, cap):
+    """Mirror of the rstest at mp2-common/src/serialization/circuit_data_serialization.rs:344-370 (valid cases):
+    write_merkle_tree -> read_merkle_tree is the identity, on an oracle-built tree (host-only code path)."""
+    import numpy as np
+
+    import oracle as O
+    from mapreduce_plonky2_b200 import plonky2 as P2
+
+    leaves = (np.arange(n * 7, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(n, 7) % np.uint64(O.P)
+    d, c = O.merkle_new(leaves, cap, 1)
+    tree = P2.MerkleTree(leaves, d, P2.MerkleCap(c), 1)
+    blob = P2.write_merkle_tree(tree)
+    assert len(blob) == 8 + n * (8 + 7 * 8) + 8 + d.shape[0] * 32 + 8 + (1 << cap) * 32
+    back = P2.read_merkle_tree(blob, 1)
+    assert np.array_equal(back.leaves, leaves) and np.array_equal(back.digests, d)
+    assert np.array_equal(back.cap.hashes, c) and back.cap.height() == cap
+    assert P2.write_merkle_tree(back) == blob
