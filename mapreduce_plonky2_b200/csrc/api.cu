@@ -16,7 +16,6 @@ namespace {
 
 struct ThreadCtx {
   int device = 0;
-  bool device_set = false;
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute
   int stream_device = -1;
@@ -246,7 +245,6 @@ const char *mp2gpu_init(int device) {
   return guarded([&]() -> Status {
     if (device < 0) return "negative device index";
     t_ctx.device = device;
-    t_ctx.device_set = true;
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
     cudaDeviceProp prop;

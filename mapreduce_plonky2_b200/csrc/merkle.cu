@@ -243,9 +243,7 @@ static int env_int(const char *name, int dflt) {
 }
 
 template <typename K>
-static Status plan_hash_launch(K kernel, int block, size_t nthreads, int, HashLaunch *out) {
-  (void)block;
-  (void)nthreads;
+static Status plan_hash_launch(K kernel, HashLaunch *out) {
   out->smem = 0;
   const int forced = env_int("MP2_HASH_CTAS", 0);
   if (forced > 0) {
@@ -263,7 +261,7 @@ static Status launch_leaf_hash_b(const u64 *in, size_t stride, u32 ncols, size_t
                                  u64 *leaves_out, u64 *digests, u64 *cap, cudaStream_t st) {
   HashLaunch hl;
   const size_t nleaves = leaf_end - leaf_begin;
-  MP2_TRY(plan_hash_launch(k_leaf_hash<KIND, COLMAJOR, BLOCK>, BLOCK, nleaves, 0, &hl));
+  MP2_TRY(plan_hash_launch(k_leaf_hash<KIND, COLMAJOR, BLOCK>, &hl));
   { ProfScope _p("k_leaf_hash", st); k_leaf_hash<KIND, COLMAJOR, BLOCK><<<grid_for(nleaves, BLOCK), BLOCK, hl.smem, st>>>(in, stride, ncols, leaf_begin, leaf_end, h,
                                                                                       leaves_out, digests, cap); }
   MP2_LAUNCH_CHECK();

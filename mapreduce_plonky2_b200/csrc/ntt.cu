@@ -23,13 +23,16 @@
 //
 // n <= 2^14 : one pass over global memory, the whole line lives in shared memory (128 KB at 2^14).
 // n >  2^14 : two passes (n = n1*n2, four-step), each a shared-memory transform on a tile of adjacent
-//             lines so that every global access is a >= 64-byte run.
+//             lines (4 lines of 2^10 points at n = 2^20: the strided pass moves whole 32-byte sectors).
 #include "internal.h"
 #include "gl.cuh"
 
 namespace mp2 {
 
-static const u32 kMaxSingleLog = 14;  // 2^14 * 8 B = 128 KB of the 227 KB shared memory
+#ifndef MP2_NTT_MAX_SINGLE_LOG
+#define MP2_NTT_MAX_SINGLE_LOG 14
+#endif
+static const u32 kMaxSingleLog = MP2_NTT_MAX_SINGLE_LOG;  // 2^14 * 8 B = 128 KB of the 227 KB shared memory
 // Tile = 2^12 elements (32 KB) and 256 threads: 4 resident CTAs per SM whose load / transform / store
 // phases interleave.  2^13-element tiles (2 resident CTAs) were 8 % slower on the 2^20 four-step path.
 #ifndef MP2_NTT_TILE_LOG
@@ -412,11 +415,11 @@ Status ntt_canonicalize(const u64 *in, size_t in_stride, u64 *out, size_t out_st
 }
 
 static Status split_two_pass(u32 n_log, TwoPass *tp) {
-  if (n_log > 2 * kMaxSingleLog - 2) return "polynomial degree 2^" + std::to_string(n_log) + " not supported (max 2^26)";
+  if (n_log > 26) return "polynomial degree 2^" + std::to_string(n_log) + " not supported (max 2^26)";
   tp->n_log = n_log;
   tp->b = (n_log + 1) / 2;
   tp->a = n_log - tp->b;
-  tp->lines_log = kTileLog - tp->b;  // a <= b <= 13
+  tp->lines_log = tp->b >= kTileLog ? 0 : kTileLog - tp->b;  // a <= b <= 13; one line per CTA once a line fills the tile
   return "";
 }
 

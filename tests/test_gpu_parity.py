@@ -170,6 +170,31 @@ def test_polynomial_batch_two_pass_sizes(G, oracle, log_n):
     _check_batch(G, oracle, cols[:2], 1, 2, 0, from_coeffs=True)
 
 
+def test_intt_lde_large_degree_tiles(G, oracle):
+    """n = 2^21 and 2^23 exercise the four-step split with a != b and b close to the tile size (device stages,
+    one column checked against the oracle)."""
+    import torch
+
+    from mapreduce_plonky2_b200 import device as D
+
+    D.bind_current_device()
+    for log_n in (21, 23):
+        col = field_elems(0x7711 + log_n, (1, 1 << log_n))
+        vals = torch.from_numpy(col.view(np.int64)).cuda()
+        coeffs = torch.empty_like(vals)
+        lde = torch.empty((1, 1 << (log_n + 1)), dtype=torch.int64, device="cuda")
+        D.intt(vals, coeffs)
+        D.coset_lde(coeffs, lde, 1)
+        torch.cuda.synchronize()
+        c_ref = oracle.ifft(col[0])
+        assert np.array_equal(coeffs.cpu().numpy().view(np.uint64)[0], c_ref)
+        nat = oracle.coset_lde(c_ref, 1)
+        got = lde.cpu().numpy().view(np.uint64)[0]
+        idx = np.array([0, 1, 2, 12345, (1 << (log_n + 1)) - 1])
+        rev = np.array([G.reverse_bits(int(i), log_n + 1) for i in idx])
+        assert np.array_equal(got[idx], nat[rev])
+
+
 def test_edge_batches_config1_shape(G, oracle):
     """all-zero, all p-1 and column j == j batches (SURVEY.md 8(d) edge inputs)."""
     n = 1 << 10
