@@ -131,6 +131,21 @@ GL_DEV u64 gl_mul(u64 a, u64 b) {
       : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
   return gl_reduce128w(w0, w1, w2, w3);
 }
+// loose * loose + loose -> loose: the addend rides on the 128-bit product (a*b + c < 2^128), one reduction
+GL_DEV u64 gl_mul_add(u64 a, u64 b, u64 c) {
+  u32 w0, w1, w2, w3;
+  asm("{\n\t.reg .u64 p00, p01, p10, p11;\n\t.reg .u32 l00, h00, l01, h01, l10, h10, l11, h11;\n\t"
+      "mul.wide.u32 p00, %4, %6;\n\tmul.wide.u32 p01, %4, %7;\n\t"
+      "mul.wide.u32 p10, %5, %6;\n\tmul.wide.u32 p11, %5, %7;\n\t"
+      "mov.b64 {l00, h00}, p00;\n\tmov.b64 {l01, h01}, p01;\n\t"
+      "mov.b64 {l10, h10}, p10;\n\tmov.b64 {l11, h11}, p11;\n\t"
+      "add.cc.u32 %1, h00, l01;\n\taddc.cc.u32 %2, h01, l11;\n\taddc.u32 %3, h11, 0;\n\t"
+      "add.cc.u32 %1, %1, l10;\n\taddc.cc.u32 %2, %2, h10;\n\taddc.u32 %3, %3, 0;\n\t"
+      "add.cc.u32 %0, l00, %8;\n\taddc.cc.u32 %1, %1, %9;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;\n\t}"
+      : "=r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(w3)
+      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)), "r"(lo32(c)), "r"(hi32(c)));
+  return gl_reduce128w(w0, w1, w2, w3);
+}
 // loose^2 -> loose: three IMAD.WIDE (the cross product is added twice)
 GL_DEV u64 gl_sqr(u64 a) {
   u32 w0, w1, w2, w3;

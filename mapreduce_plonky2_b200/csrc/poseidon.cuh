@@ -258,9 +258,9 @@ GL_DEV void p2_internal(u64 (&s)[12]) {
     asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;"
         : "+r"(a0), "+r"(a1), "+r"(a2)
         : "r"(lo32(s[i])), "r"(hi32(s[i])));
-  const u64 sum = gl_canon(gl_reduce128w(a0, a1, a2, 0u));  // canonical: one fold suffices below
+  const u64 sum = gl_reduce128w(a0, a1, a2, 0u);
 #pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_add_c(gl_mul(s[i], c_p2_diag[i]), sum);
+  for (int i = 0; i < 12; i++) s[i] = gl_mul_add(s[i], c_p2_diag[i], sum);  // the sum rides on the product
 }
 
 template <bool SYNC>
