@@ -28,6 +28,10 @@ static __constant__ u64 c_pos_rc[MP2_POSEIDON_RC_LEN] = {MP2_POSEIDON_RC_LIST};
 // ... and as 22|21|21-bit limbs, padded with one all-zero round so "MDS, then add the NEXT round's
 // constants" needs no special last round.  Index (12*round + lane)*3 + limb.
 static __constant__ u32 c_pos_rc3[MP2_POSEIDON_RC3_LEN] = {MP2_POSEIDON_RC3_LIST};
+// Partial rounds: constants pushed through the linear layers (tools/gen_poseidon_constants.py) -- lane 0
+// gets c_pos_t0[r - 4] after the layer of round r, lanes 1..11 get c_pos_d once when the partial rounds end.
+static __constant__ u64 c_pos_t0[MP2_POSEIDON_PARTIAL_T0_LEN] = {MP2_POSEIDON_PARTIAL_T0_LIST};
+static __constant__ u64 c_pos_d[MP2_POSEIDON_PARTIAL_D_LEN] = {MP2_POSEIDON_PARTIAL_D_LIST};
 static __constant__ u64 c_p2_rc[MP2_POSEIDON2_RC_LEN] = {MP2_POSEIDON2_RC_LIST};
 static __constant__ u64 c_p2_diag[MP2_POSEIDON2_DIAG_LEN] = {MP2_POSEIDON2_DIAG_LIST};
 static __constant__ u32 c_p2_rc3[MP2_POSEIDON2_RC3_LEN] = {MP2_POSEIDON2_RC3_LIST};
@@ -79,6 +83,7 @@ GL_DEV u64 pos_merge3(u32 o0, u32 o1, u32 o2) {
 // [2,-4,16,1,-1,-1] is the negacyclic-6 block.  ~90 shifts/adds per plane instead of 144
 // multiply-adds; ptxas spreads them over the alu and fma pipes.  Arithmetic wraps mod 2^32; the
 // results themselves are < 2^31 (tests/test_oracle_vs_pyref.py pins the same decomposition).
+template <bool RC>
 GL_DEV void pos_mds_plane(const u32 (&x)[12], const u32 *rc, int rc_stride, u32 (&y)[12]) {
   u32 a[6], b[6];
 #pragma unroll
@@ -108,8 +113,8 @@ GL_DEV void pos_mds_plane(const u32 (&x)[12], const u32 *rc, int rc_stride, u32 
       (b[5] << 1) - b[0] - b[1] + b[2] + (b[3] << 4) - (b[4] << 2)};
 #pragma unroll
   for (int k = 0; k < 6; k++) {
-    y[k] = ya[k] + yb[k] + rc[k * rc_stride];
-    y[k + 6] = ya[k] - yb[k] + rc[(k + 6) * rc_stride];
+    y[k] = ya[k] + yb[k] + (RC ? rc[k * rc_stride] : 0u);
+    y[k + 6] = ya[k] - yb[k] + (RC ? rc[(k + 6) * rc_stride] : 0u);
   }
   y[0] += x[0] << 3;  // DIAG[0] = 8
 }
@@ -119,9 +124,9 @@ GL_DEV void pos_mds_rc(u64 (&s)[12], const u32 *rc3) {
   u32 l0[12], l1[12], l2[12], o0[12], o1[12], o2[12];
 #pragma unroll
   for (int i = 0; i < 12; i++) pos_split3(s[i], l0[i], l1[i], l2[i]);
-  pos_mds_plane(l0, rc3, 3, o0);
-  pos_mds_plane(l1, rc3 + 1, 3, o1);
-  pos_mds_plane(l2, rc3 + 2, 3, o2);
+  pos_mds_plane<true>(l0, rc3, 3, o0);
+  pos_mds_plane<true>(l1, rc3 + 1, 3, o1);
+  pos_mds_plane<true>(l2, rc3 + 2, 3, o2);
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = pos_merge3(o0[i], o1[i], o2[i]);
 }
@@ -167,7 +172,9 @@ GL_DEV void sbox_layer(u64 (&s)[12]) {
 
 // Naive schedule (A.6): 30 x { +RC ; S-box (all lanes | lane 0) ; MDS }, 4 full + 22 partial + 4 full.
 // In the 22 partial rounds only lane 0 passes through the S-box, so lanes 1..11 stay in limb form
-// from one linear layer to the next (re-normalised, never merged) and only lane 0 is merged/split.
+// from one linear layer to the next (re-normalised, never merged) and only lane 0 is merged/split; their
+// round constants are pushed through the linear layers, leaving one constant per round on lane 0 and one
+// correction vector at the end (the algebra and its self-check are in tools/gen_poseidon_constants.py).
 template <bool SYNC>
 GL_DEV void poseidon_permute(u64 (&s)[12]) {
 #pragma unroll
@@ -194,18 +201,17 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
         s0 = gl_pow7(s0);
         pos_split3(s0, l0[0], l1[0], l2[0]);
         u32 o0[12], o1[12], o2[12];
-        const u32 *rc3 = c_pos_rc3 + 36 * (r + 1);
-        pos_mds_plane(l0, rc3, 3, o0);
-        pos_mds_plane(l1, rc3 + 1, 3, o1);
-        pos_mds_plane(l2, rc3 + 2, 3, o2);
-        s0 = pos_merge3(o0[0], o1[0], o2[0]);
+        pos_mds_plane<false>(l0, nullptr, 0, o0);
+        pos_mds_plane<false>(l1, nullptr, 0, o1);
+        pos_mds_plane<false>(l2, nullptr, 0, o2);
+        s0 = gl_add_c(pos_merge3(o0[0], o1[0], o2[0]), c_pos_t0[r - 4]);  // the only constant of the round
 #pragma unroll
         for (int i = 1; i < 12; i++) pos_renorm3(o0[i], o1[i], o2[i], l0[i], l1[i], l2[i]);
         MP2_ROUND_SYNC();
       }
       s[0] = s0;
 #pragma unroll
-      for (int i = 1; i < 12; i++) s[i] = pos_merge3(l0[i], l1[i], l2[i]);
+      for (int i = 1; i < 12; i++) s[i] = gl_add_c(pos_merge3(l0[i], l1[i], l2[i]), c_pos_d[i]);
     }
   }
 }
