@@ -79,6 +79,33 @@ struct DevBuf {
   }
 };
 
+// Column-wise host<->device copies, merged over runs of columns that are adjacent in host memory (one
+// transfer for a contiguous matrix; one per column for separately allocated Vecs -- each cudaMemcpyAsync
+// costs a few microseconds of launch time, which at 135 columns was a fifth of a config-1 call).
+Status copy_columns_h2d(u64 *dev, const uint64_t *const *cols, size_t ncols, size_t n, cudaStream_t st) {
+  for (size_t c = 0; c < ncols;) {
+    if (!cols[c]) return "null column pointer";
+    size_t run = 1;
+    while (c + run < ncols && cols[c + run] == cols[c] + run * n) run++;
+    MP2_CUDA(cudaMemcpyAsync(dev + c * n, cols[c], run * n * sizeof(u64), cudaMemcpyHostToDevice, st));
+    c += run;
+  }
+  return "";
+}
+Status copy_columns_d2h(uint64_t *const *cols, const u64 *dev, size_t ncols, size_t n, cudaStream_t st) {
+  for (size_t c = 0; c < ncols;) {
+    if (!cols[c]) {
+      c++;
+      continue;
+    }
+    size_t run = 1;
+    while (c + run < ncols && cols[c + run] == cols[c] + run * n) run++;
+    MP2_CUDA(cudaMemcpyAsync(cols[c], dev + c * n, run * n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    c += run;
+  }
+  return "";
+}
+
 Status check_commit_args(size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind) {
   if (ncols == 0) return "PolynomialBatch: no polynomials";
   if (n_log + rate_bits > 32) return "PolynomialBatch: degree_log + rate_bits exceeds two-adicity 32";
@@ -141,18 +168,13 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
     cudaEvent_t e;
     ~EvGuard() { cudaEventDestroy(e); }
   } ev_guard{ev};
-  for (size_t c = 0; c < ncols; c++) {
-    if (!cols[c]) return "null column pointer";
-    MP2_CUDA(cudaMemcpyAsync(d_in.p + c * n, cols[c], n * sizeof(u64), cudaMemcpyHostToDevice, st));
-  }
+  MP2_TRY(copy_columns_h2d(d_in.p, cols, ncols, n, st));
   if (from_coeffs) MP2_TRY(ntt_canonicalize(d_in.p, n, d_coeffs.p, n, ncols, n, st));
   else MP2_TRY(ntt_intt(d_in.p, n, d_coeffs.p, n, ncols, n_log, st));
   if (coeffs_out) {
     MP2_CUDA(cudaEventRecord(ev, st));
     MP2_CUDA(cudaStreamWaitEvent(cp, ev, 0));
-    for (size_t c = 0; c < ncols; c++)
-      if (coeffs_out[c])
-        MP2_CUDA(cudaMemcpyAsync(coeffs_out[c], d_coeffs.p + c * n, n * sizeof(u64), cudaMemcpyDeviceToHost, cp));
+    MP2_TRY(copy_columns_d2h(coeffs_out, d_coeffs.p, ncols, n, cp));
   }
   MP2_TRY(ntt_coset_lde(d_coeffs.p, n, d_lde.p, N, ncols, n_log, rate_bits, 0, 0, st));
   const size_t nchunks = (leaves_out && N >= ((size_t)1 << 16)) ? 8 : 1;
@@ -518,10 +540,7 @@ const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_ou
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
     const size_t n = (size_t)1 << b->n_log, N = n << b->rate_bits, ncap = (size_t)1 << b->cap_height;
-    if (coeffs_out)
-      for (size_t c = 0; c < b->ncols; c++)
-        if (coeffs_out[c])
-          MP2_CUDA(cudaMemcpyAsync(coeffs_out[c], b->coeffs + c * n, n * sizeof(u64), cudaMemcpyDeviceToHost, st));
+    if (coeffs_out) MP2_TRY(copy_columns_d2h(coeffs_out, b->coeffs, b->ncols, n, st));
     if (leaves_out) {
       if (!b->leaves) return "batch holds no row-major leaves";
       MP2_CUDA(cudaMemcpyAsync(leaves_out, b->leaves, N * b->ncols * sizeof(u64), cudaMemcpyDeviceToHost, st));
