@@ -87,11 +87,20 @@ def synthetic_columns(seed, shape):
 # ------------------------------------------------------------------------------------------------
 # CPU restatement (the reference arm and the cpu_baseline leg): oracle/ may only be executed here
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """All host cores this process may use.  (torchrun exports OMP_NUM_THREADS=1 to its workers; the oracle's
+    OpenMP regions take an explicit thread count, so the CPU arm still uses the whole box.)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_commit_time(a, sample_log, repeats=1, warm=0):
     import oracle as O
 
     O.build()
-    threads = O.max_threads()
+    threads = host_threads()
     kind = 0 if a.hash == "poseidon" else 1
     cols = synthetic_columns(0x6D7033, (a.ncols, 1 << sample_log))
     times = []
@@ -466,8 +475,7 @@ def run_trace(a):
                                            ", ".join("2^%d" % d for d in degrees), a.hash)
     if a.impl == "reference":
         if rank == 0:
-            import oracle as O
-            threads = O.max_threads()
+            threads = host_threads()
             dt = [cpu_trace_time(kind, threads, degrees) for _ in range(max(1, min(a.steps, 3)))]
             v = len(dt) / sum(dt)
             print(json.dumps({"impl": "reference", "metric": "mp2 proofs/s (commitment trace)", "value": v,
@@ -532,8 +540,7 @@ def run_trace(a):
                              "achieved": mads, "peak": ip["t_imad_per_s"], "unit": "T imad/s (6700 credited per permutation)",
                              "frac": mads / ip["t_imad_per_s"] if ip["t_imad_per_s"] else None, "traffic": None}}
         if not a.no_cpu_baseline and world == 1:
-            import oracle as O
-            threads = O.max_threads()
+            threads = host_threads()
             dt = cpu_trace_time(kind, threads, degrees)
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
                                     "sample": "one proof trace (%.1f s)" % dt}

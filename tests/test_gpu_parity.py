@@ -267,6 +267,24 @@ def test_bad_arguments(G):
         G.PolynomialBatch.from_values(cols, 1, False, 1, hash_kind=7)
 
 
+def test_empty_and_degenerate_inputs(G, oracle):
+    """Empty leaves (hash_or_noop of [] is the zero digest), single-leaf trees, one-row polynomials."""
+    empty = np.zeros((8, 0), dtype=np.uint64)
+    mt = G.MerkleTree.new(empty, 1, 0)
+    d, c = oracle.merkle_new(np.zeros((8, 1), dtype=np.uint64), 1, 0)   # [0] and [] hash to the same no-op digest
+    assert np.array_equal(mt.digests, d) and np.array_equal(mt.cap.hashes, c)
+    one = G.MerkleTree.new(field_elems(4, (1, 9)), 0, 1)                 # a single leaf: the cap is its hash
+    assert one.digests.size == 0 and np.array_equal(one.cap.hashes[0], oracle.hash_no_pad(one.leaves[0], 1))
+    assert len(one.prove(0)) == 0
+    with pytest.raises(G.Mp2GpuError, match="non-empty|no polynomials|power of two"):
+        G.PolynomialBatch.from_values(np.zeros((0, 8), dtype=np.uint64), 1, False, 0)
+    # degree-0 polynomials (n = 1): the LDE is constant, every leaf row equals the value row
+    cols = field_elems(8, (6, 1))
+    pb, ref = _check_batch(G, oracle, cols, 3, 2, 0)
+    assert (pb.merkle_tree.leaves == cols[:, 0]).all()
+    assert G.hash_no_pad_batch(np.zeros((0, 5), dtype=np.uint64), 0).shape == (0, 4)
+
+
 def test_concurrent_callers(G, oracle):
     """prove() is called from several threads at once (SURVEY.md 8(b) Threading)."""
     import threading

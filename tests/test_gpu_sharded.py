@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_dir, exchange):
+def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_dir, exchange, from_coeffs=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -27,7 +27,8 @@ def _worker(rank, world, port, ncols, n_log, rate_bits, cap_height, kind, out_di
     cols = field_elems(0xBEEF, (ncols, 1 << n_log))
     c_loc = ncols // world
     mine = torch.from_numpy(cols[rank * c_loc:(rank + 1) * c_loc].view(np.int64).copy()).cuda()
-    res = commit_sharded(mine, ncols, rate_bits, cap_height, kind, CudaEngine(), exchange=exchange)
+    res = commit_sharded(mine, ncols, rate_bits, cap_height, kind, CudaEngine(), exchange=exchange,
+                         from_coeffs=from_coeffs)
     torch.cuda.synchronize()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), coeffs=res.coeffs.cpu().numpy().view(np.uint64),
              leaves=res.leaves.cpu().numpy().view(np.uint64), digests=res.digests.cpu().numpy().view(np.uint64),
@@ -57,3 +58,20 @@ def test_sharded_nccl_equals_oracle(tmp_path, oracle, ncols, n_log, kind, exchan
     assert np.array_equal(np.concatenate([p["digests"] for p in parts]), ref["digests"])
     for p in parts:
         assert np.array_equal(p["cap"], ref["cap"])
+
+
+def test_sharded_from_coeffs_nccl(tmp_path, oracle):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from util import field_elems
+
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, 8, 10, 3, 4, 0, str(tmp_path), "nccl", True), nprocs=2, join=True)
+    ref = oracle.commit(field_elems(0xBEEF, (8, 1 << 10)), 3, 4, 0, True)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(2)]
+    assert np.array_equal(np.concatenate([p["coeffs"] for p in parts]), ref["coeffs"])
+    assert np.array_equal(np.concatenate([p["leaves"] for p in parts]), ref["leaves"])
+    assert np.array_equal(parts[0]["cap"], ref["cap"])
