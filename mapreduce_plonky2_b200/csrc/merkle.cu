@@ -135,6 +135,132 @@ k_merkle_layer(u64 *__restrict__ digests, u64 *__restrict__ cap, u32 h, u32 laye
   if (active) store_digest(dst, st);
 }
 
+// ---- K5': one Merkle layer, 16 lanes per node (12 active), for the SPARSE upper levels ----------------
+// One permutation is ~24 k instructions on one thread -- ~30 us when a warp has the SM to itself -- and the
+// levels with fewer nodes than the GPU has warps are pure latency.  Here a node's 12 state elements live in
+// 12 lanes: every lane does its own S-box, and the linear layers are row-wise dot products whose operands
+// are fetched from the sibling lanes with warp shuffles (3 limb shuffles per term).  ~5.7 k instructions per
+// lane and permutation: 4-5x lower latency for 4x more issue slots, so it is used only below
+// kCoopLevelNodes nodes per level.  Results are bit-identical to the one-thread form (same field arithmetic).
+static __device__ const u64 g_pos_rc[MP2_POSEIDON_RC_LEN] = {MP2_POSEIDON_RC_LIST};
+static __device__ const u64 g_p2_rc[MP2_POSEIDON2_RC_LEN] = {MP2_POSEIDON2_RC_LIST};
+static __device__ const u64 g_p2_diag[MP2_POSEIDON2_DIAG_LEN] = {MP2_POSEIDON2_DIAG_LIST};
+
+GL_DEV u32 shfl32(u32 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// Poseidon: y_r = sum_i CIRC[i]*x[(r+i)%12] + 8*x[0]*[r==0] + rc
+GL_DEV u64 coop_pos_mds(u64 x, int r, int gbase, u64 rc_next) {
+  constexpr u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+  u32 l0, l1, l2;
+  pos_split3(x, l0, l1, l2);
+  u32 a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    int src = r + i;
+    src = src >= 24 ? src - 24 : src >= 12 ? src - 12 : src;
+    src += gbase;
+    a0 += shfl32(l0, src) * CIRC[i];
+    a1 += shfl32(l1, src) * CIRC[i];
+    a2 += shfl32(l2, src) * CIRC[i];
+  }
+  if (r == 0) {
+    a0 += l0 << 3;
+    a1 += l1 << 3;
+    a2 += l2 << 3;
+  }
+  return gl_add_c(pos_merge3(a0, a1, a2), rc_next);
+}
+GL_DEV u64 coop_poseidon(u64 x, int r, int gbase) {
+  const bool act = r < 12;
+  x = act ? gl_add_c(x, g_pos_rc[r]) : 0;
+#pragma unroll 1
+  for (int round = 0; round < 30; round++) {
+    // the next round's constant is requested before the S-box so that its latency hides behind it
+    const u64 rcn = (act && round < 29) ? __ldg(g_pos_rc + 12 * (round + 1) + r) : 0;
+    const bool full = round < 4 || round >= 26;
+    if (full || r == 0) x = gl_pow7(x);
+    x = coop_pos_mds(x, r, gbase, rcn);  // __shfl_sync re-converges the warp
+  }
+  return x;
+}
+
+// Poseidon2 external layer: M_E[r][j] = M4[r%4][j%4] * (2 if r/4 == j/4 else 1)
+GL_DEV u64 coop_p2_ext(u64 x, int gbase, const u32 (&m)[4], int rblock, u64 rc_next) {
+  u32 l0, l1, l2;
+  pos_split3(x, l0, l1, l2);
+  u32 a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    const u32 coef = m[j & 3] << (rblock == (j >> 2) ? 1 : 0);
+    a0 += shfl32(l0, gbase + j) * coef;
+    a1 += shfl32(l1, gbase + j) * coef;
+    a2 += shfl32(l2, gbase + j) * coef;
+  }
+  return gl_add_c(pos_merge3(a0, a1, a2), rc_next);
+}
+// Poseidon2 internal layer: x*mu + sum(state)
+GL_DEV u64 coop_p2_int(u64 x, int gbase, u64 mu) {
+  u32 s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    const u32 lo = shfl32(lo32(x), gbase + j), hi = shfl32(hi32(x), gbase + j);
+    asm("add.cc.u32 %0, %0, %3;\n\taddc.cc.u32 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+r"(s0), "+r"(s1), "+r"(s2) : "r"(lo), "r"(hi));
+  }
+  return gl_mul_add(x, mu, gl_reduce128w(s0, s1, s2, 0u));
+}
+GL_DEV u64 coop_poseidon2(u64 x, int r, int gbase) {
+  const bool act = r < 12;
+  const int rr = act ? r : 0;
+  constexpr u32 M4[4][4] = {{5, 7, 1, 3}, {4, 6, 1, 1}, {1, 3, 5, 7}, {1, 1, 4, 6}};
+  u32 m[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) m[k] = (rr & 3) == 0 ? M4[0][k] : (rr & 3) == 1 ? M4[1][k] : (rr & 3) == 2 ? M4[2][k] : M4[3][k];
+  const int rblock = rr >> 2;
+  const u64 mu = g_p2_diag[rr];
+  if (!act) x = 0;
+  x = coop_p2_ext(x, gbase, m, rblock, act ? g_p2_rc[rr] : 0);
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    const u64 rcn = (act && k < 3) ? __ldg(g_p2_rc + 12 * (k + 1) + rr) : 0;
+    x = gl_pow7(x);
+    x = coop_p2_ext(x, gbase, m, rblock, rcn);
+  }
+  u64 rci = __ldg(g_p2_rc + 48);
+#pragma unroll 1
+  for (int t = 0; t < 22; t++) {
+    const u64 rc_now = rci;
+    rci = __ldg(g_p2_rc + 48 + (t < 21 ? t + 1 : t));
+    if (r == 0) x = gl_pow7(gl_add_c(x, rc_now));
+    x = coop_p2_int(x, gbase, mu);
+  }
+  x = act ? gl_add_c(x, g_p2_rc[70 + rr]) : 0;
+#pragma unroll 1
+  for (int k = 0; k < 4; k++) {
+    const u64 rcn = (act && k < 3) ? __ldg(g_p2_rc + 70 + 12 * (k + 1) + rr) : 0;
+    x = gl_pow7(x);
+    x = coop_p2_ext(x, gbase, m, rblock, rcn);
+  }
+  return x;
+}
+
+template <u32 KIND>
+__global__ void __launch_bounds__(128)
+k_merkle_layer_coop(u64 *__restrict__ digests, u64 *__restrict__ cap, u32 h, u32 layer, size_t nnodes) {
+  size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;  // node
+  const int r = threadIdx.x & 15, gbase = threadIdx.x & 16;
+  const bool active = t < nnodes;
+  if (!active) t = nnodes - 1;
+  u32 width_log = h - layer;
+  size_t sub = t >> width_log, m = t & (((size_t)1 << width_log) - 1);
+  size_t per = 2 * (((size_t)1 << h) - 1);
+  u64 *base = digests + 4 * sub * per;
+  const u64 *ch = base + 4 * node_slot(layer - 1, 2 * m);  // the two children: 8 contiguous u64
+  u64 x = r < 8 ? ch[r] : 0;
+  x = KIND == MP2_HASH_POSEIDON2 ? coop_poseidon2(x, r, gbase) : coop_poseidon(x, r, gbase);
+  u64 *dst = layer == h ? cap + 4 * sub : base + 4 * node_slot(layer, m);
+  if (active && r < 4) dst[r] = gl_canon(x);
+}
+
 template <u32 KIND>
 __global__ void __launch_bounds__(MP2_HASH_BLOCK)
 k_two_to_one(const u64 *__restrict__ a, const u64 *__restrict__ b, size_t count, u64 *__restrict__ out) {
@@ -280,11 +406,22 @@ static Status launch_leaf_hash(const u64 *in, size_t stride, u32 ncols, size_t l
   }
 }
 
+#ifndef MP2_COOP_LEVEL_NODES
+#define MP2_COOP_LEVEL_NODES 2048
+#endif
+
 template <u32 KIND>
 static Status build_levels(u64 *digests, u64 *cap, u32 h, u32 cap_height, cudaStream_t st) {
+  const size_t coop_below = (size_t)env_int("MP2_COOP_LEVEL_NODES", MP2_COOP_LEVEL_NODES);
   for (u32 layer = 1; layer <= h; layer++) {
     size_t nnodes = ((size_t)1 << (h - layer)) << cap_height;
-    { ProfScope _p("k_merkle_layer", st); k_merkle_layer<KIND><<<grid_for(nnodes, MP2_HASH_BLOCK), MP2_HASH_BLOCK, 0, st>>>(digests, cap, h, layer, nnodes); }
+    if (nnodes <= coop_below) {
+      ProfScope _p("k_merkle_layer_coop", st);
+      k_merkle_layer_coop<KIND><<<grid_for(nnodes * 16, 128), 128, 0, st>>>(digests, cap, h, layer, nnodes);
+    } else {
+      ProfScope _p("k_merkle_layer", st);
+      k_merkle_layer<KIND><<<grid_for(nnodes, MP2_HASH_BLOCK), MP2_HASH_BLOCK, 0, st>>>(digests, cap, h, layer, nnodes);
+    }
     MP2_LAUNCH_CHECK();
   }
   return "";
