@@ -285,19 +285,25 @@ struct TwoPass {
   u32 n_log, a, b;   // n1 = 2^a (strided pass 1), n2 = 2^b (contiguous pass 2)
   u32 lines_log;
   u32 rate_bits;
+  u32 ncols;         // pass 1 only: the grid is flattened, see k_pass1
   int inverse;       // 1: iNTT natural -> natural; 0: coset LDE natural -> leaf order
   u64 n_inv;
 };
 
 // pass 1: tile = LINES adjacent j2; size-n1 transform over j1 (stride n2); then the four-step
-// twiddle w_n^(j2*k1).  grid = (n2 / LINES, ncols, cosets)
+// twiddle w_n^(j2*k1).  1-D grid of ncols * cosets * (n2 / LINES) CTAs, column fastest, then coset, then
+// tile: the CTAs in flight share one 32 KB slice of the coset-scale table, and the 2^r cosets of an input tile
+// are ncols CTAs apart, so both are fetched from HBM once and re-read from L2 (ncu: pass-1 DRAM reads 8x the
+// input with the coset as the slowest grid dimension).
 __global__ void __launch_bounds__(1024)
 k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
         TwoPass tp, const u64 *__restrict__ W1, const u64 *__restrict__ Wn, const u64 *__restrict__ scale) {
   extern __shared__ u64 sm[];
   const u32 LINES = 1u << tp.lines_log, S = 1u << tp.a;
   const size_t n2 = (size_t)1 << tp.b;
-  const size_t c = blockIdx.y, k = blockIdx.z, q0 = (size_t)blockIdx.x * LINES;
+  const u32 kq = blockIdx.x / tp.ncols;
+  const size_t c = blockIdx.x - kq * tp.ncols, k = kq & ((1u << tp.rate_bits) - 1);
+  const size_t q0 = (size_t)(kq >> tp.rate_bits) * LINES;
   const u64 *sc = tp.inverse ? nullptr : scale + (k << tp.n_log);
   const u32 total = S << tp.lines_log, nthr = blockDim.x;
   for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
@@ -457,7 +463,10 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);
     MP2_TRY(allow_smem(k_pass1, smem));
-    dim3 grid((unsigned)(((size_t)1 << tp.b) >> tp.lines_log), (unsigned)ncols, 1);
+    const size_t ctas = (((size_t)1 << tp.b) >> tp.lines_log) * ncols;
+    if (ctas > 0x7fffffffull) return "batch too large for one iNTT launch (columns x tiles > 2^31)";
+    tp.ncols = (u32)ncols;
+    dim3 grid((unsigned)ctas, 1, 1);
     { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, tmp, n, none, tp, W1, Wn, nullptr); }
     MP2_LAUNCH_CHECK();
   }
@@ -532,7 +541,10 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);
     MP2_TRY(allow_smem(k_pass1, smem));
-    dim3 grid((unsigned)(((size_t)1 << tp.b) >> tp.lines_log), (unsigned)ncols, cosets);
+    const size_t ctas = ((((size_t)1 << tp.b) >> tp.lines_log) << rate_bits) * ncols;
+    if (ctas > 0x7fffffffull) return "batch too large for one LDE launch (columns x cosets x tiles > 2^31)";
+    tp.ncols = (u32)ncols;
+    dim3 grid((unsigned)ctas, 1, 1);
     { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, mid, 0, mid_map, tp, W1, Wn, scale); }
     MP2_LAUNCH_CHECK();
   }
