@@ -136,6 +136,21 @@ typedef struct mp2gpu_fri mp2gpu_fri;
 /* coeffs_ext: 2^n_log extension coefficients (the non-padded final polynomial; its lde(rate_bits) is implied). */
 const char *mp2gpu_fri_begin(const uint64_t *coeffs_ext, uint32_t n_log, uint32_t rate_bits,
                              uint32_t cap_height, uint32_t hash_kind, mp2gpu_fri **out);
+/* PolynomialBatch::prove_openings up to its call of fri_proof (plonky2 fri/oracle.rs; ReducingFactor of
+ * util/reducing.rs): the alpha-batched quotient
+ *     final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i),    F_i = sum_j alpha^j f_ij
+ * computed from the coefficients the committed batches keep on the device, and left there as the state of a new
+ * commit phase (*out, exactly what mp2gpu_fri_begin builds from host coefficients; rate_bits is the oracles').
+ * oracles[noracles]: handles from mp2gpu_commit_from_values / _coeffs (plonky2's FRI_ORACLES order).  Batch i
+ * opens batch_sizes[i] polynomials at the extension point points[2i..2i+2]; the polynomials of all batches are
+ * listed one after the other as FriPolynomialInfo { oracle_index, polynomial_index }.
+ * final_poly_out: optional, 2^n_log x 2 (interleaved, canonical, last coefficient 0 as divide_by_linear's
+ * padding leaves it). */
+const char *mp2gpu_fri_begin_openings(const mp2gpu_batch *const *oracles, size_t noracles,
+                                      const uint64_t *points, const uint32_t *batch_sizes, size_t nbatches,
+                                      const uint32_t *oracle_index, const uint32_t *polynomial_index,
+                                      const uint64_t alpha[2], uint32_t cap_height, uint32_t hash_kind,
+                                      uint64_t *final_poly_out, mp2gpu_fri **out);
 /* cap_out: 2^cap_height x 4. */
 const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t *cap_out);
 const char *mp2gpu_fri_fold(mp2gpu_fri *f, const uint64_t beta[2]);

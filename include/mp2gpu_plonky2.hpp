@@ -7,12 +7,15 @@
 //       circuit_data.prove at recursion-framework/src/circuit_builder.rs:308 and builder.build at :177)
 //   MerkleTree::new_ / prove / get, MerkleCap, MerkleProof          (plonky2 hash/merkle_tree.rs; called
 //       directly at recursion-framework/src/universal_verifier_gadget/circuit_set.rs:189, :216)
+//   FriInstanceInfo / FriBatchInfo / FriPolynomialInfo, the head of PolynomialBatch::prove_openings and the
+//       fri_committed_trees loop (plonky2 fri/{structure,oracle,prover}.rs; same call sites as from_values)
 //
 // Where Rust panics (MerkleTree::new with cap_height > log2(len), non power-of-two lengths) this throws
 // mp2gpu::Panic.  Header only; link with -lmp2gpu.
 #pragma once
 #include <array>
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -114,20 +117,25 @@ struct PolynomialBatch {
   MerkleTree<H> merkle_tree;
   size_t degree_log = 0, rate_bits = 0;
   bool blinding = false;
+  // the copy of this batch that stays in HBM for prove_openings and the query rounds (released with the last
+  // C++ copy of the batch); empty when the batch was built with keep_on_device = false
+  std::shared_ptr<mp2gpu_batch> device;
 
   // PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table):
   // timing / fft_root_table have no GPU counterpart (twiddles are device resident) and are omitted.
   static PolynomialBatch from_values(const std::vector<PolynomialValues> &values, size_t rate_bits, bool blinding,
-                                     size_t cap_height) {
+                                     size_t cap_height, bool keep_on_device = true) {
     std::vector<const uint64_t *> cols(values.size());
     for (size_t c = 0; c < values.size(); c++) cols[c] = values[c].values.data();
-    return commit(cols, values.empty() ? 0 : values[0].values.size(), rate_bits, blinding, cap_height, false);
+    return commit(cols, values.empty() ? 0 : values[0].values.size(), rate_bits, blinding, cap_height, false,
+                  keep_on_device);
   }
   static PolynomialBatch from_coeffs(const std::vector<PolynomialCoeffs> &polys, size_t rate_bits, bool blinding,
-                                     size_t cap_height) {
+                                     size_t cap_height, bool keep_on_device = true) {
     std::vector<const uint64_t *> cols(polys.size());
     for (size_t c = 0; c < polys.size(); c++) cols[c] = polys[c].coeffs.data();
-    return commit(cols, polys.empty() ? 0 : polys[0].coeffs.size(), rate_bits, blinding, cap_height, true);
+    return commit(cols, polys.empty() ? 0 : polys[0].coeffs.size(), rate_bits, blinding, cap_height, true,
+                  keep_on_device);
   }
   // get_lde_values(index, step): leaves[reverse_bits(index * step, degree_log + rate_bits)]
   const std::vector<F> &get_lde_values(size_t index, size_t step) const {
@@ -136,7 +144,7 @@ struct PolynomialBatch {
 
  private:
   static PolynomialBatch commit(const std::vector<const uint64_t *> &cols, size_t n, size_t rate_bits, bool blinding,
-                                size_t cap_height, bool from_coeffs) {
+                                size_t cap_height, bool from_coeffs, bool keep_on_device) {
     if (blinding) throw Panic("blinding (salted) batches are not supported on the GPU path");
     size_t n_log = 0;
     while ((size_t(1) << n_log) < n) n_log++;
@@ -155,14 +163,99 @@ struct PolynomialBatch {
     b.merkle_tree.digests.resize(N > ncap ? 2 * (N - ncap) : 0);
     b.merkle_tree.cap.hashes.resize(ncap);
     auto fn = from_coeffs ? mp2gpu_commit_from_coeffs : mp2gpu_commit_from_values;
+    mp2gpu_batch *handle = nullptr;
     check(fn(cols.data(), ncols, (uint32_t)n_log, (uint32_t)rate_bits, (uint32_t)cap_height, (uint32_t)H,
              coeff_ptrs.data(), flat.data(),
              b.merkle_tree.digests.empty() ? nullptr : b.merkle_tree.digests[0].data(),
-             b.merkle_tree.cap.hashes[0].data(), nullptr));
+             b.merkle_tree.cap.hashes[0].data(), keep_on_device ? &handle : nullptr));
+    if (handle) b.device.reset(handle, mp2gpu_batch_free);
     b.merkle_tree.leaves.resize(N);
     for (size_t i = 0; i < N; i++) b.merkle_tree.leaves[i].assign(flat.begin() + i * ncols, flat.begin() + (i + 1) * ncols);
     return b;
   }
 };
+
+// ---- FRI: instance description (plonky2 fri/structure.rs) and the prover's commit phase ----------------
+using Ext = std::array<F, 2>;  // QuadraticExtension<GoldilocksField>: a0 + a1 X, X^2 = 7
+struct FriPolynomialInfo {
+  size_t oracle_index, polynomial_index;
+};
+struct FriBatchInfo {
+  Ext point;
+  std::vector<FriPolynomialInfo> polynomials;
+};
+struct FriInstanceInfo {
+  std::vector<FriBatchInfo> batches;  // `oracles: Vec<FriOracleInfo>` only carries blinding flags (always false here)
+};
+
+// The polynomial FRI runs on and the fri_committed_trees loop over it, device resident.  The challenger stays
+// with the caller: observe the cap commit_layer returns, draw beta, fold.
+template <Hasher H>
+struct FriCommitPhase {
+  std::shared_ptr<mp2gpu_fri> state;
+  size_t cap_height = 0;
+  std::vector<Ext> final_poly;  // filled by prove_openings_begin when asked for
+
+  // lde_polynomial_coeffs of fri_proof, without its zero padding
+  static FriCommitPhase begin(const std::vector<Ext> &coeffs, size_t rate_bits, size_t cap_height) {
+    size_t n_log = 0;
+    while ((size_t(1) << n_log) < coeffs.size()) n_log++;
+    if (coeffs.empty() || (size_t(1) << n_log) != coeffs.size()) throw Panic("polynomial length must be a power of two");
+    mp2gpu_fri *f = nullptr;
+    check(mp2gpu_fri_begin(coeffs[0].data(), (uint32_t)n_log, (uint32_t)rate_bits, (uint32_t)cap_height, (uint32_t)H, &f));
+    FriCommitPhase ph;
+    ph.state.reset(f, mp2gpu_fri_free);
+    ph.cap_height = cap_height;
+    return ph;
+  }
+  // MerkleTree::new(chunked values, cap_height).cap of the next reduction layer
+  MerkleCap commit_layer(size_t arity_bits) {
+    MerkleCap cap;
+    cap.hashes.resize(size_t(1) << cap_height);
+    check(mp2gpu_fri_commit_layer(state.get(), (uint32_t)arity_bits, cap.hashes[0].data()));
+    return cap;
+  }
+  void fold(const Ext &beta) { check(mp2gpu_fri_fold(state.get(), beta.data())); }
+  std::vector<Ext> finish() {
+    size_t len = 0;
+    check(mp2gpu_fri_finish(state.get(), nullptr, &len));
+    std::vector<Ext> out(len);
+    check(mp2gpu_fri_finish(state.get(), out[0].data(), &len));
+    return out;
+  }
+};
+
+// PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params, timing) up to its call of fri_proof:
+// alpha = challenger.get_extension_challenge() is drawn by the caller; the alpha-batched quotient is built from the
+// oracles' device-resident coefficients and stays in HBM as the commit phase's polynomial.
+template <Hasher H>
+FriCommitPhase<H> prove_openings_begin(const FriInstanceInfo &instance, const std::vector<const PolynomialBatch<H> *> &oracles,
+                                       const Ext &alpha, size_t cap_height, bool want_final_poly = false) {
+  std::vector<const mp2gpu_batch *> handles;
+  for (auto *o : oracles) {
+    if (!o || !o->device) throw Panic("prove_openings needs device-resident oracles (keep_on_device)");
+    handles.push_back(o->device.get());
+  }
+  std::vector<uint64_t> points;
+  std::vector<uint32_t> sizes, oi, pi;
+  for (auto &b : instance.batches) {
+    points.push_back(b.point[0]);
+    points.push_back(b.point[1]);
+    sizes.push_back((uint32_t)b.polynomials.size());
+    for (auto &p : b.polynomials) {
+      oi.push_back((uint32_t)p.oracle_index);
+      pi.push_back((uint32_t)p.polynomial_index);
+    }
+  }
+  FriCommitPhase<H> ph;
+  ph.cap_height = cap_height;
+  if (want_final_poly && !oracles.empty() && oracles[0]) ph.final_poly.resize(size_t(1) << oracles[0]->degree_log);
+  mp2gpu_fri *f = nullptr;
+  check(mp2gpu_fri_begin_openings(handles.data(), handles.size(), points.data(), sizes.data(), sizes.size(), oi.data(),
+                                  pi.data(), alpha.data(), (uint32_t)cap_height, (uint32_t)H,
+                                  ph.final_poly.empty() ? nullptr : ph.final_poly[0].data(), &f));
+  ph.state.reset(f, mp2gpu_fri_free);
+  return ph;
+}
 
 }  // namespace mp2gpu

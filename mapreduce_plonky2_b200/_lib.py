@@ -48,6 +48,8 @@ SIGNATURES = {
     "mp2gpu_batch_shape": (_ERR, [C.c_void_p, size_p, u32p, u32p, u32p, u32p]),
     "mp2gpu_batch_free": (None, [C.c_void_p]),
     "mp2gpu_fri_begin": (_ERR, [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "mp2gpu_fri_begin_openings": (_ERR, [C.POINTER(C.c_void_p), C.c_size_t, u64p, u32p, C.c_size_t, u32p, u32p, u64p,
+                                         C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_void_p)]),
     "mp2gpu_fri_commit_layer": (_ERR, [C.c_void_p, C.c_uint32, u64p]),
     "mp2gpu_fri_fold": (_ERR, [C.c_void_p, u64p]),
     "mp2gpu_fri_layer_shape": (_ERR, [C.c_void_p, C.c_uint32, size_p, size_p, size_p, size_p]),

@@ -59,26 +59,6 @@ const char *to_c(const Status &s) {
   return p;
 }
 
-// RAII for stream-ordered scratch
-struct DevBuf {
-  u64 *p = nullptr;
-  cudaStream_t st = nullptr;
-  Status alloc(size_t elems, cudaStream_t s) {
-    st = s;
-    if (elems == 0) elems = 1;
-    MP2_CUDA(cudaMallocAsync(&p, elems * sizeof(u64), s));
-    return "";
-  }
-  u64 *release() {
-    u64 *r = p;
-    p = nullptr;
-    return r;
-  }
-  ~DevBuf() {
-    if (p) cudaFreeAsync(p, st);
-  }
-};
-
 // Column-wise host<->device copies, merged over runs of columns that are adjacent in host memory (one
 // transfer for a contiguous matrix; one per column for separately allocated Vecs -- each cudaMemcpyAsync
 // costs a few microseconds of launch time, which at 135 columns was a fifth of a config-1 call).
@@ -129,13 +109,6 @@ Status dev_commit(const u64 *cols, size_t ncols, u32 n_log, u32 rate_bits, u32 c
 
 }  // namespace
 }  // namespace mp2
-
-struct mp2gpu_batch {
-  int device;
-  size_t ncols;
-  u32 n_log, rate_bits, cap_height, hash_kind;
-  u64 *coeffs, *lde, *leaves, *digests, *cap;  // device
-};
 
 using namespace mp2;
 

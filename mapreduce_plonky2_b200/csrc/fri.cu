@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <memory>
 #include <vector>
 
 #include "../../include/mp2gpu.h"
@@ -80,6 +81,171 @@ Status fri_deinterleave(const u64 *in, u64 *out, size_t stride, size_t len, cuda
   return "";
 }
 
+// ---- prove_openings: the alpha-batched quotient that becomes FRI's input polynomial -------------------------
+// Replaces the loop of PolynomialBatch::prove_openings (plonky2 0.2.2 fri/oracle.rs) and the ReducingFactor
+// calls it makes (util/reducing.rs: reduce_polys_base, shift_poly), reached from every prove() of the
+// reference right after the three batch commitments (recursion-framework/src/circuit_builder.rs:308):
+//   final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i),   F_i = sum_j alpha^j f_ij.
+
+// F[m] = sum_j alpha^j f_j[m]: one thread per coefficient, the batch's columns streamed once (coalesced)
+__global__ void k_fri_reduce_polys(const u64 *const *__restrict__ polys, const u64 *__restrict__ pw, size_t pw_stride,
+                                   u32 count, size_t n, u64 *__restrict__ out, size_t out_stride) {
+  size_t m = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  u64 a = 0, b = 0;
+  for (u32 j = 0; j < count; j++) {
+    const u64 v = polys[j][m];
+    a = gl_mul_add(v, pw[j], a);
+    b = gl_mul_add(v, pw[pw_stride + j], b);
+  }
+  out[m] = a;
+  out[out_stride + m] = b;
+}
+
+// divide_by_linear is the recurrence b_k = b_(k+1) z + a_k run from the top coefficient down, quotient
+// coefficient k = b_(k+1): an exclusive weighted suffix sum  E[k] = sum_{m>k} x[m] w^(m-k-1)  with w = z.
+// One CTA covers kScanT * kScanL elements: Horner over kScanL per thread, a Hillis-Steele suffix scan over the
+// thread partials in shared memory (the weights w^(L 2^s) come from the host), Horner again to emit.
+// TOTALS = true writes only the CTA's inclusive total; the totals are scanned by the same kernel one level up
+// (weight w^(T L)) and come back as `carry`.
+constexpr int kScanT = 256, kScanL = 4, kScanSteps = 8;
+struct ScanPows {
+  u64 a[kScanSteps], b[kScanSteps];
+};
+template <bool TOTALS>
+__global__ void __launch_bounds__(kScanT)
+k_suffix_scan(const u64 *__restrict__ x, size_t xs, size_t len, Ext w, Ext wL, ScanPows pw,
+              const u64 *__restrict__ carry, size_t cs, u64 *out, size_t os, Ext scale, int fresh) {
+  __shared__ u64 va[kScanT], vb[kScanT];
+  const int t = threadIdx.x;
+  const size_t start = ((size_t)blockIdx.x * kScanT + t) * kScanL;
+  Ext xv[kScanL];
+#pragma unroll
+  for (int i = 0; i < kScanL; i++) {
+    const size_t idx = start + i;
+    xv[i].a = idx < len ? x[idx] : 0;
+    xv[i].b = idx < len ? x[xs + idx] : 0;
+  }
+  Ext s = {0, 0};
+#pragma unroll
+  for (int i = kScanL - 1; i >= 0; i--) {
+    s = ext_mul(s, w);
+    s.a = gl_add(s.a, xv[i].a);
+    s.b = gl_add(s.b, xv[i].b);
+  }
+  Ext k_in = {0, 0};  // suffix sum of everything after this CTA, relative to the CTA's end
+  if (!TOTALS && carry) {
+    k_in.a = carry[blockIdx.x];
+    k_in.b = carry[cs + blockIdx.x];
+    if (t == kScanT - 1) {
+      Ext p = ext_mul(k_in, wL);
+      s.a = gl_add(s.a, p.a);
+      s.b = gl_add(s.b, p.b);
+    }
+  }
+  va[t] = s.a;
+  vb[t] = s.b;
+  __syncthreads();
+  for (int sft = 0; sft < kScanSteps; sft++) {
+    const int d = 1 << sft;
+    const bool has = t + d < kScanT;
+    Ext add = {0, 0};
+    if (has) add = ext_mul(Ext{va[t + d], vb[t + d]}, Ext{pw.a[sft], pw.b[sft]});
+    __syncthreads();
+    if (has) {
+      va[t] = gl_add(va[t], add.a);
+      vb[t] = gl_add(vb[t], add.b);
+    }
+    __syncthreads();
+  }
+  if (TOTALS) {
+    if (t == 0) {
+      out[blockIdx.x] = va[0];
+      out[os + blockIdx.x] = vb[0];
+    }
+    return;
+  }
+  Ext b = t + 1 < kScanT ? Ext{va[t + 1], vb[t + 1]} : k_in;
+#pragma unroll
+  for (int i = kScanL - 1; i >= 0; i--) {
+    const size_t idx = start + i;
+    if (idx < len) {
+      Ext e = b;
+      if (!fresh) {  // shift_poly then +=
+        Ext o = ext_mul(Ext{out[idx], out[os + idx]}, scale);
+        e.a = gl_add(e.a, o.a);
+        e.b = gl_add(e.b, o.b);
+      }
+      out[idx] = gl_canon(e.a);
+      out[os + idx] = gl_canon(e.b);
+    }
+    b = ext_mul(b, w);
+    b.a = gl_add(b.a, xv[i].a);
+    b.b = gl_add(b.b, xv[i].b);
+  }
+}
+
+// host-side extension arithmetic (a handful of powers per call; no data-path work)
+struct HExt {
+  u64 a, b;
+};
+static u64 h_add(u64 a, u64 b) { return (u64)(((unsigned __int128)a + b) % kP); }
+static HExt hx_mul(HExt x, HExt y) {
+  return {h_add(h_mul(x.a, y.a), h_mul(7, h_mul(x.b, y.b))), h_add(h_mul(x.a, y.b), h_mul(x.b, y.a))};
+}
+static HExt hx_pow(HExt x, u64 e) {
+  HExt r = {1, 0};
+  while (e) {
+    if (e & 1) r = hx_mul(r, x);
+    x = hx_mul(x, x);
+    e >>= 1;
+  }
+  return r;
+}
+
+static Status suffix_scan(const u64 *x, size_t xs, size_t len, HExt w, u64 *out, size_t os, HExt scale, bool fresh,
+                          cudaStream_t st) {
+  const size_t per = (size_t)kScanT * kScanL, nb = (len + per - 1) / per;
+  if (nb > 0x7fffffffull) return "polynomial too long for the quotient scan";
+  const HExt wL = hx_pow(w, kScanL);
+  ScanPows pw;
+  HExt p = wL;
+  for (int s = 0; s < kScanSteps; s++) {
+    pw.a[s] = p.a;
+    pw.b[s] = p.b;
+    p = hx_mul(p, p);
+  }  // p = w^(T L)
+  const Ext dw = {w.a, w.b}, dwL = {wL.a, wL.b}, dscale = {scale.a, scale.b};
+  if (nb <= 1) {
+    { ProfScope _p("k_suffix_scan", st); k_suffix_scan<false><<<1, kScanT, 0, st>>>(x, xs, len, dw, dwL, pw, nullptr, 0, out, os, dscale, fresh ? 1 : 0); }
+    MP2_LAUNCH_CHECK();
+    return "";
+  }
+  DevBuf tot, car;
+  MP2_TRY(tot.alloc(2 * nb, st));
+  MP2_TRY(car.alloc(2 * nb, st));
+  { ProfScope _p("k_suffix_scan", st); k_suffix_scan<true><<<(unsigned)nb, kScanT, 0, st>>>(x, xs, len, dw, dwL, pw, nullptr, 0, tot.p, nb, dscale, 1); }
+  MP2_LAUNCH_CHECK();
+  MP2_TRY(suffix_scan(tot.p, nb, nb, p, car.p, nb, HExt{0, 0}, true, st));
+  { ProfScope _p("k_suffix_scan", st); k_suffix_scan<false><<<(unsigned)nb, kScanT, 0, st>>>(x, xs, len, dw, dwL, pw, car.p, nb, out, os, dscale, fresh ? 1 : 0); }
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+
+Status fri_reduce_polys_strided(const u64 *const *polys, const u64 *pw, size_t pw_stride, u32 count, size_t n, u64 *out,
+                                size_t out_stride, cudaStream_t st) {
+  if (!n) return "";
+  { ProfScope _p("k_fri_reduce_polys", st); k_fri_reduce_polys<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(polys, pw, pw_stride, count, n, out, out_stride); }
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+Status fri_divide_accumulate(const u64 *x, size_t x_stride, size_t len, const u64 z[2], u64 *acc, size_t acc_stride,
+                             const u64 scale[2], bool fresh, cudaStream_t st) {
+  if (!len) return "";
+  return suffix_scan(x, x_stride, len, HExt{z[0] % kP, z[1] % kP}, acc, acc_stride, HExt{scale[0] % kP, scale[1] % kP},
+                     fresh, st);
+}
+
 }  // namespace mp2
 
 using namespace mp2;
@@ -123,6 +289,31 @@ const char *guard(F f) {
     return dup_c("unknown exception");
   }
 }
+struct FriDeleter {
+  void operator()(mp2gpu_fri *f) const { mp2gpu_fri_free(f); }
+};
+typedef std::unique_ptr<mp2gpu_fri, FriDeleter> FriPtr;
+// device < 0: the calling thread's current device
+Status new_fri(u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind, int device, FriPtr *out, cudaStream_t *st) {
+  if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
+  if (n_log + rate_bits > 32) return "degree_log + rate_bits exceeds two-adicity 32";
+  cudaError_t e = device < 0 ? cudaGetDevice(&device) : cudaSetDevice(device);
+  if (e != cudaSuccess) return std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
+  FriPtr f(new mp2gpu_fri());
+  f->device = device;
+  f->n_log = n_log;
+  f->rate_bits = rate_bits;
+  f->cap_height = cap_height;
+  f->hash_kind = hash_kind;
+  f->shift = kCosetShift;
+  f->last_arity_bits = 0;
+  f->committed = false;
+  f->coeffs = nullptr;
+  MP2_CUDA(cudaMalloc(&f->coeffs, sizeof(u64) * 2 * ((size_t)1 << n_log)));
+  *st = cudaStreamPerThread;
+  *out = std::move(f);
+  return "";
+}
 }  // namespace
 
 extern "C" {
@@ -131,31 +322,86 @@ const char *mp2gpu_fri_begin(const uint64_t *coeffs_ext, uint32_t n_log, uint32_
                              uint32_t hash_kind, mp2gpu_fri **out) {
   return guard([&]() -> Status {
     if (!coeffs_ext || !out) return "null coeffs / out";
-    if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
-    if (n_log + rate_bits > 32) return "degree_log + rate_bits exceeds two-adicity 32";
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
-    cudaStream_t st = cudaStreamPerThread;
+    FriPtr f;
+    cudaStream_t st;
+    MP2_TRY(new_fri(n_log, rate_bits, cap_height, hash_kind, -1, &f, &st));
     const size_t n = (size_t)1 << n_log;
-    mp2gpu_fri *f = new mp2gpu_fri();
-    f->device = dev;
-    f->n_log = n_log;
-    f->rate_bits = rate_bits;
-    f->cap_height = cap_height;
-    f->hash_kind = hash_kind;
-    f->shift = kCosetShift;
-    f->last_arity_bits = 0;
-    f->committed = false;
-    f->coeffs = nullptr;
-    u64 *tmp = nullptr;
-    MP2_CUDA(cudaMalloc(&f->coeffs, sizeof(u64) * 2 * n));
-    MP2_CUDA(cudaMallocAsync(&tmp, sizeof(u64) * 2 * n, st));
-    MP2_CUDA(cudaMemcpyAsync(tmp, coeffs_ext, sizeof(u64) * 2 * n, cudaMemcpyHostToDevice, st));
-    MP2_TRY(fri_deinterleave(tmp, f->coeffs, n, n, st));
-    MP2_CUDA(cudaFreeAsync(tmp, st));
+    DevBuf tmp;
+    MP2_TRY(tmp.alloc(2 * n, st));
+    MP2_CUDA(cudaMemcpyAsync(tmp.p, coeffs_ext, sizeof(u64) * 2 * n, cudaMemcpyHostToDevice, st));
+    MP2_TRY(fri_deinterleave(tmp.p, f->coeffs, n, n, st));
     MP2_CUDA(cudaStreamSynchronize(st));
-    *out = f;
+    *out = f.release();
+    return "";
+  });
+}
+
+const char *mp2gpu_fri_begin_openings(const mp2gpu_batch *const *oracles, size_t noracles, const uint64_t *points,
+                                      const uint32_t *batch_sizes, size_t nbatches, const uint32_t *oracle_index,
+                                      const uint32_t *polynomial_index, const uint64_t alpha[2], uint32_t cap_height,
+                                      uint32_t hash_kind, uint64_t *final_poly_out, mp2gpu_fri **out) {
+  return guard([&]() -> Status {
+    if (!oracles || !noracles || !points || !batch_sizes || !nbatches || !oracle_index || !polynomial_index || !alpha || !out)
+      return "prove_openings: null / empty argument";
+    for (size_t o = 0; o < noracles; o++) {
+      if (!oracles[o]) return "prove_openings: null oracle handle";
+      if (oracles[o]->n_log != oracles[0]->n_log || oracles[o]->rate_bits != oracles[0]->rate_bits ||
+          oracles[o]->device != oracles[0]->device)
+        return "prove_openings: the oracles must share degree, rate_bits and device";
+    }
+    const u32 n_log = oracles[0]->n_log;
+    const size_t n = (size_t)1 << n_log;
+    size_t total = 0, max_count = 0;
+    for (size_t i = 0; i < nbatches; i++) {
+      if (!batch_sizes[i]) return "prove_openings: empty batch";
+      total += batch_sizes[i];
+      if (batch_sizes[i] > max_count) max_count = batch_sizes[i];
+    }
+    std::vector<const u64 *> ptrs(total);
+    for (size_t j = 0; j < total; j++) {
+      if (oracle_index[j] >= noracles) return "prove_openings: oracle_index " + std::to_string(oracle_index[j]) + " out of range";
+      const mp2gpu_batch *b = oracles[oracle_index[j]];
+      if (polynomial_index[j] >= b->ncols)
+        return "prove_openings: polynomial_index " + std::to_string(polynomial_index[j]) + " out of range (oracle has " +
+               std::to_string(b->ncols) + " polynomials)";
+      ptrs[j] = b->coeffs + (size_t)polynomial_index[j] * n;
+    }
+    // alpha^j, j < the largest batch: base.powers() restarts for every batch
+    const HExt al = {alpha[0] % kP, alpha[1] % kP};
+    std::vector<u64> pw(2 * max_count);
+    HExt cur = {1, 0};
+    for (size_t j = 0; j < max_count; j++) {
+      pw[j] = cur.a;
+      pw[max_count + j] = cur.b;
+      cur = hx_mul(cur, al);
+    }
+    FriPtr f;
+    cudaStream_t st;
+    MP2_TRY(new_fri(n_log, oracles[0]->rate_bits, cap_height, hash_kind, oracles[0]->device, &f, &st));
+    DevBuf d_ptrs, d_pw, comp;
+    MP2_TRY(d_ptrs.alloc(total, st));
+    MP2_TRY(d_pw.alloc(2 * max_count, st));
+    MP2_TRY(comp.alloc(2 * n, st));
+    MP2_CUDA(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), sizeof(u64 *) * total, cudaMemcpyHostToDevice, st));
+    MP2_CUDA(cudaMemcpyAsync(d_pw.p, pw.data(), sizeof(u64) * 2 * max_count, cudaMemcpyHostToDevice, st));
+    size_t at = 0;
+    for (size_t i = 0; i < nbatches; i++) {
+      const u32 count = batch_sizes[i];
+      // the powers table is component-major over max_count entries; a batch of `count` reads a prefix of each half
+      MP2_TRY(fri_reduce_polys_strided((const u64 *const *)d_ptrs.p + at, d_pw.p, max_count, count, n, comp.p, n, st));
+      const HExt shift = hx_pow(al, count);  // ReducingFactor::shift_poly: alpha^count of THIS batch
+      const u64 sc[2] = {shift.a, shift.b};
+      MP2_TRY(fri_divide_accumulate(comp.p, n, n, (const u64 *)points + 2 * i, f->coeffs, n, sc, i == 0, st));
+      at += count;
+    }
+    if (final_poly_out) {
+      DevBuf tmp;
+      MP2_TRY(tmp.alloc(2 * n, st));
+      MP2_TRY(fri_interleave(f->coeffs, n, tmp.p, n, st));
+      MP2_CUDA(cudaMemcpyAsync(final_poly_out, tmp.p, sizeof(u64) * 2 * n, cudaMemcpyDeviceToHost, st));
+    }
+    MP2_CUDA(cudaStreamSynchronize(st));
+    *out = f.release();
     return "";
   });
 }
@@ -178,18 +424,27 @@ const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t
       return "MerkleTree::new: cap_height=" + std::to_string(cap_h) + " should be at most log2(leaves.len())=" + std::to_string(leaves_log);
     L.ncap = (size_t)1 << cap_h;
     L.ndigests = 2 * (L.nleaves - L.ncap);
-    u64 *vals = nullptr;
-    MP2_CUDA(cudaMallocAsync(&vals, sizeof(u64) * 2 * N, st));
-    // values on the coset shift*<w_N>, leaf (= bit-reversed) order, both components
-    MP2_TRY(ntt_coset_lde(f->coeffs, n, vals, N, 2, f->n_log, f->rate_bits, 0, 0, st, nullptr, f->shift));
-    MP2_CUDA(cudaMalloc(&L.leaves, sizeof(u64) * 2 * N));
-    MP2_CUDA(cudaMalloc(&L.digests, sizeof(u64) * 4 * (L.ndigests ? L.ndigests : 1)));
-    MP2_CUDA(cudaMalloc(&L.cap, sizeof(u64) * 4 * L.ncap));
-    MP2_TRY(fri_interleave(vals, N, L.leaves, N, st));
-    MP2_CUDA(cudaFreeAsync(vals, st));
-    MP2_TRY(merkle_rowmajor(L.leaves, L.nleaves, L.leaf_len, cap_h, f->hash_kind, L.digests, L.cap, st));
-    MP2_CUDA(cudaMemcpyAsync(cap_out, L.cap, sizeof(u64) * 4 * L.ncap, cudaMemcpyDeviceToHost, st));
-    MP2_CUDA(cudaStreamSynchronize(st));
+    L.leaves = L.digests = L.cap = nullptr;
+    Status built = [&]() -> Status {
+      DevBuf vals;
+      MP2_TRY(vals.alloc(2 * N, st));
+      // values on the coset shift*<w_N>, leaf (= bit-reversed) order, both components
+      MP2_TRY(ntt_coset_lde(f->coeffs, n, vals.p, N, 2, f->n_log, f->rate_bits, 0, 0, st, nullptr, f->shift));
+      MP2_CUDA(cudaMalloc(&L.leaves, sizeof(u64) * 2 * N));
+      MP2_CUDA(cudaMalloc(&L.digests, sizeof(u64) * 4 * (L.ndigests ? L.ndigests : 1)));
+      MP2_CUDA(cudaMalloc(&L.cap, sizeof(u64) * 4 * L.ncap));
+      MP2_TRY(fri_interleave(vals.p, N, L.leaves, N, st));
+      MP2_TRY(merkle_rowmajor(L.leaves, L.nleaves, L.leaf_len, cap_h, f->hash_kind, L.digests, L.cap, st));
+      MP2_CUDA(cudaMemcpyAsync(cap_out, L.cap, sizeof(u64) * 4 * L.ncap, cudaMemcpyDeviceToHost, st));
+      MP2_CUDA(cudaStreamSynchronize(st));
+      return "";
+    }();
+    if (!built.empty()) {
+      cudaFree(L.leaves);
+      cudaFree(L.digests);
+      cudaFree(L.cap);
+      return built;
+    }
     f->layers.push_back(L);
     f->last_arity_bits = arity_bits;
     f->committed = true;
@@ -207,8 +462,12 @@ const char *mp2gpu_fri_fold(mp2gpu_fri *f, const uint64_t beta[2]) {
     const size_t n = (size_t)1 << f->n_log, n_out = n >> ab;
     u64 *next = nullptr;
     MP2_CUDA(cudaMalloc(&next, sizeof(u64) * 2 * n_out));
-    MP2_TRY(fri_fold(f->coeffs, n, next, n_out, n_out, ab, beta[0] % kP, beta[1] % kP, st));
-    MP2_CUDA(cudaStreamSynchronize(st));
+    Status folded = fri_fold(f->coeffs, n, next, n_out, n_out, ab, beta[0] % kP, beta[1] % kP, st);
+    if (folded.empty() && cudaStreamSynchronize(st) != cudaSuccess) folded = "fri_fold: stream synchronize failed";
+    if (!folded.empty()) {
+      cudaFree(next);
+      return folded;
+    }
     MP2_CUDA(cudaFree(f->coeffs));
     f->coeffs = next;
     f->n_log -= ab;
@@ -269,11 +528,10 @@ const char *mp2gpu_fri_finish(mp2gpu_fri *f, uint64_t *final_coeffs_out, size_t 
     const size_t n = (size_t)1 << f->n_log;
     if (len_out) *len_out = n;
     if (final_coeffs_out) {
-      u64 *tmp = nullptr;
-      MP2_CUDA(cudaMallocAsync(&tmp, sizeof(u64) * 2 * n, st));
-      MP2_TRY(fri_interleave(f->coeffs, n, tmp, n, st));
-      MP2_CUDA(cudaMemcpyAsync(final_coeffs_out, tmp, sizeof(u64) * 2 * n, cudaMemcpyDeviceToHost, st));
-      MP2_CUDA(cudaFreeAsync(tmp, st));
+      DevBuf tmp;
+      MP2_TRY(tmp.alloc(2 * n, st));
+      MP2_TRY(fri_interleave(f->coeffs, n, tmp.p, n, st));
+      MP2_CUDA(cudaMemcpyAsync(final_coeffs_out, tmp.p, sizeof(u64) * 2 * n, cudaMemcpyDeviceToHost, st));
       MP2_CUDA(cudaStreamSynchronize(st));
     }
     return "";

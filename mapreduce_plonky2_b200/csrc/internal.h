@@ -50,6 +50,29 @@ struct ProfScope {
     MP2_CUDA(cudaGetLastError()); \
   } while (0)
 
+// Stream-ordered scratch, returned to the pool on every exit path
+struct DevBuf {
+  u64 *p = nullptr;
+  cudaStream_t st = nullptr;
+  DevBuf() = default;
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  Status alloc(size_t elems, cudaStream_t s) {
+    st = s;
+    if (elems == 0) elems = 1;
+    MP2_CUDA(cudaMallocAsync(&p, elems * sizeof(u64), s));
+    return "";
+  }
+  u64 *release() {
+    u64 *r = p;
+    p = nullptr;
+    return r;
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+
 // ---- host-side Goldilocks helpers (table seeds only; no data-path work happens on the host) ----
 static const u64 kP = 0xFFFFFFFF00000001ULL;
 inline u64 h_mul(u64 a, u64 b) { return (u64)(((unsigned __int128)a * b) % kP); }
@@ -131,6 +154,16 @@ Status merkle_open(const u64 *leaves_rowmajor, const u64 *lde_colmajor, size_t l
                    const u64 *digests, size_t nleaves, u32 cap_height, const u64 *idx_host, size_t count,
                    u64 *rows_out_host, u64 *siblings_out_host, cudaStream_t st);
 
+// ---- prove_openings (fri.cu) ----
+// out[m] (+ out[stride + m]) = sum_j pw[j] * polys[j][m]: ReducingFactor::reduce_polys_base.  polys / pw are
+// device arrays (count pointers; powers component-major, the two halves pw_stride apart)
+Status fri_reduce_polys_strided(const u64 *const *polys, const u64 *pw, size_t pw_stride, u32 count, size_t n, u64 *out,
+                                size_t out_stride, cudaStream_t st);
+// acc[k] = acc[k] * scale + sum_{m > k} x[m] * z^(m-k-1)   (divide_by_linear + push(0), then shift_poly / +=);
+// `fresh` skips the read of acc.  x, acc: component-major extension polynomials of length len.
+Status fri_divide_accumulate(const u64 *x, size_t x_stride, size_t len, const u64 z[2], u64 *acc, size_t acc_stride,
+                             const u64 scale[2], bool fresh, cudaStream_t st);
+
 inline int log2_exact(size_t n) {
   if (n == 0 || (n & (n - 1))) return -1;
   int l = 0;
@@ -139,3 +172,11 @@ inline int log2_exact(size_t n) {
 }
 
 }  // namespace mp2
+
+// Device-resident PolynomialBatch behind the C ABI's opaque handle (api.cu creates it, fri.cu reads coeffs).
+struct mp2gpu_batch {
+  int device;
+  size_t ncols;
+  u32 n_log, rate_bits, cap_height, hash_kind;
+  u64 *coeffs, *lde, *leaves, *digests, *cap;  // device; coeffs: ncols x n, lde: ncols x N, column-major
+};

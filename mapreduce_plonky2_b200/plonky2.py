@@ -378,6 +378,42 @@ class FriCommitPhase:
         self.num_layers = 0
         _lib.call("mp2gpu_fri_begin", _ptr(c), n_log, rate_bits, cap_height, hash_kind, C.byref(self._h))
 
+    @classmethod
+    def from_openings(cls, oracles, batches, alpha, cap_height: int, hash_kind: int = POSEIDON2, want_final_poly=False):
+        """``PolynomialBatch::prove_openings`` up to ``fri_proof``: the alpha-batched quotient of the opened
+        polynomials, computed from the coefficients the ``oracles`` (device-resident :class:`PolynomialBatch`
+        objects, ``FRI_ORACLES`` order) hold in HBM, and kept there as this commit phase's polynomial.
+
+        ``batches``: ``[(point [z0, z1], [(oracle_index, polynomial_index), ...]), ...]`` -- plonky2's
+        ``FriBatchInfo { point, polynomials: Vec<FriPolynomialInfo> }``.  With ``want_final_poly`` the (n, 2)
+        coefficients are also returned (``self.final_poly``)."""
+        if not oracles or not batches:
+            raise Mp2GpuError("prove_openings: no oracles / no batches")
+        handles = []
+        for o in oracles:
+            if getattr(o, "_handle", None) is None or not o._handle:
+                raise Mp2GpuError("prove_openings needs device-resident batches (keep_on_device=True)")
+            handles.append(o._handle)
+        harr = (C.c_void_p * len(handles))(*[h.value if isinstance(h, C.c_void_p) else h for h in handles])
+        points = np.ascontiguousarray(np.concatenate([_arr(z).reshape(2) for z, _ in batches]))
+        sizes = np.array([len(polys) for _, polys in batches], dtype=np.uint32)
+        oi = np.array([p[0] for _, polys in batches for p in polys], dtype=np.uint32)
+        pi = np.array([p[1] for _, polys in batches for p in polys], dtype=np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        self = cls.__new__(cls)
+        self.hash_kind, self.cap_height, self.rate_bits = hash_kind, cap_height, oracles[0].rate_bits
+        self._h = C.c_void_p(None)
+        self.num_layers = 0
+        self.final_poly = None
+        out = None
+        if want_final_poly:
+            out = np.zeros((1 << oracles[0].degree_log, 2), dtype=np.uint64)
+        _lib.call("mp2gpu_fri_begin_openings", harr, len(handles), _ptr(points), sizes.ctypes.data_as(u32p), len(batches),
+                  oi.ctypes.data_as(u32p), pi.ctypes.data_as(u32p), _ptr(_arr(alpha).reshape(2)), cap_height, hash_kind,
+                  _ptr(out) if out is not None else None, C.byref(self._h))
+        self.final_poly = out
+        return self
+
     def commit_layer(self, arity_bits: int) -> MerkleCap:
         cap = np.zeros((1 << self.cap_height, 4), dtype=np.uint64)
         _lib.call("mp2gpu_fri_commit_layer", self._h, arity_bits, _ptr(cap))

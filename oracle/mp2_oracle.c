@@ -572,6 +572,50 @@ void orc_fri_fold(const uint64_t *coeffs, size_t m, uint32_t arity_bits, const u
   }
 }
 
+/* PolynomialBatch::prove_openings, up to its call of fri_proof (plonky2 0.2.2 fri/oracle.rs), with the
+ * ReducingFactor bookkeeping of util/reducing.rs:
+ *   for each batch (point z, polynomials f_0..f_{c-1}):
+ *     composition = reduce_polys_base = sum_j alpha^j f_j            (count += c)
+ *     quotient    = composition.divide_by_linear(z); quotient.push(0)
+ *     final_poly  = final_poly * alpha^count  (shift_poly; count = 0)  +  quotient            */
+int orc_fri_combine(const uint64_t *const *polys, const uint32_t *batch_sizes, size_t nbatches,
+                    const uint64_t *points, const uint64_t alpha[2], size_t n, uint64_t *out) {
+  if (!n) return -1;
+  uint64_t *comp = (uint64_t *)malloc(sizeof(uint64_t) * 2 * n);
+  memset(out, 0, sizeof(uint64_t) * 2 * n);
+  size_t at = 0;
+  for (size_t i = 0; i < nbatches; i++) {
+    const uint64_t *z = points + 2 * i;
+    uint64_t pw[2] = {1, 0}, shift[2];
+    memset(comp, 0, sizeof(uint64_t) * 2 * n);
+    for (uint32_t j = 0; j < batch_sizes[i]; j++, at++) {
+      for (size_t m = 0; m < n; m++) { /* poly.mul_extension(base_power) */
+        uint64_t v = orc_gl_canon(polys[at][m]);
+        comp[2 * m] = gl_add(comp[2 * m], gl_mul(v, pw[0]));
+        comp[2 * m + 1] = gl_add(comp[2 * m + 1], gl_mul(v, pw[1]));
+      }
+      uint64_t nx[2];
+      orc_ext_mul(pw, alpha, nx);
+      pw[0] = nx[0], pw[1] = nx[1];
+    }
+    shift[0] = pw[0], shift[1] = pw[1]; /* alpha^count */
+    /* divide_by_linear: b_k = b_(k+1) * z + a_k from the top; the quotient's coefficient k is b_(k+1) */
+    uint64_t acc[2] = {0, 0};
+    for (size_t m = n; m-- > 0;) {
+      uint64_t scaled[2], prod[2];
+      orc_ext_mul(out + 2 * m, shift, scaled);
+      out[2 * m] = gl_add(scaled[0], acc[0]); /* final[m] * alpha^count + quotient[m]; quotient[n-1] = 0 */
+      out[2 * m + 1] = gl_add(scaled[1], acc[1]);
+      orc_ext_mul(acc, z, prod);
+      acc[0] = gl_add(prod[0], comp[2 * m]);
+      acc[1] = gl_add(prod[1], comp[2 * m + 1]);
+    }
+  }
+  for (size_t m = 0; m < 2 * n; m++) out[m] = orc_gl_canon(out[m]);
+  free(comp);
+  return 0;
+}
+
 /* the extension's roots of unity of order <= 2^32 are the base field's (EXT_POWER_OF_TWO_GENERATOR^2 =
  * POWER_OF_TWO_GENERATOR), so the transform acts on the two components separately */
 void orc_coset_fft_ext(const uint64_t *coeffs, uint32_t log_m, uint64_t shift, uint64_t *values) {

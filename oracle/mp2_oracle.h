@@ -104,6 +104,13 @@ void orc_coset_fft_ext(const uint64_t *coeffs, uint32_t log_m, uint64_t shift, u
 /* reverse_index_bits_in_place(values); chunks(2^arity_bits).map(flatten): (m >> ab) leaves of (2 << ab) elements */
 void orc_fri_layer_leaves(const uint64_t *values, uint32_t log_m, uint32_t arity_bits, uint64_t *leaves);
 
+/* PolynomialBatch::prove_openings before fri_proof: the alpha-batched quotient
+ *   final_poly = sum_i alpha^(k_i) (F_i(X) - F_i(z_i)) / (X - z_i),   F_i = sum_j alpha^j f_ij
+ * polys: the batches' polynomials concatenated (pointers to n base-field coefficients); points: nbatches x 2;
+ * out: n x 2 (canonical).  Returns 0 / -1. */
+int orc_fri_combine(const uint64_t *const *polys, const uint32_t *batch_sizes, size_t nbatches,
+                    const uint64_t *points, const uint64_t alpha[2], size_t n, uint64_t *out);
+
 /* fri_proof_of_work: smallest candidate c >= start such that, with state[pos] = c, permute(state)[7] (the
  * last squeezed rate element) has >= min_leading_zeros leading zero bits in canonical form.  plonky2 searches
  * with rayon find_any (any witness is valid); "smallest" is the deterministic rule both sides use here

@@ -74,6 +74,8 @@ def lib():
         L.orc_fri_fold.argtypes = [_u64p, C.c_size_t, C.c_uint32, _u64p, _u64p]
         L.orc_coset_fft_ext.argtypes = [_u64p, C.c_uint32, C.c_uint64, _u64p]
         L.orc_fri_layer_leaves.argtypes = [_u64p, C.c_uint32, C.c_uint32, _u64p]
+        L.orc_fri_combine.restype = C.c_int
+        L.orc_fri_combine.argtypes = [C.POINTER(_u64p), C.POINTER(C.c_uint32), C.c_size_t, _u64p, _u64p, C.c_size_t, _u64p]
         L.orc_fri_pow.restype = C.c_int
         L.orc_fri_pow.argtypes = [C.c_uint32, _u64p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, _u64p]
         L.orc_max_threads.restype = C.c_int
@@ -286,6 +288,21 @@ def fri_committed_trees(coeffs, values, arity_bits_list, betas, cap_height, hash
         shift = gl_pow(shift, 1 << ab)
         values = coset_fft_ext(coeffs, shift)
     return trees, coeffs[:coeffs.shape[0] >> rate_bits]
+
+
+def fri_combine(batches, alpha) -> np.ndarray:
+    """``batches``: [(point [z0, z1], [coefficient column, ...]), ...] -> (n, 2) final polynomial of prove_openings."""
+    cols = [_arr(c) for _, polys in batches for c in polys]
+    n = cols[0].size
+    assert all(c.size == n for c in cols)
+    ptrs = (_u64p * len(cols))(*[_p(c) for c in cols])
+    sizes = (C.c_uint32 * len(batches))(*[len(polys) for _, polys in batches])
+    points = np.concatenate([_arr(z).reshape(2) for z, _ in batches])
+    out = np.zeros((n, 2), dtype=np.uint64)
+    rc = lib().orc_fri_combine(ptrs, sizes, len(batches), _p(points), _p(_arr(alpha)), n, _p(out))
+    if rc != 0:
+        raise ValueError("orc_fri_combine: bad arguments")
+    return out
 
 
 def fri_pow(state, pos, min_leading_zeros, hash_kind=POSEIDON, start=0, limit=1 << 40):

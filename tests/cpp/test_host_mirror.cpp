@@ -57,6 +57,37 @@ static int run(uint32_t kind) {
   uint64_t root[4];
   orc_merkle_verify(set_leaves[7].data(), 4, 7, proof.siblings[0].data(), 4, kind, root);
   REQUIRE(!std::memcmp(root, mt.cap.hashes[0].data(), 32));
+  // prove_openings: all polynomials at zeta, the first two again at g*zeta; then one reduction layer
+  {
+    FriInstanceInfo inst;
+    Ext zeta = {splitmix(seed) >> 1, splitmix(seed) >> 1}, gzeta = {splitmix(seed) >> 1, splitmix(seed) >> 1};
+    Ext alpha = {splitmix(seed) >> 1, splitmix(seed) >> 1}, beta = {splitmix(seed) >> 1, splitmix(seed) >> 1};
+    FriBatchInfo b0{zeta, {}}, b1{gzeta, {{0, 0}, {0, 1}}};
+    for (size_t c = 0; c < ncols; c++) b0.polynomials.push_back({0, c});
+    inst.batches = {b0, b1};
+    auto ph = prove_openings_begin<H>(inst, {&pb}, alpha, cap_height, true);
+    std::vector<const uint64_t *> polys;
+    for (auto &b : inst.batches)
+      for (auto &pinfo : b.polynomials) polys.push_back(&coeffs[pinfo.polynomial_index * n]);
+    const uint32_t sizes[2] = {(uint32_t)ncols, 2};
+    const uint64_t points[4] = {zeta[0], zeta[1], gzeta[0], gzeta[1]};
+    std::vector<uint64_t> fin(2 * n);
+    REQUIRE(orc_fri_combine(polys.data(), sizes, 2, points, alpha.data(), n, fin.data()) == 0);
+    REQUIRE(ph.final_poly.size() == n && !std::memcmp(ph.final_poly[0].data(), fin.data(), 16 * n));
+    // fri_committed_trees, one layer of arity 16: cap, fold, remaining coefficients
+    auto layer_cap = ph.commit_layer(4);
+    std::vector<uint64_t> padded(2 * N, 0), vals(2 * N), lv(2 * N), dg(2 * (N / 16 - 16) * 4), cp(16 * 4);
+    std::memcpy(padded.data(), fin.data(), 16 * n);
+    orc_coset_fft_ext(padded.data(), n_log + rate_bits, 7, vals.data());
+    orc_fri_layer_leaves(vals.data(), n_log + rate_bits, 4, lv.data());
+    REQUIRE(orc_merkle_new(lv.data(), N / 16, 32, cap_height, kind, dg.data(), cp.data(), 2) == 0);
+    REQUIRE(!std::memcmp(layer_cap.hashes[0].data(), cp.data(), cp.size() * 8));
+    ph.fold(beta);
+    auto rest = ph.finish();
+    std::vector<uint64_t> folded(2 * (N / 16));
+    orc_fri_fold(padded.data(), N, 4, beta.data(), folded.data());
+    REQUIRE(rest.size() == n / 16 && !std::memcmp(rest[0].data(), folded.data(), 16 * (n / 16)));
+  }
   // panics like plonky2
   bool threw = false;
   try {

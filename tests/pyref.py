@@ -279,6 +279,37 @@ def ext_horner(coeffs, x):
     return acc
 
 
+def ext_inv(a):
+    """1/(a0 + a1 X) = (a0 - a1 X) / (a0^2 - 7 a1^2)."""
+    norm_inv = pow((a[0] * a[0] - 7 * a[1] * a[1]) % P, P - 2, P)
+    return (a[0] * norm_inv % P, (P - a[1]) * norm_inv % P)
+
+
+def fri_combined_eval(batches, alpha, x):
+    """prove_openings' final polynomial evaluated at the extension point x, from its defining formula
+        sum_i alpha^(k_i) (F_i(x) - F_i(z_i)) / (x - z_i),  F_i = sum_j alpha^j f_ij,
+    where batch i is multiplied by alpha^(number of polynomials in the batches after it... that were reduced
+    after it): k_i = sum of the sizes of batches i+1.. (ReducingFactor::shift_poly).
+    ``batches``: [(z, [coefficient list, ...]), ...]."""
+    total = (0, 0)
+    sizes = [len(polys) for _, polys in batches]
+    for i, (z, polys) in enumerate(batches):
+        def big_f(pt):
+            acc, pw = (0, 0), (1, 0)
+            for f in polys:
+                v = ext_horner([(c % P, 0) for c in f], pt)
+                t = ext_mul(v, pw)
+                acc = ((acc[0] + t[0]) % P, (acc[1] + t[1]) % P)
+                pw = ext_mul(pw, alpha)
+            return acc
+        fx, fz = big_f(x), big_f(z)
+        num = ((fx[0] - fz[0]) % P, (fx[1] - fz[1]) % P)
+        den = ext_inv(((x[0] - z[0]) % P, (x[1] - z[1]) % P))
+        term = ext_mul(ext_mul(num, den), ext_pow(alpha, sum(sizes[i + 1:])))
+        total = ((total[0] + term[0]) % P, (total[1] + term[1]) % P)
+    return total
+
+
 def fri_committed_trees(coeffs, arity_bits_list, betas, cap_height, kind=0, rate_bits=3):
     """coeffs: list of ext pairs (zero-padded LDE length).  Every layer is computed from the definition:
     values[i] = P(shift * w^i) by Horner in the extension field; the fold is

@@ -86,3 +86,118 @@ def test_fri_proof_of_work_smallest_witness(oracle, kind):
         st[pos] = w
         resp = int(oracle.permute(st, kind)[7])
         assert resp < 1 << (64 - bits)
+
+
+# ---- prove_openings: the alpha-batched quotient (mp2gpu_fri_begin_openings) ----
+def _oracles(G, degree_bits, widths, kind, seed):
+    n = 1 << degree_bits
+    return [G.PolynomialBatch.from_coeffs(list(field_elems(seed + 7 * k, (w, n))), 3, False, min(4, degree_bits + 3),
+                                          hash_kind=kind, keep_on_device=True, fetch_leaves=False)
+            for k, w in enumerate(widths)]
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("degree_bits,widths", [(0, (2, 1)), (1, (3, 2)), (5, (3, 4, 2)), (10, (9, 17, 5, 4)),
+                                                 (11, (5, 3)), (14, (85, 135, 20, 16))])
+def test_prove_openings_final_poly_matches_oracle(oracle, kind, degree_bits, widths):
+    """plonky2's instance shape: every polynomial of every oracle at zeta, the first two polynomials of the
+    third (or last) oracle -- the Zs -- again at g*zeta."""
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    oracles = _oracles(G, degree_bits, widths, kind, 0x09E0 + degree_bits)
+    zeta, gzeta, alpha = (field_elems(0x2E7A + i + degree_bits, 2) for i in range(3))
+    all_polys = [(o, p) for o, w in enumerate(widths) for p in range(w)]
+    z_oracle = min(2, len(widths) - 1)
+    zs = [(z_oracle, p) for p in range(min(2, widths[z_oracle]))]
+    batches = [(zeta, all_polys), (gzeta, zs)]
+    ph = G.FriCommitPhase.from_openings(oracles, batches, alpha, min(4, degree_bits), kind, want_final_poly=True)
+    ref = oracle.fri_combine([(z, [oracles[o].polynomials[p] for o, p in polys]) for z, polys in batches], alpha)
+    assert np.array_equal(ph.final_poly, ref)
+    assert not ph.final_poly[-1].any()            # divide_by_linear drops a degree; push(ZERO) pads it back
+    if degree_bits >= 5:
+        # the device-resident polynomial feeds the commit phase exactly like host coefficients would
+        arity = 4 if degree_bits >= 4 else 1
+        cap = ph.commit_layer(arity)
+        ph2 = G.FriCommitPhase(ref, 3, min(4, degree_bits), kind)
+        assert np.array_equal(cap.hashes, ph2.commit_layer(arity).hashes)
+        ph2.free()
+    ph.free()
+    for o in oracles:
+        o.free()
+
+
+def test_prove_openings_three_batches_and_noncanonical_challenges(oracle):
+    """ReducingFactor::shift_poly multiplies what has been accumulated by alpha^(size of the NEW batch): three
+    batches of different sizes pin that exponent; challenges >= p are reduced."""
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    oracles = _oracles(G, 12, (6, 3), 1, 0x7B3)
+    pts = [np.array([P + 5, 3], dtype=np.uint64), field_elems(0x51, 2), field_elems(0x52, 2)]
+    alpha = np.array([2**64 - 1, P + 1], dtype=np.uint64)
+    batches = [(pts[0], [(0, 0), (0, 1), (0, 2), (1, 2), (0, 5)]), (pts[1], [(1, 0)]), (pts[2], [(0, 3), (1, 1), (0, 3)])]
+    ph = G.FriCommitPhase.from_openings(oracles, batches, alpha, 4, 1, want_final_poly=True)
+    ref = oracle.fri_combine([(z % np.uint64(P), [oracles[o].polynomials[p] for o, p in polys]) for z, polys in batches],
+                             alpha % np.uint64(P))
+    assert np.array_equal(ph.final_poly, ref)
+    ph.free()
+    for o in oracles:
+        o.free()
+
+
+def test_prove_openings_large_degree_evaluation_identity(oracle):
+    """n = 2^18 (two levels of the quotient scan): (X - z) * quotient + F(z) == F at a random point, with the
+    evaluations done by the oracle's extension Horner -- no O(n) oracle pass over 2^18 x c."""
+    import mapreduce_plonky2_b200 as G
+    import pyref
+
+    G.init(0)
+    degree_bits, w = 18, 3
+    oracles = _oracles(G, degree_bits, (w,), 1, 0x18AB)
+    z, alpha, x = (tuple(int(v) for v in field_elems(0x90 + i, 2)) for i in range(3))
+    ph = G.FriCommitPhase.from_openings(oracles, [(np.array(z, dtype=np.uint64), [(0, p) for p in range(w)])],
+                                        np.array(alpha, dtype=np.uint64), 4, 1, want_final_poly=True)
+    q = ph.final_poly
+
+    def horner_np(coeffs_ext, pt):      # vectorised-free but O(n) python ints: 2^18 steps is ~1 s
+        acc = (0, 0)
+        for a, b in zip(coeffs_ext[::-1, 0].tolist(), coeffs_ext[::-1, 1].tolist()):
+            acc = pyref.ext_mul(acc, pt)
+            acc = ((acc[0] + a) % P, (acc[1] + b) % P)
+        return acc
+
+    comp = np.zeros((1 << degree_bits, 2), dtype=object)
+    pw = (1, 0)
+    for p in range(w):
+        col = oracles[0].polynomials[p].astype(object)
+        comp[:, 0] = (comp[:, 0] + col * pw[0]) % P
+        comp[:, 1] = (comp[:, 1] + col * pw[1]) % P
+        pw = pyref.ext_mul(pw, alpha)
+    fx, fz, qx = horner_np(comp, x), horner_np(comp, z), horner_np(q.astype(object), x)
+    lhs = pyref.ext_mul(qx, ((x[0] - z[0]) % P, (x[1] - z[1]) % P))
+    assert ((lhs[0] + fz[0]) % P, (lhs[1] + fz[1]) % P) == fx
+    ph.free()
+    oracles[0].free()
+
+
+def test_prove_openings_errors():
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    a = _oracles(G, 6, (3,), 0, 1)[0]
+    b = _oracles(G, 7, (3,), 0, 2)[0]
+    host_only = G.PolynomialBatch.from_coeffs(list(field_elems(3, (2, 64))), 3, False, 4, hash_kind=0)
+    z = np.array([1, 2], dtype=np.uint64)
+    with pytest.raises(G.Mp2GpuError, match="share degree"):
+        G.FriCommitPhase.from_openings([a, b], [(z, [(0, 0)])], z, 4, 0)
+    with pytest.raises(G.Mp2GpuError, match="polynomial_index"):
+        G.FriCommitPhase.from_openings([a], [(z, [(0, 3)])], z, 4, 0)
+    with pytest.raises(G.Mp2GpuError, match="oracle_index"):
+        G.FriCommitPhase.from_openings([a], [(z, [(1, 0)])], z, 4, 0)
+    with pytest.raises(G.Mp2GpuError, match="empty batch"):
+        G.FriCommitPhase.from_openings([a], [(z, [])], z, 4, 0)
+    with pytest.raises(G.Mp2GpuError, match="device-resident"):
+        G.FriCommitPhase.from_openings([host_only], [(z, [(0, 0)])], z, 4, 0)
+    a.free()
+    b.free()

@@ -157,3 +157,23 @@ def test_fri_commit_phase_oracle_vs_definition(oracle):
     # FFTs commute with the field inclusion (QuadraticExtension<GoldilocksField>::EXT_POWER_OF_TWO_GENERATOR)
     g = (0, 15659105665374529263)
     assert R.ext_mul(g, g) == (1753635133440165772, 0)
+
+
+def test_prove_openings_combination_oracle_vs_definition(oracle):
+    """oracle.fri_combine (plonky2's loop: reduce_polys_base, divide_by_linear, shift_poly, +=) evaluated at random
+    points equals the defining formula sum_i alpha^(k_i) (F_i(x) - F_i(z_i)) / (x - z_i) from pyref."""
+    rng = random.Random(0x0FE)
+    for n, sizes in ((1, [1]), (2, [2, 1]), (16, [5, 2]), (32, [3, 1, 4])):
+        batches = [((rng.randrange(P), rng.randrange(P)), [[rng.randrange(P) for _ in range(n)] for _ in range(c)])
+                   for c in sizes]
+        alpha = (rng.randrange(P), rng.randrange(P))
+        out = oracle.fri_combine([(np.array(z, dtype=np.uint64), [np.array(f, dtype=np.uint64) for f in polys])
+                                  for z, polys in batches], np.array(alpha, dtype=np.uint64))
+        assert out.shape == (n, 2) and not out[-1].any()
+        coeffs = [(int(a), int(b)) for a, b in out]
+        for _ in range(3):
+            x = (rng.randrange(P), rng.randrange(P))
+            assert R.ext_horner(coeffs, x) == R.fri_combined_eval(batches, alpha, x)
+    # an extension inverse really is one
+    a = (rng.randrange(P), rng.randrange(P))
+    assert R.ext_mul(a, R.ext_inv(a)) == (1, 0)
