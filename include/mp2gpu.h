@@ -114,6 +114,10 @@ const char *mp2gpu_batch_prove(const mp2gpu_batch *b, size_t leaf_index, uint64_
  * its (log2 N - cap_height) x 4 sibling digests, bottom-up; gathered on the device, two copies back. */
 const char *mp2gpu_batch_open(const mp2gpu_batch *b, const uint64_t *leaf_idx, size_t count,
                               uint64_t *rows_out, uint64_t *siblings_out);
+/* OpeningSet::new's `c.polynomials.par_iter().map(|p| p.to_extension().eval(z))` (plonky2 plonk/proof.rs; step 7 of
+ * prove(), between the quotient commitment and prove_openings) on the resident coefficients.
+ * points: npoints x 2 (extension elements); out: npoints x ncols x 2, out[(p * ncols + c)] = polynomial c at point p. */
+const char *mp2gpu_batch_eval(const mp2gpu_batch *b, const uint64_t *points, size_t npoints, uint64_t *out);
 /* Any of the outputs may be NULL. Sizes as for mp2gpu_commit_from_values. */
 const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_out,
                                uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out);

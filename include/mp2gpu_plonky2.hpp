@@ -137,6 +137,18 @@ struct PolynomialBatch {
     return commit(cols, polys.empty() ? 0 : polys[0].coeffs.size(), rate_bits, blinding, cap_height, true,
                   keep_on_device);
   }
+  // OpeningSet::new's `polynomials.par_iter().map(|p| p.to_extension().eval(z))` for several points at once, on
+  // the device-resident coefficients: result[point][polynomial] = [a0, a1]
+  std::vector<std::vector<std::array<F, 2>>> eval(const std::vector<std::array<F, 2>> &points) const {
+    if (!device) throw Panic("batch was not kept on the device");
+    std::vector<uint64_t> flat(points.size() * polynomials.size() * 2);
+    if (!points.empty()) check(mp2gpu_batch_eval(device.get(), points[0].data(), points.size(), flat.data()));
+    std::vector<std::vector<std::array<F, 2>>> out(points.size(), std::vector<std::array<F, 2>>(polynomials.size()));
+    for (size_t p = 0; p < points.size(); p++)
+      for (size_t c = 0; c < polynomials.size(); c++)
+        out[p][c] = {flat[2 * (p * polynomials.size() + c)], flat[2 * (p * polynomials.size() + c) + 1]};
+    return out;
+  }
   // get_lde_values(index, step): leaves[reverse_bits(index * step, degree_log + rate_bits)]
   const std::vector<F> &get_lde_values(size_t index, size_t step) const {
     return merkle_tree.leaves[reverse_bits(index * step, degree_log + rate_bits)];

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mp2gpu_batch_open": (_ERR, [C.c_void_p, u64p, C.c_size_t, u64p, u64p]),
     "mp2gpu_fri_open_layer": (_ERR, [C.c_void_p, C.c_uint32, u64p, C.c_size_t, u64p, u64p]),
     "mp2gpu_batch_fetch": (_ERR, [C.c_void_p, u64pp, u64p, u64p, u64p]),
+    "mp2gpu_batch_eval": (_ERR, [C.c_void_p, u64p, C.c_size_t, u64p]),
     "mp2gpu_batch_shape": (_ERR, [C.c_void_p, size_p, u32p, u32p, u32p, u32p]),
     "mp2gpu_batch_free": (None, [C.c_void_p]),
     "mp2gpu_fri_begin": (_ERR, [u64p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p)]),

@@ -185,6 +185,47 @@ k_suffix_scan(const u64 *__restrict__ x, size_t xs, size_t len, Ext w, Ext wL, S
   }
 }
 
+// ---- OpeningSet: every polynomial of a batch evaluated at extension points -------------------------------
+// Replaces `c.polynomials.par_iter().map(|p| p.to_extension().eval(z))` of plonky2's OpeningSet::new
+// (plonk/proof.rs; step 7 of prove(), between the quotient commitment and prove_openings).
+// grid = (ncols, npoints); thread t owns the coefficients m = t (mod T): coalesced loads, Horner in
+// w = z^T, then z^t from a host-made table and a shared-memory sum.  tab: per point 2 x (T + 1) entries,
+// component-major: z^0 .. z^(T-1), z^T.
+constexpr int kEvalT = 256;
+__global__ void __launch_bounds__(kEvalT)
+k_eval_polys(const u64 *__restrict__ coeffs, size_t stride, size_t n, const u64 *__restrict__ tab,
+             u64 *__restrict__ out, size_t ncols) {
+  __shared__ u64 ra[kEvalT], rb[kEvalT];
+  const int t = threadIdx.x;
+  const size_t c = blockIdx.x, pt = blockIdx.y;
+  const u64 *tb = tab + pt * 2 * (kEvalT + 1);
+  const Ext w = {tb[kEvalT], tb[kEvalT + 1 + kEvalT]};
+  const u64 *f = coeffs + c * stride;
+  Ext acc = {0, 0};
+  if ((size_t)t < n) {
+    const size_t top = (n - 1 - t) / kEvalT;  // largest i with t + T i < n
+    for (size_t i = top + 1; i-- > 0;) {
+      acc = ext_mul(acc, w);
+      acc.a = gl_add(acc.a, f[t + kEvalT * i]);
+    }
+    acc = ext_mul(acc, Ext{tb[t], tb[kEvalT + 1 + t]});
+  }
+  ra[t] = acc.a;
+  rb[t] = acc.b;
+  __syncthreads();
+  for (int d = kEvalT / 2; d > 0; d >>= 1) {
+    if (t < d) {
+      ra[t] = gl_add(ra[t], ra[t + d]);
+      rb[t] = gl_add(rb[t], rb[t + d]);
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    out[2 * (pt * ncols + c)] = gl_canon(ra[0]);
+    out[2 * (pt * ncols + c) + 1] = gl_canon(rb[0]);
+  }
+}
+
 // host-side extension arithmetic (a handful of powers per call; no data-path work)
 struct HExt {
   u64 a, b;
@@ -232,6 +273,32 @@ static Status suffix_scan(const u64 *x, size_t xs, size_t len, HExt w, u64 *out,
   return "";
 }
 
+// out[pt][c] = polynomial c evaluated at points[pt]; out is a DEVICE buffer of npoints x ncols pairs
+Status fri_eval_polys(const u64 *coeffs, size_t stride, size_t ncols, size_t n, const u64 *points_host, size_t npoints,
+                      u64 *out, cudaStream_t st) {
+  if (!ncols || !npoints || !n) return "";
+  if (npoints > 65535) return "too many evaluation points";
+  std::vector<u64> tab(npoints * 2 * (kEvalT + 1));
+  for (size_t p = 0; p < npoints; p++) {
+    const HExt z = {points_host[2 * p] % kP, points_host[2 * p + 1] % kP};
+    u64 *ta = tab.data() + p * 2 * (kEvalT + 1), *tb = ta + kEvalT + 1;
+    HExt cur = {1, 0};
+    for (int t = 0; t <= kEvalT; t++) {
+      ta[t] = cur.a;
+      tb[t] = cur.b;
+      cur = hx_mul(cur, z);
+    }
+  }
+  DevBuf d_tab;
+  MP2_TRY(d_tab.alloc(tab.size(), st));
+  MP2_CUDA(cudaMemcpyAsync(d_tab.p, tab.data(), sizeof(u64) * tab.size(), cudaMemcpyHostToDevice, st));
+  // the table is pageable host memory: the copy above has been staged when the call returns
+  dim3 grid((unsigned)ncols, (unsigned)npoints, 1);
+  if (ncols > 0x7fffffffull) return "too many polynomials";
+  { ProfScope _p("k_eval_polys", st); k_eval_polys<<<grid, kEvalT, 0, st>>>(coeffs, stride, n, d_tab.p, out, ncols); }
+  MP2_LAUNCH_CHECK();
+  return "";
+}
 Status fri_reduce_polys_strided(const u64 *const *polys, const u64 *pw, size_t pw_stride, u32 count, size_t n, u64 *out,
                                 size_t out_stride, cudaStream_t st) {
   if (!n) return "";
@@ -332,6 +399,23 @@ const char *mp2gpu_fri_begin(const uint64_t *coeffs_ext, uint32_t n_log, uint32_
     MP2_TRY(fri_deinterleave(tmp.p, f->coeffs, n, n, st));
     MP2_CUDA(cudaStreamSynchronize(st));
     *out = f.release();
+    return "";
+  });
+}
+
+const char *mp2gpu_batch_eval(const mp2gpu_batch *b, const uint64_t *points, size_t npoints, uint64_t *out) {
+  return guard([&]() -> Status {
+    if (!b) return "null batch handle";
+    if (npoints && (!points || !out)) return "null points / out";
+    if (!npoints) return "";
+    MP2_CUDA(cudaSetDevice(b->device));
+    cudaStream_t st = cudaStreamPerThread;
+    DevBuf d_out;
+    MP2_TRY(d_out.alloc(2 * npoints * b->ncols, st));
+    MP2_TRY(fri_eval_polys(b->coeffs, (size_t)1 << b->n_log, b->ncols, (size_t)1 << b->n_log, (const u64 *)points, npoints,
+                           d_out.p, st));
+    MP2_CUDA(cudaMemcpyAsync(out, d_out.p, sizeof(u64) * 2 * npoints * b->ncols, cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaStreamSynchronize(st));
     return "";
   });
 }

@@ -159,6 +159,9 @@ Status merkle_open(const u64 *leaves_rowmajor, const u64 *lde_colmajor, size_t l
 // device arrays (count pointers; powers component-major, the two halves pw_stride apart)
 Status fri_reduce_polys_strided(const u64 *const *polys, const u64 *pw, size_t pw_stride, u32 count, size_t n, u64 *out,
                                 size_t out_stride, cudaStream_t st);
+// out[pt * ncols + c] (pairs, device) = polynomial c evaluated at the extension point points_host[pt]
+Status fri_eval_polys(const u64 *coeffs, size_t stride, size_t ncols, size_t n, const u64 *points_host, size_t npoints,
+                      u64 *out, cudaStream_t st);
 // acc[k] = acc[k] * scale + sum_{m > k} x[m] * z^(m-k-1)   (divide_by_linear + push(0), then shift_poly / +=);
 // `fresh` skips the read of acc.  x, acc: component-major extension polynomials of length len.
 Status fri_divide_accumulate(const u64 *x, size_t x_stride, size_t len, const u64 z[2], u64 *acc, size_t acc_stride,

@@ -344,6 +344,16 @@ class PolynomialBatch:
         _lib.call("mp2gpu_batch_open", self._handle, _ptr(idx), idx.size, _ptr(rows), _ptr(sib) if h else None)
         return rows, sib
 
+    def eval(self, points) -> np.ndarray:
+        """``p.to_extension().eval(z)`` for every polynomial and every extension point (``OpeningSet::new``):
+        (npoints, ncols, 2), computed from the coefficients resident in HBM."""
+        if self._handle is None:
+            raise Mp2GpuError("batch was not kept on the device (keep_on_device=False)")
+        pts = np.ascontiguousarray(_arr(points).reshape(-1, 2))
+        out = np.zeros((pts.shape[0], len(self.polynomials), 2), dtype=np.uint64)
+        _lib.call("mp2gpu_batch_eval", self._handle, _ptr(pts), pts.shape[0], _ptr(out))
+        return out
+
     def free(self) -> None:
         if self._handle is not None:
             _lib.load().mp2gpu_batch_free(self._handle)

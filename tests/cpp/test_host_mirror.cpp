@@ -65,6 +65,19 @@ static int run(uint32_t kind) {
     FriBatchInfo b0{zeta, {}}, b1{gzeta, {{0, 0}, {0, 1}}};
     for (size_t c = 0; c < ncols; c++) b0.polynomials.push_back({0, c});
     inst.batches = {b0, b1};
+    // OpeningSet: polynomial 3 at zeta by Horner in GF(p^2) with the oracle's extension multiplication
+    auto opened = pb.eval({zeta, gzeta});
+    {
+      uint64_t acc[2] = {0, 0};
+      for (size_t m = n; m-- > 0;) {
+        uint64_t prod[2];
+        orc_ext_mul(acc, zeta.data(), prod);
+        acc[0] = orc_gl_add(prod[0], coeffs[3 * n + m]);
+        acc[1] = prod[1];
+      }
+      REQUIRE(opened.size() == 2 && opened[0].size() == ncols);
+      REQUIRE(opened[0][3][0] == orc_gl_canon(acc[0]) && opened[0][3][1] == orc_gl_canon(acc[1]));
+    }
     auto ph = prove_openings_begin<H>(inst, {&pb}, alpha, cap_height, true);
     std::vector<const uint64_t *> polys;
     for (auto &b : inst.batches)

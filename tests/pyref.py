@@ -336,3 +336,125 @@ def fri_committed_trees(coeffs, arity_bits_list, betas, cap_height, kind=0, rate
         coeffs = folded
         shift = pow(shift, arity, P)
     return out, coeffs[:len(coeffs) >> rate_bits]
+
+
+# ---------------- FRI verifier (plonky2 fri/verifier.rs, iop/challenger.rs), by definition ----------------
+class Challenger:
+    """Overwrite-mode duplex sponge of the Fiat-Shamir transcript; outputs are popped from the end."""
+
+    def __init__(self, kind=0):
+        self.kind, self.state, self.inp, self.out = kind, [0] * 12, [], []
+
+    def observe(self, xs):
+        for x in xs:
+            self.out = []
+            self.inp.append(int(x) % P)
+            if len(self.inp) == 8:
+                self.duplex()
+
+    def duplex(self):
+        for i, x in enumerate(self.inp):
+            self.state[i] = x
+        self.inp = []
+        self.state = permute(self.state, self.kind)
+        self.out = list(self.state[:8])
+
+    def challenge(self):
+        if self.inp or not self.out:
+            self.duplex()
+        return self.out.pop()
+
+    def ext_challenge(self):
+        a = self.challenge()
+        return (a, self.challenge())
+
+
+def verify_merkle_proof_to_cap(leaf, index, cap, siblings, kind=0):
+    cur = hash_or_noop(list(leaf), kind)
+    for sib in siblings:
+        cur = two_to_one(cur, list(sib), kind) if index & 1 == 0 else two_to_one(list(sib), cur, kind)
+        index >>= 1
+    return list(cur) == list(cap[index])
+
+
+def _ext_sub(a, b):
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+def _ext_add(a, b):
+    return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+
+
+def _reduce_with_alpha(values, alpha):
+    """ReducingFactor::reduce: sum_j alpha^j v_j."""
+    acc = (0, 0)
+    for v in reversed(values):
+        acc = _ext_add(ext_mul(acc, alpha), v)
+    return acc
+
+
+def fri_compute_evaluation(x, x_index_within_coset, arity_bits, evals, beta):
+    """Interpolate {(x g^i, P(x g^i))} over the coset of x and evaluate at beta (Lagrange, by definition)."""
+    arity = 1 << arity_bits
+    g = root_of_unity(arity_bits)
+    ordered = [evals[bitrev(i, arity_bits)] for i in range(arity)]
+    coset_start = x * pow(g, arity - bitrev(x_index_within_coset, arity_bits), P) % P
+    pts = [(coset_start * pow(g, i, P) % P, 0) for i in range(arity)]
+    total = (0, 0)
+    for i in range(arity):
+        num, den = (1, 0), (1, 0)
+        for j in range(arity):
+            if j != i:
+                num = ext_mul(num, _ext_sub(beta, pts[j]))
+                den = ext_mul(den, _ext_sub(pts[i], pts[j]))
+        total = _ext_add(total, ext_mul(ordered[i], ext_mul(num, ext_inv(den))))
+    return total
+
+
+def verify_fri_proof(batches, openings, initial_caps, proof, challenger, degree_bits, arity_bits_list,
+                     rate_bits=3, pow_bits=16, kind=0):
+    """plonky2 ``verify_fri_proof`` with the challenges re-derived from the transcript.
+
+    batches: [(point, [(oracle_index, polynomial_index), ...])]; openings: per batch the claimed values;
+    initial_caps: per oracle its cap; proof: dict(caps, final_poly, pow_witness, rounds=[dict(initial=[(row, siblings)],
+    steps=[(evals, siblings)])]).  ``challenger`` has already observed whatever precedes FRI (caps, openings).
+    Returns None, raises AssertionError with the failing check otherwise."""
+    alpha = challenger.ext_challenge()
+    betas = []
+    for cap in proof["caps"]:
+        challenger.observe([x for h in cap for x in h])
+        betas.append(challenger.ext_challenge())
+    challenger.observe([x for c in proof["final_poly"] for x in c])
+    challenger.observe([proof["pow_witness"]])
+    pow_response = challenger.challenge()
+    assert 64 - pow_response.bit_length() >= pow_bits, "proof of work"
+    log_n = degree_bits + rate_bits
+    n = 1 << log_n
+    assert len(proof["final_poly"]) == 1 << (degree_bits - sum(arity_bits_list))
+    x_indices = [challenger.challenge() % n for _ in proof["rounds"]]
+    reduced_openings = [_reduce_with_alpha([tuple(v) for v in vals], alpha) for vals in openings]
+    for x_index, rnd in zip(x_indices, proof["rounds"]):
+        for (row, sib), cap in zip(rnd["initial"], initial_caps):
+            assert verify_merkle_proof_to_cap(row, x_index, cap, sib, kind), "initial tree proof"
+        subgroup_x = 7 * pow(root_of_unity(log_n), bitrev(x_index, log_n), P) % P
+        # fri_combine_initial
+        total, count = (0, 0), 0
+        for (point, polys), red in zip(batches, reduced_openings):
+            evals = [(int(rnd["initial"][o][0][p]) % P, 0) for o, p in polys]
+            num = _ext_sub(_reduce_with_alpha(evals, alpha), red)
+            den = _ext_sub((subgroup_x, 0), tuple(point))
+            total = ext_mul(total, ext_pow(alpha, len(polys)))      # alpha.shift(sum): count of THIS batch's reduce
+            total = _ext_add(total, ext_mul(num, ext_inv(den)))
+        old_eval = total
+        for i, ab in enumerate(arity_bits_list):
+            evals, sib = rnd["steps"][i]
+            evals = [tuple(int(v) for v in e) for e in evals]
+            coset_index, within = x_index >> ab, x_index & ((1 << ab) - 1)
+            assert evals[within] == old_eval, "consistency with the previous layer (layer %d)" % i
+            old_eval = fri_compute_evaluation(subgroup_x, within, ab, evals, betas[i])
+            assert verify_merkle_proof_to_cap([x for e in evals for x in e], coset_index, proof["caps"][i], sib, kind), \
+                "layer tree proof"
+            subgroup_x = pow(subgroup_x, 1 << ab, P)
+            x_index = coset_index
+        final = ext_horner([tuple(int(v) for v in c) for c in proof["final_poly"]], (subgroup_x, 0))
+        assert final == old_eval, "final polynomial evaluation"

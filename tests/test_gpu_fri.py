@@ -201,3 +201,83 @@ def test_prove_openings_errors():
         G.FriCommitPhase.from_openings([host_only], [(z, [(0, 0)])], z, 4, 0)
     a.free()
     b.free()
+
+
+# ---- whole FRI prover: openings -> prove_openings -> fri_proof, against the oracle-built proof and the verifier ----
+@pytest.mark.parametrize("kind,degree_bits,widths", [(0, 6, (3, 5, 4, 2)), (1, 6, (2, 9, 3)), (1, 10, (3, 2)),
+                                                      (1, 12, (5, 7, 3, 2))])
+def test_fri_proof_matches_oracle_and_verifies(oracle, kind, degree_bits, widths):
+    import fri_ref
+    import pyref
+    import mapreduce_plonky2_b200 as G
+    from mapreduce_plonky2_b200 import fri as GF
+
+    G.init(0)
+    n = 1 << degree_bits
+    rounds, pow_bits = 5, 6
+    coeff_sets = [field_elems(0xF0 + 3 * k + degree_bits, (w, n)) for k, w in enumerate(widths)]
+    zeta, gzeta = (tuple(int(v) for v in field_elems(0x5E7A + i, 2)) for i in range(2))
+    ref_batches = fri_ref.plonky2_instance(widths, zeta, gzeta)
+    commits, ref_openings, ref = fri_ref.oracle_fri_proof(oracle, coeff_sets, ref_batches, degree_bits, kind,
+                                                          pow_bits=pow_bits, num_query_rounds=rounds)
+    # device side
+    oracles = [G.PolynomialBatch.from_coeffs(list(c), 3, False, 4, hash_kind=kind, keep_on_device=True, fetch_leaves=False)
+               for c in coeff_sets]
+    batches = [GF.FriBatchInfo(np.array(z, dtype=np.uint64), polys) for z, polys in ref_batches]
+    openings = GF.open_batches(batches, oracles)
+    for got, want in zip(openings, ref_openings):
+        assert got.tolist() == [list(v) for v in want]
+    ch = GF.Challenger(kind)
+    for o in oracles:
+        ch.observe_cap(o.merkle_tree.cap)
+    for vals in openings:
+        ch.observe_extension_elements(vals)
+    params = GF.FriConfig(proof_of_work_bits=pow_bits, num_query_rounds=rounds).fri_params(degree_bits)
+    assert params.reduction_arity_bits == fri_ref.arity_schedule(degree_bits)
+    proof = GF.prove_openings(batches, oracles, ch, params)
+    # bit-exact against the proof assembled from the oracle's pieces
+    assert len(proof.commit_phase_merkle_caps) == len(ref["caps"])
+    for cap, rc in zip(proof.commit_phase_merkle_caps, ref["caps"]):
+        assert np.array_equal(cap.hashes, rc)
+    assert np.array_equal(proof.final_poly, ref["final_poly"])
+    assert proof.pow_witness == ref["pow_witness"]
+    assert len(proof.query_round_proofs) == rounds
+    for rnd, rr in zip(proof.query_round_proofs, ref["rounds"]):
+        for (row, mp), (rrow, rsib) in zip(rnd.initial_trees_proof, rr["initial"]):
+            assert np.array_equal(row, rrow) and np.array_equal(mp.siblings, rsib)
+        for st, (rev, rsib) in zip(rnd.steps, rr["steps"]):
+            assert np.array_equal(st.evals, rev) and np.array_equal(st.merkle_proof.siblings, rsib)
+    # and accepted by the by-definition verifier with its own transcript
+    vch = pyref.Challenger(kind)
+    caps = [o.merkle_tree.cap.hashes.tolist() for o in oracles]
+    fri_ref.transcript_head(vch.observe, caps, [v.tolist() for v in openings])
+    p = {"caps": [c.hashes.tolist() for c in proof.commit_phase_merkle_caps], "final_poly": proof.final_poly.tolist(),
+         "pow_witness": proof.pow_witness,
+         "rounds": [{"initial": [(r.tolist(), m.siblings.tolist()) for r, m in rnd.initial_trees_proof],
+                     "steps": [(s.evals.tolist(), s.merkle_proof.siblings.tolist()) for s in rnd.steps]}
+                    for rnd in proof.query_round_proofs]}
+    pyref.verify_fri_proof(ref_batches, [[tuple(v) for v in vals.tolist()] for vals in openings], caps, p, vch,
+                           degree_bits, params.reduction_arity_bits, pow_bits=pow_bits, kind=kind)
+    for o in oracles:
+        o.free()
+
+
+def test_batch_eval_matches_horner(oracle):
+    """mp2gpu_batch_eval over short, non-multiple-of-256 and long polynomials, base and extension points."""
+    import pyref
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    for degree_bits, w in ((0, 2), (3, 3), (8, 2), (9, 2), (13, 1)):
+        n = 1 << degree_bits
+        cols = field_elems(0xE7A1 + degree_bits, (w, n))
+        b = G.PolynomialBatch.from_coeffs(list(cols), 3, False, min(4, degree_bits + 3), hash_kind=1,
+                                          keep_on_device=True, fetch_leaves=False)
+        pts = np.array([[5, 0], [P + 2, 2**64 - 1], field_elems(0x99, 2).tolist()], dtype=np.uint64)
+        got = b.eval(pts)
+        assert got.shape == (3, w, 2)
+        for pi, z in enumerate(pts.tolist()):
+            for c in range(w):
+                want = pyref.ext_horner([(int(v), 0) for v in cols[c]], (z[0] % P, z[1] % P))
+                assert tuple(got[pi, c].tolist()) == want
+        b.free()
