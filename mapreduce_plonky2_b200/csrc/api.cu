@@ -14,36 +14,58 @@ std::atomic<uint64_t> g_launches{0};
 
 namespace {
 
-struct ThreadCtx {
-  int device = 0;
+// Per calling thread: the device chosen with mp2gpu_init and one (compute, copy) stream pair per device the
+// thread has touched -- a prover thread that also reads a batch living on another device keeps both pairs.
+struct DevStreams {
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute
-  int stream_device = -1;
+};
+struct ThreadCtx {
+  int device = 0;
+  std::vector<DevStreams> per_device;
 };
 thread_local ThreadCtx t_ctx;
 
-// Binds the calling thread to its device and returns its private stream.
-Status ctx_stream(cudaStream_t *out) {
+// Binds the calling thread to its device and returns its private stream (and, optionally, its copy stream).
+Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr) {
   ThreadCtx &c = t_ctx;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     return std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
-  if (c.device >= ndev) return "device " + std::to_string(c.device) + " out of range";
+  if (c.device < 0 || c.device >= ndev) return "device " + std::to_string(c.device) + " out of range";
   MP2_CUDA(cudaSetDevice(c.device));
-  if (!c.stream || c.stream_device != c.device) {
-    MP2_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    MP2_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-    c.stream_device = c.device;
+  if (c.per_device.size() < (size_t)ndev) c.per_device.resize(ndev);
+  DevStreams &d = c.per_device[c.device];
+  if (!d.stream) {
+    cudaStream_t s1 = nullptr, s2 = nullptr;
+    MP2_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
+    if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamDestroy(s1);
+      return "cudaStreamCreateWithFlags failed for the copy stream";
+    }
+    d.stream = s1;
+    d.copy_stream = s2;
     // keep freed blocks in the stream-ordered pool: commitments reuse the same sizes over and over
     cudaMemPool_t pool;
     MP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
     uint64_t keep = UINT64_MAX;
     MP2_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
-  *out = c.stream;
+  *out = d.stream;
+  if (copy_out) *copy_out = d.copy_stream;
   return "";
 }
+
+// Runs the rest of the scope on the device a handle lives on, then gives the thread its own device back.
+struct DeviceScope {
+  int saved;
+  explicit DeviceScope(int device) : saved(t_ctx.device) { t_ctx.device = device; }
+  ~DeviceScope() {
+    t_ctx.device = saved;
+    cudaSetDevice(saved);
+  }
+};
 
 Status pick_stream(void *user, cudaStream_t *out) {
   cudaStream_t own;
@@ -119,12 +141,18 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
                    uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **handle_out) {
   MP2_TRY(check_commit_args(ncols, n_log, rate_bits, cap_height, hash_kind));
   if (!cols || !cap_out) return "null cols / cap_out";
-  cudaStream_t st;
-  MP2_TRY(ctx_stream(&st));
+  cudaStream_t st, cp;
+  MP2_TRY(ctx_stream(&st, &cp));
   const size_t n = (size_t)1 << n_log, N = n << rate_bits, ncap = (size_t)1 << cap_height;
   const size_t ndig = 2 * (N - ncap);
   const bool want_rows = leaves_out != nullptr || handle_out != nullptr;
   DevBuf d_in, d_coeffs, d_lde, d_leaves, d_dig, d_cap;
+  // declared after the buffers, so it runs before they are returned to the pool: on an early error return the
+  // copy stream may still be reading them
+  struct CopyDrain {
+    cudaStream_t s;
+    ~CopyDrain() { cudaStreamSynchronize(s); }
+  } copy_drain{cp};
   MP2_TRY(d_in.alloc(ncols * n, st));
   MP2_TRY(d_coeffs.alloc(ncols * n, st));
   MP2_TRY(d_lde.alloc(ncols * N, st));
@@ -134,7 +162,6 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
   // The copy stream trails the compute stream: coefficients go back while the LDE runs, each block of
   // leaf rows goes back while the next block is hashed.  PCIe, not HBM, bounds this entry point
   // (SURVEY.md section 7), so hiding the copies behind the hashing is worth ~2x end to end.
-  cudaStream_t cp = t_ctx.copy_stream;
   cudaEvent_t ev;
   MP2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   struct EvGuard {
@@ -168,15 +195,17 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
   MP2_CUDA(cudaStreamSynchronize(st));
   MP2_CUDA(cudaStreamSynchronize(cp));
   if (handle_out) {
+    int device = 0;
+    MP2_CUDA(cudaGetDevice(&device));
     mp2gpu_batch *b = new mp2gpu_batch();
-    MP2_CUDA(cudaGetDevice(&b->device));
+    b->device = device;
     b->ncols = ncols;
     b->n_log = n_log;
     b->rate_bits = rate_bits;
     b->cap_height = cap_height;
     b->hash_kind = hash_kind;
     b->coeffs = d_coeffs.release();
-    b->lde = d_lde.release();
+    b->lde = nullptr;  // the row-major leaves serve every reader of the handle; the column-major copy is dropped
     b->leaves = d_leaves.release();
     b->digests = d_dig.release();
     b->cap = d_cap.release();
@@ -458,7 +487,7 @@ const char *mp2gpu_batch_fetch_rows(const mp2gpu_batch *b, const uint64_t *row_i
     const size_t N = ((size_t)1 << b->n_log) << b->rate_bits;
     for (size_t i = 0; i < nrows; i++)
       if (row_idx[i] >= N) return "get_lde_values: row index out of range";
-    t_ctx.device = b->device;
+    DeviceScope on_batch_device(b->device);
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
     DevBuf d_idx, d_out;
@@ -480,7 +509,7 @@ const char *mp2gpu_batch_prove(const mp2gpu_batch *b, size_t leaf_index, uint64_
     std::vector<size_t> idx;
     MP2_TRY(merkle_prove_indices(N, b->cap_height, leaf_index, &idx));
     if (!idx.empty() && !siblings_out) return "null siblings_out";
-    t_ctx.device = b->device;
+    DeviceScope on_batch_device(b->device);
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
     for (size_t i = 0; i < idx.size(); i++)
@@ -496,7 +525,7 @@ const char *mp2gpu_batch_open(const mp2gpu_batch *b, const uint64_t *leaf_idx, s
   return guarded([&]() -> Status {
     if (!b) return "null batch handle";
     if (count && !leaf_idx) return "null leaf_idx";
-    t_ctx.device = b->device;
+    DeviceScope on_batch_device(b->device);
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
     const size_t N = ((size_t)1 << b->n_log) << b->rate_bits;
@@ -509,7 +538,7 @@ const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_ou
                                uint64_t *digests_out, uint64_t *cap_out) {
   return guarded([&]() -> Status {
     if (!b) return "null batch handle";
-    t_ctx.device = b->device;
+    DeviceScope on_batch_device(b->device);
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
     const size_t n = (size_t)1 << b->n_log, N = n << b->rate_bits, ncap = (size_t)1 << b->cap_height;

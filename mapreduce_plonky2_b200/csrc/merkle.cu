@@ -527,15 +527,15 @@ Status pow_search(const u64 *state12_host, u32 pos, u32 min_lz, u32 hash_kind, u
   if (pos >= 8) return "witness position must be inside the sponge rate";
   PowState init;
   for (int i = 0; i < 12; i++) init.s[i] = state12_host[i];
-  u64 *d_best = nullptr;
-  MP2_CUDA(cudaMallocAsync(&d_best, sizeof(u64), st));
+  DevBuf best;
+  MP2_TRY(best.alloc(1, st));
+  u64 *d_best = best.p;
   MP2_CUDA(cudaMemsetAsync(d_best, 0xFF, sizeof(u64), st));
   unsigned g = grid_for(count, MP2_HASH_BLOCK);
   if (hash_kind == MP2_HASH_POSEIDON2) { ProfScope _p("k_pow_search", st); k_pow_search<MP2_HASH_POSEIDON2><<<g, MP2_HASH_BLOCK, 0, st>>>(init, pos, min_lz, start, count, d_best); }
   else { ProfScope _p("k_pow_search", st); k_pow_search<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(init, pos, min_lz, start, count, d_best); }
   MP2_LAUNCH_CHECK();
   MP2_CUDA(cudaMemcpyAsync(found, d_best, sizeof(u64), cudaMemcpyDeviceToHost, st));
-  MP2_CUDA(cudaFreeAsync(d_best, st));
   MP2_CUDA(cudaStreamSynchronize(st));
   return "";
 }
@@ -571,25 +571,23 @@ Status merkle_open(const u64 *rowmajor, const u64 *colmajor, size_t stride, size
       slots[q * h + i] = base + 2 * ((pair_index << (i + 1)) + ((size_t)1 << i) - 1) + (1 - parity);
     }
   }
-  u64 *d_idx = nullptr, *d_rows = nullptr, *d_slots = nullptr, *d_sib = nullptr;
-  MP2_CUDA(cudaMallocAsync(&d_idx, sizeof(u64) * count, st));
-  MP2_CUDA(cudaMemcpyAsync(d_idx, idx_host, sizeof(u64) * count, cudaMemcpyHostToDevice, st));
+  DevBuf d_idx, d_rows, d_slots, d_sib;
+  MP2_TRY(d_idx.alloc(count, st));
+  MP2_CUDA(cudaMemcpyAsync(d_idx.p, idx_host, sizeof(u64) * count, cudaMemcpyHostToDevice, st));
   if (rows_out && leaf_len) {
-    MP2_CUDA(cudaMallocAsync(&d_rows, sizeof(u64) * count * leaf_len, st));
-    MP2_TRY(gather_rows(rowmajor, colmajor, stride, leaf_len, d_idx, count, d_rows, st));
-    MP2_CUDA(cudaMemcpyAsync(rows_out, d_rows, sizeof(u64) * count * leaf_len, cudaMemcpyDeviceToHost, st));
+    MP2_TRY(d_rows.alloc(count * leaf_len, st));
+    MP2_TRY(gather_rows(rowmajor, colmajor, stride, leaf_len, d_idx.p, count, d_rows.p, st));
+    MP2_CUDA(cudaMemcpyAsync(rows_out, d_rows.p, sizeof(u64) * count * leaf_len, cudaMemcpyDeviceToHost, st));
   }
   if (sib_out && h) {
-    MP2_CUDA(cudaMallocAsync(&d_slots, sizeof(u64) * count * h, st));
-    MP2_CUDA(cudaMallocAsync(&d_sib, sizeof(u64) * 4 * count * h, st));
-    MP2_CUDA(cudaMemcpyAsync(d_slots, slots.data(), sizeof(u64) * count * h, cudaMemcpyHostToDevice, st));
-    { ProfScope _p("k_gather_digests", st); k_gather_digests<<<grid_for(4 * count * h, 256), 256, 0, st>>>(digests, d_slots, count * h, d_sib); }
+    MP2_TRY(d_slots.alloc(count * h, st));
+    MP2_TRY(d_sib.alloc(4 * count * h, st));
+    MP2_CUDA(cudaMemcpyAsync(d_slots.p, slots.data(), sizeof(u64) * count * h, cudaMemcpyHostToDevice, st));
+    { ProfScope _p("k_gather_digests", st); k_gather_digests<<<grid_for(4 * count * h, 256), 256, 0, st>>>(digests, d_slots.p, count * h, d_sib.p); }
     MP2_LAUNCH_CHECK();
-    MP2_CUDA(cudaMemcpyAsync(sib_out, d_sib, sizeof(u64) * 4 * count * h, cudaMemcpyDeviceToHost, st));
+    MP2_CUDA(cudaMemcpyAsync(sib_out, d_sib.p, sizeof(u64) * 4 * count * h, cudaMemcpyDeviceToHost, st));
   }
   MP2_CUDA(cudaStreamSynchronize(st));
-  for (u64 *p : {d_idx, d_rows, d_slots, d_sib})
-    if (p) MP2_CUDA(cudaFreeAsync(p, st));
   return "";
 }
 }  // namespace mp2

@@ -457,8 +457,9 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
   MP2_TRY(table_roots(tp.b, st, &W2));
   MP2_TRY(table_roots(n_log, st, &Wn));
   const size_t n = (size_t)1 << n_log;
-  u64 *tmp = nullptr;
-  MP2_CUDA(cudaMallocAsync(&tmp, sizeof(u64) * n * ncols, st));
+  DevBuf scratch;
+  MP2_TRY(scratch.alloc(n * ncols, st));
+  u64 *tmp = scratch.p;
   {
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);
@@ -481,7 +482,6 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, none, tp2, W2); }
     MP2_LAUNCH_CHECK();
   }
-  MP2_CUDA(cudaFreeAsync(tmp, st));
   return "";
 }
 
@@ -530,12 +530,14 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
   // output lives in other ranks' HBM) in a scratch buffer of the same shape
   LdeMap mid_map = map;
   u64 *mid = lde;
+  DevBuf scratch;
   if (map.peer) {
     const size_t N = (size_t)1 << N_log;
     mid_map = LdeMap{};
     mid_map.ls_log = N_log;
     mid_map.col_stride = N;
-    MP2_CUDA(cudaMallocAsync(&mid, sizeof(u64) * N * ncols, st));
+    MP2_TRY(scratch.alloc(N * ncols, st));
+    mid = scratch.p;
   }
   {
     u32 tile_log = tp.a + tp.lines_log;
@@ -559,7 +561,6 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(mid, 0, lde, 0, mid_map, map, tp2, W2); }
     MP2_LAUNCH_CHECK();
   }
-  if (map.peer) MP2_CUDA(cudaFreeAsync(mid, st));
   return "";
 }
 
