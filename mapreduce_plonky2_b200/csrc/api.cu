@@ -19,6 +19,7 @@ namespace {
 struct DevStreams {
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute
+  cudaStream_t up_stream = nullptr;    // host->device uploads overlapped with compute
 };
 struct ThreadCtx {
   int device = 0;
@@ -27,7 +28,7 @@ struct ThreadCtx {
 thread_local ThreadCtx t_ctx;
 
 // Binds the calling thread to its device and returns its private stream (and, optionally, its copy stream).
-Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr) {
+Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr, cudaStream_t *up_out = nullptr) {
   ThreadCtx &c = t_ctx;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -38,14 +39,17 @@ Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr) {
   if (c.per_device.size() < (size_t)ndev) c.per_device.resize(ndev);
   DevStreams &d = c.per_device[c.device];
   if (!d.stream) {
-    cudaStream_t s1 = nullptr, s2 = nullptr;
+    cudaStream_t s1 = nullptr, s2 = nullptr, s3 = nullptr;
     MP2_CUDA(cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking));
-    if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking) != cudaSuccess) {
       cudaStreamDestroy(s1);
-      return "cudaStreamCreateWithFlags failed for the copy stream";
+      if (s2) cudaStreamDestroy(s2);
+      return "cudaStreamCreateWithFlags failed for the copy streams";
     }
     d.stream = s1;
     d.copy_stream = s2;
+    d.up_stream = s3;
     // keep freed blocks in the stream-ordered pool: commitments reuse the same sizes over and over
     cudaMemPool_t pool;
     MP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, c.device));
@@ -54,6 +58,7 @@ Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr) {
   }
   *out = d.stream;
   if (copy_out) *copy_out = d.copy_stream;
+  if (up_out) *up_out = d.up_stream;
   return "";
 }
 
@@ -141,8 +146,8 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
                    uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **handle_out) {
   MP2_TRY(check_commit_args(ncols, n_log, rate_bits, cap_height, hash_kind));
   if (!cols || !cap_out) return "null cols / cap_out";
-  cudaStream_t st, cp;
-  MP2_TRY(ctx_stream(&st, &cp));
+  cudaStream_t st, cp, up;
+  MP2_TRY(ctx_stream(&st, &cp, &up));
   const size_t n = (size_t)1 << n_log, N = n << rate_bits, ncap = (size_t)1 << cap_height;
   const size_t ndig = 2 * (N - ncap);
   const bool want_rows = leaves_out != nullptr || handle_out != nullptr;
@@ -150,9 +155,12 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
   // declared after the buffers, so it runs before they are returned to the pool: on an early error return the
   // copy stream may still be reading them
   struct CopyDrain {
-    cudaStream_t s;
-    ~CopyDrain() { cudaStreamSynchronize(s); }
-  } copy_drain{cp};
+    cudaStream_t a, b;
+    ~CopyDrain() {
+      cudaStreamSynchronize(a);
+      cudaStreamSynchronize(b);
+    }
+  } copy_drain{cp, up};
   MP2_TRY(d_in.alloc(ncols * n, st));
   MP2_TRY(d_coeffs.alloc(ncols * n, st));
   MP2_TRY(d_lde.alloc(ncols * N, st));
@@ -168,15 +176,31 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
     cudaEvent_t e;
     ~EvGuard() { cudaEventDestroy(e); }
   } ev_guard{ev};
-  MP2_TRY(copy_columns_h2d(d_in.p, cols, ncols, n, st));
-  if (from_coeffs) MP2_TRY(ntt_canonicalize(d_in.p, n, d_coeffs.p, n, ncols, n, st));
-  else MP2_TRY(ntt_intt(d_in.p, n, d_coeffs.p, n, ncols, n_log, st));
-  if (coeffs_out) {
+  // The transforms are per column, so big batches go through in column blocks: the upload of block k+1 overlaps
+  // the iNTT + LDE of block k, and block k's coefficients travel back while block k+1 is transformed.
+  const size_t nblocks = (ncols >= 16 && ncols * n >= ((size_t)1 << 24)) ? 8 : 1;
+  if (nblocks > 1) {  // the buffers were allocated in st's order: the upload stream may touch them only after that
     MP2_CUDA(cudaEventRecord(ev, st));
-    MP2_CUDA(cudaStreamWaitEvent(cp, ev, 0));
-    MP2_TRY(copy_columns_d2h(coeffs_out, d_coeffs.p, ncols, n, cp));
+    MP2_CUDA(cudaStreamWaitEvent(up, ev, 0));
   }
-  MP2_TRY(ntt_coset_lde(d_coeffs.p, n, d_lde.p, N, ncols, n_log, rate_bits, 0, 0, st));
+  for (size_t k = 0; k < nblocks; k++) {
+    const size_t c0 = k * ncols / nblocks, c1 = (k + 1) * ncols / nblocks, cnt = c1 - c0;
+    if (!cnt) continue;
+    u64 *in_k = d_in.p + c0 * n, *co_k = d_coeffs.p + c0 * n;
+    MP2_TRY(copy_columns_h2d(in_k, cols + c0, cnt, n, nblocks > 1 ? up : st));
+    if (nblocks > 1) {
+      MP2_CUDA(cudaEventRecord(ev, up));
+      MP2_CUDA(cudaStreamWaitEvent(st, ev, 0));
+    }
+    if (from_coeffs) MP2_TRY(ntt_canonicalize(in_k, n, co_k, n, cnt, n, st));
+    else MP2_TRY(ntt_intt(in_k, n, co_k, n, cnt, n_log, st));
+    if (coeffs_out) {
+      MP2_CUDA(cudaEventRecord(ev, st));
+      MP2_CUDA(cudaStreamWaitEvent(cp, ev, 0));
+      MP2_TRY(copy_columns_d2h(coeffs_out + c0, co_k, cnt, n, cp));
+    }
+    MP2_TRY(ntt_coset_lde(co_k, n, d_lde.p + c0 * N, N, cnt, n_log, rate_bits, 0, 0, st));
+  }
   const size_t nchunks = (leaves_out && N >= ((size_t)1 << 16)) ? 8 : 1;
   for (size_t j = 0; j < nchunks; j++) {
     const size_t lb = j * (N / nchunks), le = (j + 1) * (N / nchunks);
@@ -209,6 +233,7 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
     b->leaves = d_leaves.release();
     b->digests = d_dig.release();
     b->cap = d_cap.release();
+    b->owner_stream = st;
     *handle_out = b;
   }
   return "";
@@ -557,9 +582,16 @@ const char *mp2gpu_batch_fetch(const mp2gpu_batch *b, uint64_t *const *coeffs_ou
 
 void mp2gpu_batch_free(mp2gpu_batch *b) {
   if (!b) return;
+  // Every call that reads a handle synchronises before it returns, so nothing is in flight on these buffers.
+  // They are freed on the stream they were allocated on: the pool then hands the same blocks to that thread's
+  // next commitment without growing (freeing 17 GB on another stream, or with cudaFree, made the next
+  // allocation map fresh pages: 350 -> 530..960 ms per wide-batch call).
+  int prev = 0;
+  cudaGetDevice(&prev);
   cudaSetDevice(b->device);
   for (u64 *p : {b->coeffs, b->lde, b->leaves, b->digests, b->cap})
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, b->owner_stream);
+  cudaSetDevice(prev);
   delete b;
 }
 

@@ -182,4 +182,5 @@ struct mp2gpu_batch {
   size_t ncols;
   u32 n_log, rate_bits, cap_height, hash_kind;
   u64 *coeffs, *lde, *leaves, *digests, *cap;  // device; coeffs: ncols x n, lde: ncols x N, column-major
+  cudaStream_t owner_stream;  // the stream the buffers were allocated on (stream-ordered pool): they are freed on it
 };
