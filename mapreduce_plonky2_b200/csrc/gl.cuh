@@ -129,7 +129,11 @@ GL_DEV u64 gl_mul(u64 a, u64 b) {
       "add.cc.u32 %1, %1, l10;\n\taddc.cc.u32 %2, %2, h10;\n\taddc.u32 %3, %3, 0;\n\t}"
       : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
       : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+#ifdef MP2_MUL_REDUCE_FMA  // per translation unit: the NTT kernels are alu-bound with the fma pipe half idle
+  return gl_reduce128w_fma(w0, w1, w2, w3);
+#else
   return gl_reduce128w(w0, w1, w2, w3);
+#endif
 }
 // loose * loose + loose -> loose: the addend rides on the 128-bit product (a*b + c < 2^128), one reduction
 GL_DEV u64 gl_mul_add(u64 a, u64 b, u64 c) {

@@ -25,6 +25,9 @@
 // n >  2^14 : two passes (n = n1*n2, four-step), each a shared-memory transform on a tile of adjacent
 //             lines (4 lines of 2^10 points at n = 2^20: the strided pass moves whole 32-byte sectors).
 #include "internal.h"
+#ifdef MP2_NTT_MUL_REDUCE_FMA
+#define MP2_MUL_REDUCE_FMA 1
+#endif
 #include "gl.cuh"
 
 namespace mp2 {
@@ -285,25 +288,30 @@ struct TwoPass {
   u32 n_log, a, b;   // n1 = 2^a (strided pass 1), n2 = 2^b (contiguous pass 2)
   u32 lines_log;
   u32 rate_bits;
-  u32 ncols;         // pass 1 only: the grid is flattened, see k_pass1
+  u32 ncols, tg_log; // pass 1 only: the grid is flattened, see k_pass1 (tg_log = log2 of tiles per group)
   int inverse;       // 1: iNTT natural -> natural; 0: coset LDE natural -> leaf order
   u64 n_inv;
 };
 
 // pass 1: tile = LINES adjacent j2; size-n1 transform over j1 (stride n2); then the four-step
-// twiddle w_n^(j2*k1).  1-D grid of ncols * cosets * (n2 / LINES) CTAs, column fastest, then coset, then
-// tile: the CTAs in flight share one 32 KB slice of the coset-scale table, and the 2^r cosets of an input tile
-// are ncols CTAs apart, so both are fetched from HBM once and re-read from L2 (ncu: pass-1 DRAM reads 8x the
-// input with the coset as the slowest grid dimension).
+// twiddle w_n^(j2*k1).  1-D grid of ncols * cosets * (n2 / LINES) CTAs ordered (fast -> slow) 4 adjacent tiles,
+// coset, column, tile group:
+//   * the 2^r cosets of an input tile are 4 CTAs apart, so the tile comes from HBM once and is re-read from L2
+//     (with the coset as the slowest grid dimension pass 1 read the input 8 times: 17.5 GB for 2.1 GB);
+//   * 4 adjacent tiles (4 x 32-byte sectors = one 128-byte line of every row) run together, so no fetched
+//     sector is left unused (ordering by column first lost that: 21.5 GB at 256 columns);
+//   * the coset-scale slices of a tile group (1 MB) stay in L2 while the columns sweep over them.
 __global__ void __launch_bounds__(1024)
 k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
         TwoPass tp, const u64 *__restrict__ W1, const u64 *__restrict__ Wn, const u64 *__restrict__ scale) {
   extern __shared__ u64 sm[];
   const u32 LINES = 1u << tp.lines_log, S = 1u << tp.a;
   const size_t n2 = (size_t)1 << tp.b;
-  const u32 kq = blockIdx.x / tp.ncols;
-  const size_t c = blockIdx.x - kq * tp.ncols, k = kq & ((1u << tp.rate_bits) - 1);
-  const size_t q0 = (size_t)(kq >> tp.rate_bits) * LINES;
+  const u32 t4 = blockIdx.x & ((1u << tp.tg_log) - 1);
+  const size_t k = (blockIdx.x >> tp.tg_log) & ((1u << tp.rate_bits) - 1);
+  const u32 rest = blockIdx.x >> (tp.tg_log + tp.rate_bits), tg = rest / tp.ncols;
+  const size_t c = rest - tg * tp.ncols;
+  const size_t q0 = (size_t)((tg << tp.tg_log) + t4) * LINES;
   const u64 *sc = tp.inverse ? nullptr : scale + (k << tp.n_log);
   const u32 total = S << tp.lines_log, nthr = blockDim.x;
   for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
@@ -467,6 +475,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     const size_t ctas = (((size_t)1 << tp.b) >> tp.lines_log) * ncols;
     if (ctas > 0x7fffffffull) return "batch too large for one iNTT launch (columns x tiles > 2^31)";
     tp.ncols = (u32)ncols;
+    tp.tg_log = std::min(2u, tp.b - tp.lines_log);
     dim3 grid((unsigned)ctas, 1, 1);
     { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, tmp, n, none, tp, W1, Wn, nullptr); }
     MP2_LAUNCH_CHECK();
@@ -546,6 +555,7 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     const size_t ctas = ((((size_t)1 << tp.b) >> tp.lines_log) << rate_bits) * ncols;
     if (ctas > 0x7fffffffull) return "batch too large for one LDE launch (columns x cosets x tiles > 2^31)";
     tp.ncols = (u32)ncols;
+    tp.tg_log = std::min(2u, tp.b - tp.lines_log);
     dim3 grid((unsigned)ctas, 1, 1);
     { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, mid, 0, mid_map, tp, W1, Wn, scale); }
     MP2_LAUNCH_CHECK();
