@@ -179,6 +179,12 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
   // The transforms are per column, so big batches go through in column blocks: the upload of block k+1 overlaps
   // the iNTT + LDE of block k, and block k's coefficients travel back while block k+1 is transformed.
   const size_t nblocks = (ncols >= 16 && ncols * n >= ((size_t)1 << 24)) ? 8 : 1;
+  // Leaf rows go back to the host in blocks while the next block is hashed.  When the LDE is the two-pass kind and
+  // a block is one coset (leaf block j = coset bitrev_r(j)), the contiguous pass of that coset is run just before
+  // its block is hashed, so the first rows start travelling one pass earlier.
+  const size_t cosets = (size_t)1 << rate_bits;
+  const size_t nchunks = !(leaves_out && N >= ((size_t)1 << 16)) ? 1 : (cosets >= 4 && cosets <= 16) ? cosets : 8;
+  const bool split_lde = nchunks == cosets && nchunks > 1 && ntt_lde_is_two_pass(n_log);
   if (nblocks > 1) {  // the buffers were allocated in st's order: the upload stream may touch them only after that
     MP2_CUDA(cudaEventRecord(ev, st));
     MP2_CUDA(cudaStreamWaitEvent(up, ev, 0));
@@ -199,11 +205,16 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
       MP2_CUDA(cudaStreamWaitEvent(cp, ev, 0));
       MP2_TRY(copy_columns_d2h(coeffs_out + c0, co_k, cnt, n, cp));
     }
-    MP2_TRY(ntt_coset_lde(co_k, n, d_lde.p + c0 * N, N, cnt, n_log, rate_bits, 0, 0, st));
+    MP2_TRY(ntt_coset_lde(co_k, n, d_lde.p + c0 * N, N, cnt, n_log, rate_bits, 0, 0, st, nullptr, kCosetShift,
+                          split_lde ? LDE_PASS1 : LDE_ALL));
   }
-  const size_t nchunks = (leaves_out && N >= ((size_t)1 << 16)) ? 8 : 1;
   for (size_t j = 0; j < nchunks; j++) {
     const size_t lb = j * (N / nchunks), le = (j + 1) * (N / nchunks);
+    if (split_lde) {
+      u32 k = 0;  // bitrev_r(j)
+      for (u32 bit = 0; bit < rate_bits; bit++) k |= ((j >> bit) & 1) << (rate_bits - 1 - bit);
+      MP2_TRY(ntt_coset_lde(d_coeffs.p, n, d_lde.p, N, ncols, n_log, rate_bits, 0, 0, st, nullptr, kCosetShift, LDE_PASS2, k, 1));
+    }
     MP2_TRY(merkle_colmajor_leaves(d_lde.p, N, ncols, N, cap_height, hash_kind, lb, le, d_leaves.p, d_dig.p, d_cap.p, st));
     if (leaves_out) {
       MP2_CUDA(cudaEventRecord(ev, st));

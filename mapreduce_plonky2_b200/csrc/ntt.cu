@@ -289,6 +289,7 @@ struct TwoPass {
   u32 lines_log;
   u32 rate_bits;
   u32 ncols, tg_log; // pass 1 only: the grid is flattened, see k_pass1 (tg_log = log2 of tiles per group)
+  u32 coset0;        // pass 2 only: first coset of this launch (grid.z counts from it)
   int inverse;       // 1: iNTT natural -> natural; 0: coset LDE natural -> leaf order
   u64 n_inv;
 };
@@ -359,7 +360,7 @@ k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, siz
   extern __shared__ u64 sm[];
   const u32 LINES = 1u << tp.lines_log, S = 1u << tp.b;
   const size_t n = (size_t)1 << tp.n_log, n1 = (size_t)1 << tp.a, n2 = (size_t)1 << tp.b;
-  const size_t c = blockIdx.y, k = blockIdx.z, r0 = (size_t)blockIdx.x * LINES;
+  const size_t c = blockIdx.y, k = blockIdx.z + tp.coset0, r0 = (size_t)blockIdx.x * LINES;
   const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
   const u32 total = S << tp.lines_log, nthr = blockDim.x;
   for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
@@ -494,10 +495,14 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
   return "";
 }
 
+bool ntt_lde_is_two_pass(u32 n_log) { return n_log > kMaxSingleLog; }
+
 Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols, u32 n_log,
                      u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st, u64 *const *peer_bases,
-                     u64 shift) {
+                     u64 shift, int phase, u32 coset0, u32 ncosets) {
   if (ncols == 0) return "";
+  if (phase != LDE_ALL && (peer_bases || !ntt_lde_is_two_pass(n_log))) return "split LDE phases need the local two-pass path";
+  if (phase == LDE_PASS2 && (ncosets == 0 || coset0 + ncosets > (1u << rate_bits))) return "bad coset range";
   const u32 N_log = n_log + rate_bits;
   if (N_log > 32) return "n_log + rate_bits exceeds the field's two-adicity (32)";
   if (shard_log > N_log) return "shard_log larger than log2(number of leaves)";
@@ -548,7 +553,8 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     MP2_TRY(scratch.alloc(N * ncols, st));
     mid = scratch.p;
   }
-  {
+  tp.coset0 = 0;
+  if (phase != LDE_PASS2) {
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);
     MP2_TRY(allow_smem(k_pass1, smem));
@@ -560,14 +566,15 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, mid, 0, mid_map, tp, W1, Wn, scale); }
     MP2_LAUNCH_CHECK();
   }
-  {
+  if (phase != LDE_PASS1) {
     u32 lines_log = std::min(tp.lines_log, tp.a);
     TwoPass tp2 = tp;
     tp2.lines_log = lines_log;
+    tp2.coset0 = phase == LDE_PASS2 ? coset0 : 0;
     u32 tile_log = tp.b + lines_log;
     size_t smem = smem_bytes_for(tile_log);
     MP2_TRY(allow_smem(k_pass2, smem));
-    dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, cosets);
+    dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, phase == LDE_PASS2 ? ncosets : cosets);
     { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(mid, 0, lde, 0, mid_map, map, tp2, W2); }
     MP2_LAUNCH_CHECK();
   }

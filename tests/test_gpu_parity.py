@@ -168,6 +168,9 @@ def test_polynomial_batch_two_pass_sizes(G, oracle, log_n):
     cols = field_elems(0x2A55 + log_n, (3, 1 << log_n))
     _check_batch(G, oracle, cols, 3, 4, 1)
     _check_batch(G, oracle, cols[:2], 1, 2, 0, from_coeffs=True)
+    if log_n == 15:     # the host entry point finishes the LDE coset by coset for 4..16 cosets: cover 4 and 16 too
+        _check_batch(G, oracle, cols[:2], 2, 3, 1)
+        _check_batch(G, oracle, cols[:1], 4, 0, 0, from_coeffs=True)
 
 
 def test_intt_lde_large_degree_tiles(G, oracle):
