@@ -20,7 +20,10 @@
  * pinned: the 360 Poseidon round constants (regenerated from ChaCha8Rng seed 0 and
  * checked against the published table anchors), plonky2's three Poseidon
  * permutation test vectors, the Horizen-Labs Poseidon2 t=12 KAT, and the
- * Goldilocks generators (tests/test_oracle_pins.py).
+ * Goldilocks generators (tests/test_oracle_pins.py).  Structurally (the kind of pin the reference's own
+ * tests use -- prove then verify): a FRI proof assembled from this library's commitments, prove_openings
+ * combination, commit phase and Merkle paths is accepted by a by-definition restatement of plonky2's FRI
+ * verifier, and tampered proofs are rejected (tests/test_fri_prove_verify.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may call into this library.
