@@ -58,7 +58,7 @@ def parse_args():
                     help="leaf: mp2-v1 values-extraction leaf proof (configs[1]); aggregation: 2-proof universal-verifier "
                          "aggregation (configs[3])")
     ap.add_argument("--proofs", type=int, default=64, help="trace workload: proofs per GPU per step")
-    ap.add_argument("--streams", type=int, default=4, help="trace workload: proofs in flight per GPU")
+    ap.add_argument("--streams", type=int, default=8, help="trace workload: proofs in flight per GPU")
     ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
                     help="N > 1: peer = LDE kernel stores into the peers' buffers over NVLink; nccl = all_to_all_single")
     ap.add_argument("--no-e2e", action="store_true")

@@ -74,7 +74,7 @@ def proof_ops(degrees=LEAF_PROOF_DEGREES) -> List[Op]:
 class TraceRunner:
     """Replays proof traces on the current CUDA device, ``nstreams`` proofs in flight."""
 
-    def __init__(self, degrees=LEAF_PROOF_DEGREES, hash_kind: int = 1, nstreams: int = 4):
+    def __init__(self, degrees=LEAF_PROOF_DEGREES, hash_kind: int = 1, nstreams: int = 8):
         import torch
 
         from . import device as D
