@@ -202,11 +202,14 @@ const char *mp2gpu_dev_coset_lde(const uint64_t *coeffs, size_t in_stride, uint6
  * rank g) is written straight to shard_bases[g] + c*lde_stride -- pointers into the other ranks' HBM
  * mapped over NVLink/NVSwitch (peer or symmetric memory), so no all-to-all follows.  shard_bases is a
  * HOST array of 2^shard_log (<= 16) device pointers.  Callers order the kernel against the peers with
- * their own barrier (sharded.py: symmetric-memory barrier before and after). */
+ * their own barrier (sharded.py: symmetric-memory barrier before and after).  first_shard: the destination this
+ * launch stores to first, the others following in rotated order -- every rank passes its own index, so that at
+ * any moment the ranks write to different peers (all starting with shard 0 serialises the exchange on one
+ * NVLink ingress). */
 const char *mp2gpu_dev_coset_lde_peer(const uint64_t *coeffs, size_t in_stride,
                                       uint64_t *const *shard_bases, size_t lde_stride, size_t ncols,
                                       uint32_t n_log, uint32_t rate_bits, uint32_t shard_log,
-                                      void *stream);
+                                      uint32_t first_shard, void *stream);
 /* Leaf-ordered column-major LDE (column c at lde + c*lde_stride, nleaves elements) -> optional
  * row-major leaves (nleaves x ncols), digests and cap of a tree with `nleaves` leaves.  A rank of a
  * G-way row-sharded batch passes nleaves = N/G and cap_height - log2(G): its digests/cap are the

@@ -108,6 +108,8 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
                 u32 n_log, cudaStream_t st);
 // peer_bases (optional, host array of 2^shard_log device pointers): shard g is written to peer_bases[g]
 // (column c at + c*lde_stride) instead of lde + g*shard_stride -- the exchange fused into the store.
+// first_shard: the destination the launch stores to first (the others follow in rotated order); ranks pass
+// their own index so that they do not all target the same peer at the same time.
 // phase (two-pass sizes only, local output): LDE_PASS1 runs the strided pass of every coset and leaves the
 // four-step intermediate in `lde`; LDE_PASS2 finishes cosets [coset0, coset0 + ncosets), i.e. the leaf blocks
 // bitrev_r(k) -- the host entry point interleaves those with the hashing and the copy-out of each block.
@@ -116,7 +118,7 @@ bool ntt_lde_is_two_pass(u32 n_log);
 Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols,
                      u32 n_log, u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st,
                      u64 *const *peer_bases = nullptr, u64 shift = kCosetShift, int phase = LDE_ALL,
-                     u32 coset0 = 0, u32 ncosets = 0);
+                     u32 coset0 = 0, u32 ncosets = 0, u32 first_shard = 0);
 
 // ---- FRI commit phase (fri.cu) ----
 // coeffs' = chunks(2^arity_bits) reduced with powers of beta; ext polys are component-major (2 x len)

@@ -49,6 +49,10 @@ static const u32 kTileLog = MP2_NTT_TILE_LOG;  // target tile (elements) when se
 struct LdeMap {  // (column c, leaf L) -> address in the leaf-ordered, column-major, shardable buffer
   u32 ls_log;    // log2(leaves per shard)
   size_t shard_stride, col_stride;
+  // coset_rot: the launch visits the cosets in the order brev_r((z + coset_rot) mod 2^r), i.e. leaf blocks -- and
+  // with them destination shards -- in rotated natural order, so that the ranks of a peer exchange, each passing
+  // its own rotation, store to different destinations at any moment instead of all hitting rank 0 first
+  u32 coset_rot;
   // peer mode: shard g of the output starts at bases[g] -- a buffer in rank g's HBM, mapped over NVLink
   // (the exchange of the sharded commitment happens in the store of the LDE kernel itself)
   u32 peer;
@@ -256,7 +260,8 @@ __global__ void __launch_bounds__(1024)
 k_lde_single(const u64 *__restrict__ coeffs, size_t in_stride, u64 *__restrict__ lde, LdeMap map, u32 ncols, u32 s,
              u32 lines_log, u32 rate_bits, const u64 *__restrict__ W, const u64 *__restrict__ scale) {
   extern __shared__ u64 sm[];
-  const u32 S = 1u << s, c0 = blockIdx.x << lines_log, k = blockIdx.y;
+  const u32 S = 1u << s, c0 = blockIdx.x << lines_log;
+  const u32 k = map.peer ? brev_bits((blockIdx.y + map.coset_rot) & ((1u << rate_bits) - 1), rate_bits) : blockIdx.y;
   const u64 *sc = scale + ((size_t)k << s);  // (7*w_N^k)^j
   const u32 total = S << lines_log, nthr = blockDim.x;
   for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
@@ -360,7 +365,9 @@ k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, siz
   extern __shared__ u64 sm[];
   const u32 LINES = 1u << tp.lines_log, S = 1u << tp.b;
   const size_t n = (size_t)1 << tp.n_log, n1 = (size_t)1 << tp.a, n2 = (size_t)1 << tp.b;
-  const size_t c = blockIdx.y, k = blockIdx.z + tp.coset0, r0 = (size_t)blockIdx.x * LINES;
+  const size_t c = blockIdx.y, r0 = (size_t)blockIdx.x * LINES;
+  const size_t k = out_map.peer ? brev_bits((blockIdx.z + out_map.coset_rot) & ((1u << tp.rate_bits) - 1), tp.rate_bits)
+                                : blockIdx.z + tp.coset0;
   const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
   const u32 total = S << tp.lines_log, nthr = blockDim.x;
   for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
@@ -499,7 +506,7 @@ bool ntt_lde_is_two_pass(u32 n_log) { return n_log > kMaxSingleLog; }
 
 Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_stride, size_t ncols, u32 n_log,
                      u32 rate_bits, u32 shard_log, size_t shard_stride, cudaStream_t st, u64 *const *peer_bases,
-                     u64 shift, int phase, u32 coset0, u32 ncosets) {
+                     u64 shift, int phase, u32 coset0, u32 ncosets, u32 first_shard) {
   if (ncols == 0) return "";
   if (phase != LDE_ALL && (peer_bases || !ntt_lde_is_two_pass(n_log))) return "split LDE phases need the local two-pass path";
   if (phase == LDE_PASS2 && (ncosets == 0 || coset0 + ncosets > (1u << rate_bits))) return "bad coset range";
@@ -515,7 +522,11 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
   map.col_stride = lde_stride;
   if (peer_bases) {
     if (shard_log > 4) return "peer exchange supports at most 16 ranks";
+    if (first_shard >> shard_log) return "first_shard out of range";
     map.peer = 1;
+    // leaf block j belongs to shard j >> (rate_bits - shard_log) (shard_log <= rate_bits is implied by G <= 2^cap
+    // only for the usual shapes; with more shards than cosets every block spans several shards and no rotation helps)
+    map.coset_rot = shard_log <= rate_bits ? first_shard << (rate_bits - shard_log) : 0;
     for (u32 g = 0; g < (1u << shard_log); g++) map.bases[g] = peer_bases[g];
   }
   const unsigned cosets = 1u << rate_bits;

@@ -82,16 +82,17 @@ def coset_lde(coeffs: torch.Tensor, lde: torch.Tensor, rate_bits: int, shard_log
               n.bit_length() - 1, rate_bits, shard_log, shard_stride, _stream_ptr())
 
 
-def coset_lde_peer(coeffs: torch.Tensor, shard_ptrs, n_loc: int, rate_bits: int) -> None:
+def coset_lde_peer(coeffs: torch.Tensor, shard_ptrs, n_loc: int, rate_bits: int, first_shard: int = 0) -> None:
     """coeffs (ncols, n) -> LDE whose shard g is stored at device address ``shard_ptrs[g]`` (column c at
-    + c*n_loc elements): the peers' receive buffers, i.e. the all-to-all happens in the kernel's store."""
+    + c*n_loc elements): the peers' receive buffers, i.e. the all-to-all happens in the kernel's store.
+    ``first_shard``: destination written first (pass the caller's rank: the ranks then never share a target)."""
     import ctypes as C
 
     ncols, n = coeffs.shape
     G = len(shard_ptrs)
     arr = (C.c_void_p * G)(*[C.c_void_p(int(p)) for p in shard_ptrs])
     _lib.call("mp2gpu_dev_coset_lde_peer", _chk(coeffs, "coeffs"), n, arr, n_loc, ncols, n.bit_length() - 1,
-              rate_bits, G.bit_length() - 1, _stream_ptr())
+              rate_bits, G.bit_length() - 1, first_shard, _stream_ptr())
 
 
 def merkle_colmajor(lde: torch.Tensor, cap_height: int, hash_kind: int, leaves: Optional[torch.Tensor],

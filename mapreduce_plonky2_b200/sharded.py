@@ -45,8 +45,8 @@ class CudaEngine:
     def coset_lde(self, coeffs, lde, rate_bits, shard_log):
         self.d.coset_lde(coeffs, lde, rate_bits, shard_log)
 
-    def coset_lde_peer(self, coeffs, shard_ptrs, n_loc, rate_bits):
-        self.d.coset_lde_peer(coeffs, shard_ptrs, n_loc, rate_bits)
+    def coset_lde_peer(self, coeffs, shard_ptrs, n_loc, rate_bits, first_shard=0):
+        self.d.coset_lde_peer(coeffs, shard_ptrs, n_loc, rate_bits, first_shard)
 
     def merkle_colmajor(self, lde, cap_height, hash_kind, leaves, digests, cap):
         self.d.merkle_colmajor(lde, cap_height, hash_kind, leaves, digests, cap)
@@ -137,7 +137,8 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
             ex = PeerExchange(G, c_loc, n_loc, group)
             sc["peer_exchange"] = ex
         ex.barrier()   # peers are done reading what the previous step put into my buffer
-        engine.coset_lde_peer(coeffs, ex.shard_ptrs, n_loc, rate_bits)
+        # rank g stores to rank g first, then g+1, ...: at any moment the ranks target different peers
+        engine.coset_lde_peer(coeffs, ex.shard_ptrs, n_loc, rate_bits, g)
         ex.barrier()   # every block of my receive buffer has landed
         recv = ex.recv
     else:

@@ -304,3 +304,28 @@ def test_concurrent_callers(G, oracle):
     [t.join() for t in th]
     for t in range(4):
         assert np.array_equal(out[t], oracle.commit(cols[t], 3, 4, t % 2, want_leaves=False)["cap"])
+
+
+@pytest.mark.parametrize("log_n,nshards", [(10, 8), (12, 2), (15, 8), (16, 4)])
+def test_peer_store_lde_equals_sharded_lde_on_one_gpu(G, log_n, nshards):
+    """mp2gpu_dev_coset_lde_peer with all "peer" buffers on this GPU: for every first_shard rotation the shards
+    land exactly where the shard_log layout of mp2gpu_dev_coset_lde puts them (single- and two-pass sizes)."""
+    import torch
+
+    from mapreduce_plonky2_b200 import device as D
+
+    D.bind_current_device()
+    ncols, r = 3, 3
+    n, N = 1 << log_n, 1 << (log_n + r)
+    n_loc = N // nshards
+    coeffs = torch.from_numpy(field_elems(0x9EE7 + log_n, (ncols, n)).view(np.int64)).cuda()
+    want = torch.empty((nshards, ncols, n_loc), dtype=torch.int64, device="cuda")
+    D.coset_lde(coeffs, want, r, nshards.bit_length() - 1)
+    for first in range(nshards):
+        got = torch.zeros((nshards, ncols, n_loc), dtype=torch.int64, device="cuda")
+        ptrs = [got[g].data_ptr() for g in range(nshards)]
+        D.coset_lde_peer(coeffs, ptrs, n_loc, r, first)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), first
+    with pytest.raises(Exception, match="first_shard"):
+        D.coset_lde_peer(coeffs, ptrs, n_loc, r, nshards)
