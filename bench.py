@@ -59,7 +59,7 @@ def parse_args():
                          "aggregation (configs[3])")
     ap.add_argument("--proofs", type=int, default=64, help="trace workload: proofs per GPU per step")
     ap.add_argument("--streams", type=int, default=8, help="trace workload: proofs in flight per GPU")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
                     help="N > 1: peer = LDE kernel stores into the peers' buffers over NVLink; nccl = all_to_all_single")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
