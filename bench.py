@@ -276,6 +276,10 @@ def run_ours(a):
     D.profile_enable(False)
     prof = D.profile_report()
     clocks = sampler.stop() if sampler else None
+    if world > 1 and os.environ.get("MP2_SHARDED_TIMING"):  # diagnostic: per-stage ms of every call, every rank
+        for i, rec in enumerate(S.timing_report(scratch)):
+            print("[timing rank %d call %d] %s" % (rank, i, " ".join("%s=%.2f" % kv for kv in rec.items())),
+                  file=sys.stderr, flush=True)
     ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)

@@ -17,11 +17,39 @@ an oracle-backed stand-in inside ``tests/`` to exercise this file's index logic 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
 import torch
 import torch.distributed as dist
+
+
+class _StageTimer:
+    """Optional per-stage CUDA-event timing of one commit_sharded call (``MP2_SHARDED_TIMING=1``): the marks are
+    appended to ``scratch["timing"]`` as (label, event) lists, one list per call; :func:`timing_report` turns them
+    into milliseconds after a synchronize.  Diagnostic only (round-1 open item: two stalled peer-exchange samples
+    with unchanged kernel times); no effect when the variable is unset."""
+
+    def __init__(self, scratch):
+        self.on = bool(os.environ.get("MP2_SHARDED_TIMING")) and torch.cuda.is_available() and scratch is not None
+        if self.on:
+            self.marks = []
+            scratch.setdefault("timing", []).append(self.marks)
+
+    def mark(self, label):
+        if self.on:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.marks.append((label, ev))
+
+
+def timing_report(scratch) -> list:
+    """[{stage: ms, ...} per recorded call]; call after ``torch.cuda.synchronize()``."""
+    out = []
+    for marks in (scratch or {}).get("timing", []):
+        out.append({"%s->%s" % (a[0], b[0]): a[1].elapsed_time(b[1]) for a, b in zip(marks, marks[1:])})
+    return out
 
 
 class CudaEngine:
@@ -124,6 +152,8 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
             sc[name] = t
         return t
 
+    tm = _StageTimer(scratch)
+    tm.mark("start")
     # 1. per-column work on the local column shard
     coeffs = buf("coeffs", (c_loc, n))
     if from_coeffs:
@@ -136,19 +166,26 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
         if ex is None or ex.shape != (G, c_loc, n_loc):
             ex = PeerExchange(G, c_loc, n_loc, group)
             sc["peer_exchange"] = ex
+        tm.mark("intt")
         ex.barrier()   # peers are done reading what the previous step put into my buffer
+        tm.mark("barrier1")
         # rank g stores to rank g first, then g+1, ...: at any moment the ranks target different peers
         engine.coset_lde_peer(coeffs, ex.shard_ptrs, n_loc, rate_bits, g)
+        tm.mark("lde_peer")
         ex.barrier()   # every block of my receive buffer has landed
+        tm.mark("barrier2")
         recv = ex.recv
     else:
         # 2. LDE written leaf-ordered and blocked by destination rank: send[s] = (c_loc, n_loc) block for rank s
         send = buf("send", (G, c_loc, n_loc))
+        tm.mark("intt")
         engine.coset_lde(coeffs, send, rate_bits, glog)
+        tm.mark("lde")
         # 3. the one exchange of the path
         if G > 1:
             recv = buf("recv", (G, c_loc, n_loc))
             dist.all_to_all_single(recv, send, group=group)
+            tm.mark("all_to_all")
         else:
             recv = send
     # recv[s][j] is column s*c_loc + j restricted to my leaves: a (ncols_total, n_loc) column-major LDE
@@ -158,10 +195,12 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
     digests = buf("digests", (max(ndig_loc, 1), 4))
     cap_local = buf("cap_local", (ncap_loc, 4))
     engine.merkle_colmajor(lde_rows, cap_height - glog, hash_kind, leaves, digests, cap_local)
+    tm.mark("merkle")
     # 5. everyone gets the whole cap
     cap = buf("cap", (1 << cap_height, 4))
     if G > 1:
         dist.all_gather_into_tensor(cap, cap_local, group=group)
     else:
         cap.copy_(cap_local)
+    tm.mark("cap")
     return ShardedBatch(coeffs, leaves, digests[:ndig_loc], cap, g, G)
