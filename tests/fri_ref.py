@@ -83,3 +83,31 @@ def oracle_fri_proof(oracle, coeff_sets, batches, degree_bits, kind, rate_bits=3
         rounds.append({"initial": initial, "steps": steps})
     proof = {"caps": caps, "final_poly": final_poly, "pow_witness": witness, "rounds": rounds}
     return commits, openings, proof
+
+
+def load_fri_golden():
+    """tests/golden/fri_small.json decoded to numpy: list of dicts with oracles [(w, n) arrays], batches
+    [(point (2,), [(oracle_index, polynomial_index)])], alpha (2,), arity_bits, betas (k, 2), final_poly (n, 2),
+    layer_caps [(4, 4)], layer_digests_xor [(4,)], final_coeffs (m, 2)."""
+    import json
+    import os
+
+    from util import GOLDEN_DIR, unhex
+
+    with open(os.path.join(GOLDEN_DIR, "fri_small.json")) as f:
+        raw = json.load(f)["cases"]
+    out = []
+    for c in raw:
+        oracles = [unhex([x for col in o for x in col]).reshape(len(o), -1) for o in c["oracles"]]
+        out.append({
+            "hash_kind": c["hash_kind"], "degree_bits": c["degree_bits"], "rate_bits": c["rate_bits"],
+            "cap_height": c["cap_height"], "oracles": oracles,
+            "batches": [(unhex(z), [tuple(p) for p in polys]) for z, polys in zip(c["points"], c["batches"])],
+            "alpha": unhex(c["alpha"]), "arity_bits": list(c["arity_bits"]),
+            "betas": unhex([x for b in c["betas"] for x in b]).reshape(-1, 2),
+            "final_poly": unhex([x for r in c["final_poly"] for x in r]).reshape(-1, 2),
+            "layer_caps": [unhex([x for h in cap for x in h]).reshape(-1, 4) for cap in c["layer_caps"]],
+            "layer_digests_xor": [unhex(d) for d in c["layer_digests_xor"]],
+            "final_coeffs": unhex([x for r in c["final_coeffs"] for x in r]).reshape(-1, 2),
+        })
+    return out

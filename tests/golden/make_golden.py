@@ -10,6 +10,9 @@
 * ``merkle_small.json`` -- MerkleTree::new outputs incl. the circuit-set shape of
                            recursion-framework/src/universal_verifier_gadget/circuit_set.rs:173-191
                            (4-element digests padded with vec![F::ZERO], cap_height 0), from pyref.
+* ``fri_small.json``    -- prove_openings' final polynomial (pyref.fri_combine: composition, exact division by
+                           X - z, alpha weights -- by definition) and the FRI commit phase over it (layer caps, final
+                           coefficients; pyref.fri_committed_trees: Horner evaluation, explicit fold) for tiny instances.
 * ``config1_caps.json`` -- Merkle caps of the BASELINE config-1 shapes on seeded inputs, frozen from the
                            C oracle (self-golden: regression pin, not an external anchor).
 
@@ -104,6 +107,29 @@ def merkle_small():
     return {"generator": "tests/pyref.py", "cases": cases, "misc": misc}
 
 
+def fri_small():
+    rng = random.Random(0x6D7036)
+    cases = []
+    for kind, degree_bits, widths, arities in ((0, 5, (3, 2), [4]), (1, 6, (2, 3, 1), [4])):
+        n = 1 << degree_bits
+        oracles = [[[rng.randrange(R.P) for _ in range(n)] for _ in range(w)] for w in widths]
+        zeta, gzeta, alpha = ((rng.randrange(R.P), rng.randrange(R.P)) for _ in range(3))
+        polys0 = [(o, p) for o, w in enumerate(widths) for p in range(w)]
+        polys1 = [(len(widths) - 1, 0), (0, 1)]
+        batches = [(zeta, polys0), (gzeta, polys1)]
+        final = R.fri_combine([(z, [oracles[o][p] for o, p in polys]) for z, polys in batches], alpha)
+        betas = [(rng.randrange(R.P), rng.randrange(R.P)) for _ in arities]
+        padded = final + [(0, 0)] * (n * 7)
+        layers, rest = R.fri_committed_trees(padded, arities, betas, 2, kind, 3)
+        cases.append({"hash_kind": kind, "degree_bits": degree_bits, "rate_bits": 3, "cap_height": 2,
+                      "oracles": [hx2(o) for o in oracles], "points": [hx(zeta), hx(gzeta)], "alpha": hx(alpha),
+                      "batches": [polys0, polys1], "arity_bits": arities, "betas": hx2(betas),
+                      "final_poly": hx2(final), "layer_caps": [hx2(l["cap"]) for l in layers],
+                      "layer_digests_xor": [hx([__import__("functools").reduce(lambda a, b: a ^ b, col) for col in zip(*l["digests"])]) if l["digests"] else [] for l in layers],
+                      "final_coeffs": hx2(rest)})
+    return {"generator": "tests/pyref.py (fri_combine, fri_committed_trees: by definition)", "cases": cases}
+
+
 def config1_caps():
     import oracle as O
     out = {"generator": "oracle/mp2_oracle.c (self-golden, regression pin)", "cases": []}
@@ -122,8 +148,11 @@ def config1_caps():
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, fn in (("kats", kats), ("commit_small", commit_small), ("merkle_small", merkle_small),
-                     ("config1_caps", config1_caps)):
+                     ("fri_small", fri_small), ("config1_caps", config1_caps)):
+        if only and name not in only:
+            continue
         with open(os.path.join(HERE, name + ".json"), "w") as f:
             json.dump(fn(), f, indent=0, separators=(",", ":"))
         print("wrote", name)

@@ -310,6 +310,30 @@ def fri_combined_eval(batches, alpha, x):
     return total
 
 
+def fri_combine(batches, alpha):
+    """prove_openings' final polynomial as a list of n extension coefficients, from the definition: for each batch
+    the composition F_i = sum_j alpha^j f_ij, its exact quotient by (X - z_i) (the remainder F_i(z_i) is dropped;
+    one zero coefficient pads the quotient back to n), and the sum of the quotients weighted by alpha^(number of
+    polynomials in the later batches)."""
+    n = len(batches[0][1][0])
+    sizes = [len(polys) for _, polys in batches]
+    total = [(0, 0)] * n
+    for i, (z, polys) in enumerate(batches):
+        comp, pw = [(0, 0)] * n, (1, 0)
+        for f in polys:
+            comp = [((c[0] + v % P * pw[0]) % P, (c[1] + v % P * pw[1]) % P) for c, v in zip(comp, f)]
+            pw = ext_mul(pw, alpha)
+        # long division by (X - z): q_(n-2) = a_(n-1), q_(k-1) = a_k + z q_k
+        q = [(0, 0)] * n
+        carry = (0, 0)
+        for k in range(n - 1, 0, -1):
+            carry = ((comp[k][0] + ext_mul(carry, z)[0]) % P, (comp[k][1] + ext_mul(carry, z)[1]) % P)
+            q[k - 1] = carry
+        weight = ext_pow(alpha, sum(sizes[i + 1:]))
+        total = [((t[0] + ext_mul(x, weight)[0]) % P, (t[1] + ext_mul(x, weight)[1]) % P) for t, x in zip(total, q)]
+    return total
+
+
 def fri_committed_trees(coeffs, arity_bits_list, betas, cap_height, kind=0, rate_bits=3):
     """coeffs: list of ext pairs (zero-padded LDE length).  Every layer is computed from the definition:
     values[i] = P(shift * w^i) by Horner in the extension field; the fold is

@@ -78,3 +78,23 @@ def test_tampered_fri_proofs_are_rejected(oracle):
     bad["pow_witness"] += 1
     with pytest.raises(AssertionError):
         _verify(batches, commits, openings, bad, degree_bits, kind)
+
+
+def test_oracle_equals_fri_golden(oracle):
+    """tests/golden/fri_small.json (pyref, by definition): prove_openings' final polynomial, the layer caps of the
+    commit phase and the remaining coefficients -- the oracle's FFT-based restatement must reproduce them."""
+    cases = fri_ref.load_fri_golden()
+    assert len(cases) == 2
+    for c in cases:
+        final = oracle.fri_combine([(z, [c["oracles"][o][p] for o, p in polys]) for z, polys in c["batches"]], c["alpha"])
+        assert np.array_equal(final, c["final_poly"])
+        n = 1 << c["degree_bits"]
+        padded = np.zeros((n << c["rate_bits"], 2), dtype=np.uint64)
+        padded[:n] = final
+        trees, rest = oracle.fri_committed_trees(padded, oracle.coset_fft_ext(padded, 7), c["arity_bits"], c["betas"],
+                                                 c["cap_height"], c["hash_kind"], c["rate_bits"])
+        assert len(trees) == len(c["layer_caps"])
+        for (leaves, digests, cap), want_cap, want_xor in zip(trees, c["layer_caps"], c["layer_digests_xor"]):
+            assert np.array_equal(cap, want_cap)
+            assert np.array_equal(np.bitwise_xor.reduce(digests, axis=0), want_xor)
+        assert np.array_equal(rest, c["final_coeffs"])

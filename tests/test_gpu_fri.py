@@ -281,3 +281,28 @@ def test_batch_eval_matches_horner(oracle):
                 want = pyref.ext_horner([(int(v), 0) for v in cols[c]], (z[0] % P, z[1] % P))
                 assert tuple(got[pi, c].tolist()) == want
         b.free()
+
+
+def test_gpu_equals_fri_golden():
+    """tests/golden/fri_small.json (computed by definition in tests/pyref.py): the device's prove_openings polynomial,
+    the commit-phase caps / digests and the remaining coefficients."""
+    import fri_ref
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    for c in fri_ref.load_fri_golden():
+        kind = c["hash_kind"]
+        oracles = [G.PolynomialBatch.from_coeffs(list(o), c["rate_bits"], False, 4, hash_kind=kind, keep_on_device=True,
+                                                 fetch_leaves=False) for o in c["oracles"]]
+        ph = G.FriCommitPhase.from_openings(oracles, c["batches"], c["alpha"], c["cap_height"], kind, want_final_poly=True)
+        assert np.array_equal(ph.final_poly, c["final_poly"])
+        for ab, beta, want_cap in zip(c["arity_bits"], c["betas"], c["layer_caps"]):
+            cap = ph.commit_layer(ab)
+            assert np.array_equal(cap.hashes, want_cap)
+            ph.fold(beta)
+        for i, want_xor in enumerate(c["layer_digests_xor"]):
+            assert np.array_equal(np.bitwise_xor.reduce(ph.layer(i).digests, axis=0), want_xor)
+        assert np.array_equal(ph.finish(), c["final_coeffs"])
+        ph.free()
+        for o in oracles:
+            o.free()
