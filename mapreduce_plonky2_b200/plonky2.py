@@ -96,6 +96,17 @@ def hash_pad(x, hash_kind: int = POSEIDON2) -> np.ndarray:
     return hash_no_pad(np.array(x + [1], dtype=np.uint64), hash_kind)
 
 
+def circuit_digest(constants_sigmas_cap, degree_bits: int, hash_kind: int = POSEIDON2, domain_separator=()) -> np.ndarray:
+    """plonky2's ``circuit_digest`` of ``CircuitBuilder::build``: ``hash_no_pad(cap ‖ hash_pad(domain_separator) ‖
+    [degree_bits])`` -- the first consumer of the constants/sigmas commitment's cap, and the formula the reference
+    re-checks in-circuit at recursion-framework/src/universal_verifier_gadget/circuit_set.rs:136-158 (which assumes an
+    empty domain separator, the default here)."""
+    cap = constants_sigmas_cap.hashes if isinstance(constants_sigmas_cap, MerkleCap) else _arr(constants_sigmas_cap)
+    parts = np.concatenate([_arr(cap).reshape(-1), hash_pad(np.array(list(domain_separator), dtype=np.uint64), hash_kind),
+                            np.array([degree_bits], dtype=np.uint64)])
+    return hash_no_pad(parts, hash_kind)
+
+
 def hash_or_noop(x, hash_kind: int = POSEIDON2) -> np.ndarray:
     x = _arr(x).reshape(-1)
     if x.size <= 4:

@@ -20,6 +20,10 @@ def cpu_primitives(monkeypatch, oracle):
             row[:] = oracle.permute(row, hash_kind)
         return st
 
+    def hash_no_pad_batch(inputs, hash_kind=1):
+        return np.stack([oracle.hash_no_pad(np.asarray(row, dtype=np.uint64), hash_kind) for row in inputs])
+
+    monkeypatch.setattr(P2, "hash_no_pad_batch", hash_no_pad_batch)
     monkeypatch.setattr(P2, "permute", permute)
     monkeypatch.setattr(P2, "fri_proof_of_work",
                         lambda state, pos, bits=16, kind=1: oracle.fri_pow(np.array(state, dtype=np.uint64), pos, bits, kind))
@@ -139,3 +143,17 @@ def test_fri_proof_glue_equals_reference_flow(cpu_primitives, kind, degree_bits,
             assert np.array_equal(row, rrow) and np.array_equal(mp.siblings, rsib)
         for st, (rev, rsib) in zip(rnd.steps, rr["steps"]):
             assert np.array_equal(st.evals, rev) and np.array_equal(st.merkle_proof.siblings, rsib)
+
+
+def test_circuit_digest_formula(cpu_primitives):
+    """circuit_digest = hash_no_pad(cap ‖ hash_pad(&[]) ‖ [degree_bits]) -- the native side of
+    recursion-framework/src/universal_verifier_gadget/circuit_set.rs:136-158, against pyref's sponge."""
+    from mapreduce_plonky2_b200 import plonky2 as P2
+
+    cap = field_elems(0xC1C, (16, 4))
+    for kind in (0, 1):
+        want = pyref.hash_no_pad([int(x) for x in cap.reshape(-1)] + list(pyref.hash_pad([], kind)) + [12], kind)
+        assert [int(x) for x in P2.circuit_digest(cap, 12, kind)] == [int(x) for x in want]
+        assert [int(x) for x in P2.circuit_digest(P2.MerkleCap(cap), 12, kind)] == [int(x) for x in want]
+        other = P2.circuit_digest(cap, 13, kind)
+        assert [int(x) for x in other] != [int(x) for x in want]

@@ -329,3 +329,12 @@ def test_peer_store_lde_equals_sharded_lde_on_one_gpu(G, log_n, nshards):
         assert torch.equal(got, want), first
     with pytest.raises(Exception, match="first_shard"):
         D.coset_lde_peer(coeffs, ptrs, n_loc, r, nshards)
+
+
+def test_circuit_digest_on_device(G, oracle):
+    """hash_no_pad(cap ‖ hash_pad(&[]) ‖ [degree_bits]) (circuit_set.rs:136-158) through the device hashers."""
+    cap = field_elems(0xC1C, (16, 4))
+    for kind in (0, 1):
+        parts = np.concatenate([cap.reshape(-1), oracle.hash_pad(np.zeros(0, dtype=np.uint64), kind),
+                                np.array([12], dtype=np.uint64)])
+        assert np.array_equal(G.circuit_digest(cap, 12, kind), oracle.hash_no_pad(parts, kind))
