@@ -247,6 +247,44 @@ def read_merkle_tree(data: bytes, hash_kind: int = POSEIDON2) -> MerkleTree:
     return MerkleTree(leaves, digests, MerkleCap(cap), hash_kind)
 
 
+# plonky2 util/serialization `Write::write_polynomial_batch` (inside CircuitData::to_bytes, which the reference
+# caches parameters with: mp2-common/src/serialization/circuit_data_serialization.rs:74-150):
+#   polynomials.len(); per polynomial: coeffs.len() + canonical u64 LE coefficients; the merkle tree as above;
+#   degree_log, rate_bits as usize; blinding as one byte.   Layout restated from plonky2 0.2.2, unconfirmed (no
+#   Rust toolchain here), like write_merkle_tree.
+def write_polynomial_batch(batch: "PolynomialBatch") -> bytes:
+    import struct
+
+    polys = _arr(batch.polynomials, 2)
+    out = [struct.pack("<Q", polys.shape[0])]
+    for col in polys:
+        out.append(struct.pack("<Q", col.size))
+        out.append(col.astype("<u8").tobytes())
+    out.append(write_merkle_tree(batch.merkle_tree))
+    out.append(struct.pack("<QQB", batch.degree_log, batch.rate_bits, 1 if batch.blinding else 0))
+    return b"".join(out)
+
+
+def read_polynomial_batch(data: bytes, hash_kind: int = POSEIDON2) -> "PolynomialBatch":
+    import struct
+
+    off = 0
+    (npolys,) = struct.unpack_from("<Q", data, off)
+    off += 8
+    cols = []
+    for _ in range(npolys):
+        (ln,) = struct.unpack_from("<Q", data, off)
+        off += 8
+        cols.append(np.frombuffer(data, dtype="<u8", count=ln, offset=off).astype(np.uint64))
+        off += 8 * ln
+    tree = read_merkle_tree(data[off:], hash_kind)
+    off += len(write_merkle_tree(tree))
+    degree_log, rate_bits, blinding = struct.unpack_from("<QQB", data, off)
+    if off + 17 != len(data):
+        raise Mp2GpuError("trailing bytes after the polynomial batch")
+    return PolynomialBatch(np.stack(cols), tree, degree_log, rate_bits, bool(blinding))
+
+
 def verify_merkle_proof_to_cap(leaf_data, leaf_index: int, cap: MerkleCap, proof: MerkleProof,
                                hash_kind: int = POSEIDON2) -> None:
     """plonky2's ``verify_merkle_proof_to_cap`` (native twin of the gadget used at

@@ -83,3 +83,29 @@ def test_merkle_tree_wire_format_round_trip(n, cap):
     assert np.array_equal(back.leaves, leaves) and np.array_equal(back.digests, d)
     assert np.array_equal(back.cap.hashes, c) and back.cap.height() == cap
     assert P2.write_merkle_tree(back) == blob
+
+
+def test_polynomial_batch_wire_format_round_trip():
+    """write_polynomial_batch -> read_polynomial_batch is the identity on an oracle-built batch (host-only code path);
+    the byte count follows plonky2's Write::write_polynomial_batch field by field."""
+    import numpy as np
+
+    import oracle as O
+    from mapreduce_plonky2_b200 import plonky2 as P2
+    from util import field_elems
+
+    ncols, n_log, r, cap = 5, 4, 3, 2
+    n, N = 1 << n_log, 1 << (n_log + r)
+    res = O.commit(field_elems(0xB17E, (ncols, n)), r, cap, 1)
+    tree = P2.MerkleTree(res["leaves"], res["digests"], P2.MerkleCap(res["cap"]), 1)
+    batch = P2.PolynomialBatch(res["coeffs"], tree, n_log, r, False)
+    blob = P2.write_polynomial_batch(batch)
+    tree_bytes = 8 + N * (8 + ncols * 8) + 8 + res["digests"].shape[0] * 32 + 8 + (1 << cap) * 32
+    assert len(blob) == 8 + ncols * (8 + n * 8) + tree_bytes + 8 + 8 + 1
+    back = P2.read_polynomial_batch(blob, 1)
+    assert np.array_equal(back.polynomials, res["coeffs"]) and np.array_equal(back.merkle_tree.leaves, res["leaves"])
+    assert np.array_equal(back.merkle_tree.digests, res["digests"]) and np.array_equal(back.merkle_tree.cap.hashes, res["cap"])
+    assert (back.degree_log, back.rate_bits, back.blinding) == (n_log, r, False)
+    assert P2.write_polynomial_batch(back) == blob
+    with pytest.raises(P2.Mp2GpuError, match="trailing"):
+        P2.read_polynomial_batch(blob + b"\0", 1)
