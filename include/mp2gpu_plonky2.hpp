@@ -237,6 +237,74 @@ struct FriCommitPhase {
   }
 };
 
+// Challenger<F, H> (plonky2 iop/challenger.rs): the overwrite-mode duplex sponge of the Fiat-Shamir transcript.
+// `Permute` is any callable void(uint64_t state[12]); DevicePermute sends the state through mp2gpu_permute_batch
+// (the library has no host hashing path), tests instantiate it with the CPU oracle's permutation.
+template <Hasher H>
+struct DevicePermute {
+  void operator()(uint64_t *state) const { check(mp2gpu_permute_batch(state, 1, (uint32_t)H)); }
+};
+template <typename Permute>
+struct Challenger {
+  static constexpr size_t kWidth = 12, kRate = 8;
+  static constexpr uint64_t kOrder = 0xFFFFFFFF00000001ULL;
+  std::array<F, kWidth> sponge_state{};
+  std::vector<F> input_buffer, output_buffer;
+  Permute permute;
+
+  explicit Challenger(Permute p = Permute()) : permute(p) {}
+  void observe_element(F x) {
+    output_buffer.clear();  // any buffered outputs are now invalid
+    input_buffer.push_back(x >= kOrder ? x - kOrder : x);
+    if (input_buffer.size() == kRate) duplexing();
+  }
+  void observe_elements(const F *xs, size_t n) {
+    for (size_t i = 0; i < n; i++) observe_element(xs[i]);
+  }
+  void observe_extension_element(const Ext &e) { observe_elements(e.data(), 2); }
+  void observe_hash(const HashOut &h) { observe_elements(h.data(), 4); }
+  void observe_cap(const MerkleCap &cap) {
+    for (auto &h : cap.hashes) observe_hash(h);
+  }
+  F get_challenge() {
+    if (!input_buffer.empty() || output_buffer.empty()) duplexing();
+    F c = output_buffer.back();  // challenges are popped from the END of the squeezed rate
+    output_buffer.pop_back();
+    return c;
+  }
+  Ext get_extension_challenge() {
+    F a = get_challenge();
+    return {a, get_challenge()};
+  }
+  void duplexing() {
+    for (size_t i = 0; i < input_buffer.size(); i++) sponge_state[i] = input_buffer[i];
+    input_buffer.clear();
+    permute(sponge_state.data());
+    output_buffer.assign(sponge_state.begin(), sponge_state.begin() + kRate);
+  }
+  // fri_proof_of_work's view of the transcript: the state with the pending inputs written, and where the witness goes
+  std::array<F, kWidth> pow_intermediate_state(size_t *witness_pos) const {
+    std::array<F, kWidth> st = sponge_state;
+    for (size_t i = 0; i < input_buffer.size(); i++) st[i] = input_buffer[i];
+    *witness_pos = input_buffer.size();
+    return st;
+  }
+};
+
+// FriConfig of standard_recursion_config (mp2-common/src/lib.rs:45-47) and FriReductionStrategy::ConstantArityBits
+struct FriConfig {
+  size_t rate_bits = 3, cap_height = 4, proof_of_work_bits = 16, num_query_rounds = 28;
+  size_t arity_bits = 4, final_poly_bits = 5;
+  std::vector<size_t> reduction_arity_bits(size_t degree_bits) const {
+    std::vector<size_t> out;
+    while (degree_bits > final_poly_bits && degree_bits + rate_bits - cap_height > arity_bits) {
+      out.push_back(arity_bits);
+      degree_bits -= arity_bits;
+    }
+    return out;
+  }
+};
+
 // PolynomialBatch::prove_openings(instance, oracles, challenger, fri_params, timing) up to its call of fri_proof:
 // alpha = challenger.get_extension_challenge() is drawn by the caller; the alpha-batched quotient is built from the
 // oracles' device-resident coefficients and stays in HBM as the commit phase's polynomial.
