@@ -142,7 +142,7 @@ static inline uint64_t gl_reduce128_loose(u128 x) {
   uint64_t hh = hi >> 32, hl = hi & GL_EPS;
   uint64_t t0 = lo - hh;
   if (lo < hh) t0 -= GL_EPS;
-  uint64_t t1 = hl * GL_EPS;
+  uint64_t t1 = (hl << 32) - hl;
   uint64_t r = t0 + t1;
   if (r < t0) r += GL_EPS;
   return r;
@@ -153,6 +153,15 @@ static inline uint64_t sbox7_loose(uint64_t x) {
   return gl_mul_loose(x3, x4);
 }
 static inline uint64_t sbox7(uint64_t x) { return orc_gl_canon(sbox7_loose(x)); }
+/* the full-round S-box layer, one multiplication step at a time over all 12 lanes: twelve independent
+ * products per step instead of twelve serial x -> x^7 chains (the out-of-order core overlaps them) */
+static inline void sbox7_layer_loose(uint64_t s[12]) {
+  uint64_t x2[12], x3[12], x4[12];
+  for (int i = 0; i < 12; i++) x2[i] = gl_mul_loose(s[i], s[i]);
+  for (int i = 0; i < 12; i++) x4[i] = gl_mul_loose(x2[i], x2[i]);
+  for (int i = 0; i < 12; i++) x3[i] = gl_mul_loose(s[i], x2[i]);
+  for (int i = 0; i < 12; i++) s[i] = gl_mul_loose(x3[i], x4[i]);
+}
 
 /* out[r] = sum_i state[(i+r)%12] * CIRC[i] + state[r] * DIAG[r] + rc[r]   (mds_row_shf) */
 static inline void pos_mds_rc(uint64_t s[12], const uint64_t *rc) {
@@ -176,7 +185,7 @@ void orc_poseidon_permute(uint64_t s[12]) {
   for (int i = 0; i < 12; i++) s[i] = gl_add(orc_gl_canon(s[i]), POS_RC[i]);
   for (int round = 0; round < 30; round++) {
     if (round < 4 || round >= 26) {
-      for (int i = 0; i < 12; i++) s[i] = sbox7_loose(s[i]);
+      sbox7_layer_loose(s);
     } else {
       s[0] = sbox7_loose(s[0]);
     }
@@ -245,47 +254,61 @@ static void p2_init(void) {
   }
 }
 
-/* M_E: M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] on each 4-lane chunk, then add column sums */
-static void p2_external(uint64_t s[12]) {
+/* M_E: M4 = [[5,7,1,3],[4,6,1,1],[1,3,5,7],[1,1,4,6]] on each 4-lane chunk, then add column sums.  Row sums are
+ * <= 64, so the network runs on the 32-bit halves of the (loose) state in plain 64-bit adds and every lane is
+ * recombined and reduced once. */
+static inline void p2_m4_half(uint64_t x[12]) {
   for (int c = 0; c < 12; c += 4) {
-    uint64_t x0 = s[c], x1 = s[c + 1], x2 = s[c + 2], x3 = s[c + 3];
-    uint64_t t0 = gl_add(x0, x1), t1 = gl_add(x2, x3);
-    uint64_t t2 = gl_add(gl_add(x1, x1), t1), t3 = gl_add(gl_add(x3, x3), t0);
-    uint64_t t1_4 = gl_add(t1, t1); t1_4 = gl_add(t1_4, t1_4);
-    uint64_t t0_4 = gl_add(t0, t0); t0_4 = gl_add(t0_4, t0_4);
-    uint64_t t4 = gl_add(t1_4, t3), t5 = gl_add(t0_4, t2);
-    s[c] = gl_add(t3, t5);
-    s[c + 1] = t5;
-    s[c + 2] = gl_add(t2, t4);
-    s[c + 3] = t4;
+    uint64_t x0 = x[c], x1 = x[c + 1], x2 = x[c + 2], x3 = x[c + 3];
+    uint64_t t0 = x0 + x1, t1 = x2 + x3;
+    uint64_t t2 = 2 * x1 + t1, t3 = 2 * x3 + t0;
+    uint64_t t4 = 4 * t1 + t3, t5 = 4 * t0 + t2;
+    x[c] = t3 + t5;
+    x[c + 1] = t5;
+    x[c + 2] = t2 + t4;
+    x[c + 3] = t4;
   }
   uint64_t col[4];
-  for (int l = 0; l < 4; l++) col[l] = gl_add(gl_add(s[l], s[4 + l]), s[8 + l]);
-  for (int i = 0; i < 12; i++) s[i] = gl_add(s[i], col[i % 4]);
+  for (int l = 0; l < 4; l++) col[l] = x[l] + x[4 + l] + x[8 + l];
+  for (int i = 0; i < 12; i++) x[i] += col[i % 4];
 }
-/* M_I: out[i] = state[i] * mu_i + sum(state) */
+static void p2_external(uint64_t s[12]) {
+  uint64_t lo[12], hi[12];
+  for (int i = 0; i < 12; i++) {
+    lo[i] = s[i] & GL_EPS;
+    hi[i] = s[i] >> 32;
+  }
+  p2_m4_half(lo);
+  p2_m4_half(hi);
+  for (int i = 0; i < 12; i++) s[i] = gl_reduce128_loose((u128)lo[i] + ((u128)hi[i] << 32));
+}
+/* M_I: out[i] = state[i] * mu_i + sum(state); the sum rides on the 128-bit product */
 static void p2_internal(uint64_t s[12]) {
-  uint64_t sum = 0;
-  for (int i = 0; i < 12; i++) sum = gl_add(sum, s[i]);
-  for (int i = 0; i < 12; i++) s[i] = gl_add(gl_mul(s[i], P2_DIAG[i]), sum);
+  u128 acc = 0;
+  for (int i = 0; i < 12; i++) acc += s[i];
+  const uint64_t sum = gl_reduce128_loose(acc);
+  for (int i = 0; i < 12; i++) s[i] = gl_reduce128_loose((u128)s[i] * P2_DIAG[i] + sum);
 }
+/* loose arithmetic throughout (values in [0, 2^64)), canonicalised once at the end -- as in orc_poseidon_permute */
 void orc_poseidon2_permute(uint64_t s[12]) {
   p2_init();
-  for (int i = 0; i < 12; i++) s[i] = orc_gl_canon(s[i]);
   const uint64_t *rc = P2_RC;
   p2_external(s);
   for (int r = 0; r < 4; r++) {
-    for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], *rc++));
+    for (int i = 0; i < 12; i++) s[i] = gl_reduce128_loose((u128)s[i] + *rc++);
+    sbox7_layer_loose(s);
     p2_external(s);
   }
   for (int r = 0; r < 22; r++) {
-    s[0] = sbox7(gl_add(s[0], *rc++));
+    s[0] = sbox7_loose(gl_reduce128_loose((u128)s[0] + *rc++));
     p2_internal(s);
   }
   for (int r = 0; r < 4; r++) {
-    for (int i = 0; i < 12; i++) s[i] = sbox7(gl_add(s[i], *rc++));
+    for (int i = 0; i < 12; i++) s[i] = gl_reduce128_loose((u128)s[i] + *rc++);
+    sbox7_layer_loose(s);
     p2_external(s);
   }
+  for (int i = 0; i < 12; i++) s[i] = orc_gl_canon(s[i]);
 }
 
 void orc_permute(uint32_t kind, uint64_t s[12]) {
