@@ -63,12 +63,27 @@ def parse_args():
                     help="N > 1: peer = LDE kernel stores into the peers' buffers over NVLink; nccl = all_to_all_single")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-map-stage", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
+    ap.add_argument("--map-proofs", type=int, default=32, help="map_stage sub-record: proofs per GPU per step")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "wide batch: 2^%d rows x %d columns coset LDE rate_bits=%d + %s Merkle tree cap_height=%d (from_values)" % (
-        a.n_log, a.ncols, a.rate_bits, "Poseidon" if a.hash == "poseidon" else "Poseidon2", a.cap_height)
+    label = "wide batch" if (a.n_log, a.ncols) == (20, 256) else "config 1 batch" if (a.n_log, a.ncols) == (14, 135) \
+        else "polynomial batch"
+    return "%s: 2^%d rows x %d columns coset LDE rate_bits=%d + %s Merkle tree cap_height=%d (from_values)" % (
+        label, a.n_log, a.ncols, a.rate_bits, "Poseidon" if a.hash == "poseidon" else "Poseidon2", a.cap_height)
+
+
+def global_columns(torch, a, c0, count, n):
+    """Columns [c0, c0 + count) of the synthetic global batch, on the current CUDA device."""
+    gen = torch.Generator(device="cuda")
+    out = torch.empty((count, n), dtype=torch.int64, device="cuda")
+    for j in range(count):
+        gen.manual_seed((0x6D7033 << 20) + c0 + j)
+        out[j] = torch.randint(0, 1 << 62, (n,), dtype=torch.int64, device="cuda", generator=gen)
+    return out
 
 
 def perms_per_commit(ncols, N, cap_height):
@@ -214,10 +229,10 @@ def run_ours(a):
     elems = a.ncols * N
     launches0 = G.launch_count()
 
-    # synthetic inputs, resident in HBM before the timed region (field elements < 2^62 < p)
-    gen = torch.Generator(device="cuda")
-    gen.manual_seed(0x6D7033 + rank)
-    cols = torch.randint(0, 1 << 62, (c_loc, n), dtype=torch.int64, device="cuda", generator=gen)
+    # synthetic inputs, resident in HBM before the timed region (field elements < 2^62 < p).  Column j of the
+    # GLOBAL batch is seeded by j alone, so every N commits the same 2^n_log x ncols batch: cap_xor must be
+    # identical at N = 1, 2, 4, 8, and rank 0 can rebuild the whole batch for the single-GPU cross-check below.
+    cols = global_columns(torch, a, rank * c_loc, c_loc, n)
     engine = S.CudaEngine()
     scratch = {}
     exchange_note = None
@@ -357,6 +372,16 @@ def run_ours(a):
             line["config"]["exchange_note"] = exchange_note
         line.update(roof)
 
+    # ---- self-verification (outside every timed region) ----
+    parity = parity_check(a, torch, D, S, G, world, rank, kind, res, cap_host)
+    if rank == 0:
+        line["parity_check"] = parity
+    # ---- the second half of the metric: map-stage proofs/s with independent replicas at this N ----
+    if not a.no_map_stage:
+        ms = measure_map_stage(a, torch, dist, G, world, rank)
+        if rank == 0:
+            line["map_stage"] = ms
+    del res
     # ---- e2e: host buffers, copies inside the timed region ----
     if not a.no_e2e:
         e2e = run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bufs)
@@ -374,6 +399,95 @@ def run_ours(a):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_check(a, torch, D, S, G, world, rank, kind, res, cap_host):
+    """N > 1: rank 0 rebuilds the WHOLE batch (same per-column seeds), commits it on its own GPU with the
+    single-GPU path and compares cap, its digest slice and its leaf rows with what the sharded run produced.
+    N = 1: the commitment of a 2^12-row slice of the same columns is compared with the CPU oracle (bit-exact)."""
+    if a.no_parity_check:
+        return {"skipped": True}
+    n, N = 1 << a.n_log, (1 << a.n_log) << a.rate_bits
+    out = {}
+    if world > 1:
+        if rank == 0:
+            full = global_columns(torch, a, 0, a.ncols, n)
+            bufs = D.CommitBuffers(a.ncols, a.n_log, a.rate_bits, a.cap_height, True)
+            D.commit_resident(full, bufs, kind, False)
+            torch.cuda.synchronize()
+            nd = res.digests.shape[0]
+            out = {"cap_equals_single_gpu": bool(torch.equal(bufs.cap, res.cap)),
+                   "rank0_digests_equal_single_gpu": bool(torch.equal(bufs.digests[:nd], res.digests)),
+                   "rank0_leaves_equal_single_gpu": bool(torch.equal(bufs.leaves[:N // world], res.leaves)),
+                   "how": "rank 0 re-generated all %d columns, ran one single-GPU mp2gpu_dev_commit and compared" % a.ncols}
+            del full, bufs
+            torch.cuda.empty_cache()
+        return out
+    # N = 1: oracle cross-check on a slice small enough for the CPU (first 2^12 rows of every column)
+    import oracle as O
+
+    O.build()
+    s_log = min(12, a.n_log)
+    cols = global_columns(torch, a, 0, a.ncols, n)[:, :1 << s_log].contiguous()
+    bufs = D.CommitBuffers(a.ncols, s_log, a.rate_bits, a.cap_height, True)
+    D.commit_resident(cols, bufs, kind, False)
+    torch.cuda.synchronize()
+    ref = O.commit(cols.cpu().numpy().view(np.uint64), a.rate_bits, a.cap_height, kind, False, nthreads=host_threads(),
+                   want_leaves=True)
+    out = {"sample_rows_log": s_log,
+           "cap_equals_oracle": bool(np.array_equal(bufs.cap.cpu().numpy().view(np.uint64), ref["cap"])),
+           "digests_equal_oracle": bool(np.array_equal(bufs.digests.cpu().numpy().view(np.uint64), ref["digests"])),
+           "leaves_equal_oracle": bool(np.array_equal(bufs.leaves.cpu().numpy().view(np.uint64), ref["leaves"])),
+           "how": "first 2^%d rows of the bench's own columns committed on the GPU and by oracle/ (CPU restatement)" % s_log}
+    return out
+
+
+def measure_map_stage(a, torch, dist, G, world, rank):
+    """BASELINE.json's second metric, 'mp2 leaf proofs/s at 1/2/4/8 B200': independent proof traces, one replica
+    set per GPU, no collective (SURVEY.md 8(e) map stage; work unit = one opaque proof per task,
+    mp2-v1/src/api.rs:154-165).  Trace replay with ASSUMED degrees; Poseidon2 = the reference's
+    default hasher (mp2-common/src/lib.rs:37-40)."""
+    from mapreduce_plonky2_b200 import trace as T
+    from mapreduce_plonky2_b200 import device as D
+
+    streams = 8
+    runner = T.TraceRunner(T.LEAF_PROOF_DEGREES, 1, streams)
+    for _ in range(2):
+        runner.run(streams)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 2
+    l0 = G.launch_count()
+    e0.record()
+    for _ in range(steps):
+        runner.run(a.map_proofs)
+        for st in runner.streams:
+            torch.cuda.current_stream().wait_stream(st)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / steps
+    launches = G.launch_count() - l0
+    out = None
+    if rank == 0:
+        ip = D.int_pipe_peak()
+        perms = runner.perms_per_proof
+        mads = perms * a.map_proofs * PERM_MADS / (ms_step * 1e-3) / 1e12
+        out = {"metric": "mp2 leaf proofs/s (commitment + FRI-tree trace)", "value": world * a.map_proofs / (ms_step * 1e-3),
+               "unit": "proofs/s", "n_gpus": world, "proofs_per_gpu_per_step": a.map_proofs, "steps": steps,
+               "ms_per_step": ms_step, "scaling": "weak", "parallelism": "replicas only, no collective",
+               "hash": "poseidon2", "degrees": "2^14 + 2^13 + 2^12 (ASSUMED: trace replay, degrees assumed)",
+               "includes": T.TRACE_INCLUDES, "perms_per_proof": perms,
+               "lde_elems_per_proof": runner.lde_elems_per_proof, "gpu_launches": int(launches),
+               "int_pipe_frac": (mads / ip["t_imad_per_s"]) if ip["t_imad_per_s"] else None,
+               "note": "upper bound on prover throughput: witness generation and quotient evaluation are host-side"}
+    del runner
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bufs):
@@ -436,14 +550,14 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         cap_h = torch.empty((ncap, 4), dtype=torch.int64, pin_memory=True)
         cols_d = torch.empty((c_loc, n), dtype=torch.int64, device="cuda")
 
+        host_out = S.HostOutputs(coeffs_h, leaves_h, dig_h, cap_h, torch.cuda.Stream())
+
         def call():
+            # upload on the compute stream, then the sharded commitment with its outputs streamed back to the
+            # pinned buffers under the compute (coefficients under the LDE, leaf blocks under the hashing)
             cols_d.copy_(cols_h, non_blocking=True)
-            r = S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
-                                 exchange=a.exchange)
-            coeffs_h.copy_(r.coeffs, non_blocking=True)
-            leaves_h.copy_(r.leaves, non_blocking=True)
-            dig_h.copy_(r.digests, non_blocking=True)
-            cap_h.copy_(r.cap, non_blocking=True)
+            S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
+                             exchange=a.exchange, host_out=host_out)
             torch.cuda.synchronize()
 
         call()
@@ -456,7 +570,7 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        api = "sharded.commit_sharded with pinned host shards (H2D + D2H per rank)"
+        api = "sharded.commit_sharded(host_out=...) with pinned host shards (H2D + D2H per rank, D2H overlapped with hashing)"
     elems = a.ncols * N
     out = {"value": elems / dt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": dt * 1e3, "steps": steps, "api": api,
@@ -473,15 +587,22 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
 # proof-trace replay (map stage): independent proofs, one GPU each, no collective
 # ------------------------------------------------------------------------------------------------
 def measured_traffic(a, world):
-    """DRAM bytes per launch from the committed ncu captures (profiles/traffic.json), for the shapes they cover."""
+    """DRAM bytes per launch for the shapes the committed ncu captures cover (profiles/traffic.json).  These are
+    STATIC figures -- taken from an `ncu --set full` capture, not from this run (bench.py never runs under a
+    profiler) -- so the source string carries the capture file and the commit of the kernels it profiled."""
     if world != 1:
         return {}
     key = "2^%dx%d r%d %s" % (a.n_log, a.ncols, a.rate_bits, "poseidon2" if a.hash in ("poseidon2", 1) else "poseidon")
     try:
         with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic.json")) as f:
-            return json.load(f).get(key, {})
+            t = json.load(f).get(key, {})
     except (OSError, ValueError):
         return {}
+    if t:
+        t = dict(t)
+        t["source"] = "static: ncu capture %s (kernels at commit %s), not measured in this run" % (
+            t.get("source"), t.get("commit", "unknown"))
+    return t
 
 
 def cpu_trace_time(kind, threads, degrees):

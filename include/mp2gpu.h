@@ -210,6 +210,15 @@ const char *mp2gpu_dev_coset_lde_peer(const uint64_t *coeffs, size_t in_stride,
                                       uint64_t *const *shard_bases, size_t lde_stride, size_t ncols,
                                       uint32_t n_log, uint32_t rate_bits, uint32_t shard_log,
                                       uint32_t first_shard, void *stream);
+/* The two halves of mp2gpu_dev_merkle_colmajor, for callers that overlap the hashing of one leaf range with
+ * the device->host copy of the previous one: leaf digests (and optional row-major rows) of leaves
+ * [leaf_begin, leaf_end) only; then the inner levels + cap once every leaf has been hashed. */
+const char *mp2gpu_dev_merkle_colmajor_leaves(const uint64_t *lde, size_t lde_stride, size_t ncols, size_t nleaves,
+                                              uint32_t cap_height, uint32_t hash_kind, size_t leaf_begin,
+                                              size_t leaf_end, uint64_t *leaves_out, uint64_t *digests_out,
+                                              uint64_t *cap_out, void *stream);
+const char *mp2gpu_dev_merkle_levels(size_t nleaves, uint32_t cap_height, uint32_t hash_kind, uint64_t *digests,
+                                     uint64_t *cap, void *stream);
 /* Leaf-ordered column-major LDE (column c at lde + c*lde_stride, nleaves elements) -> optional
  * row-major leaves (nleaves x ncols), digests and cap of a tree with `nleaves` leaves.  A rank of a
  * G-way row-sharded batch passes nleaves = N/G and cap_height - log2(G): its digests/cap are the
@@ -237,6 +246,27 @@ const char *mp2gpu_dev_canonicalize(const uint64_t *in, uint64_t *out, size_t co
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t mp2gpu_launch_count(void);
 
+/* ---- one wide batch over several GPUs of ONE process --------------------
+ * The multi-GPU form of PolynomialBatch::from_values / from_coeffs for a prover process that owns G devices
+ * (the reference runs one prover process per machine: mp2-v1/src/api.rs:154-165 hands it opaque tasks).
+ * mp2gpu_comm_init binds G = 2^k devices (G <= 2^cap_height at commit time), enables peer access between
+ * every pair and creates one worker context (streams, receive buffer) per device.
+ * mp2gpu_commit_from_values_sharded then runs, with one host thread per device:
+ *     columns [g*c/G, (g+1)*c/G) -> upload -> iNTT -> coset LDE whose stores go straight into the owners' HBM
+ *     over NVLink (leaf L belongs to device L / (N/G); no separate all-to-all) -> barrier -> leaf hashing of
+ *     rows [g*N/G, (g+1)*N/G) in blocks, each block copied to the host while the next is hashed ->
+ *     the device's 2^cap/G subtrees -> its slice of digests / cap.
+ * Arguments and outputs are exactly those of mp2gpu_commit_from_values (host buffers, global layouts:
+ * coeffs_out[c], leaves_out N x ncols row-major, digests_out in plonky2's layout, cap_out); any of
+ * coeffs_out / leaves_out / digests_out may be NULL.  ncols must be a multiple of G. */
+typedef struct mp2gpu_comm mp2gpu_comm;
+const char *mp2gpu_comm_init(int ndev, const int *devs, mp2gpu_comm **comm_out);
+void mp2gpu_comm_free(mp2gpu_comm *comm);
+const char *mp2gpu_commit_from_values_sharded(mp2gpu_comm *comm, const uint64_t *const *cols, size_t ncols,
+                                              uint32_t n_log, uint32_t rate_bits, uint32_t cap_height,
+                                              uint32_t hash_kind, int from_coeffs, uint64_t *const *coeffs_out,
+                                              uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
 /* While enabled, every kernel launch is bracketed by CUDA events on its own stream. */
 const char *mp2gpu_profile_enable(int on);
@@ -247,6 +277,16 @@ const char *mp2gpu_profile_report(char *buf, size_t buf_len);
  * thread-instructions per clock per SM, SM clock held during the probe (MHz), and T IMAD/s. */
 const char *mp2gpu_debug_int_pipe_peak(double *imad_per_clk_per_sm, double *sm_clock_mhz,
                                        double *t_imad_per_s);
+
+/* Device self-test of the Goldilocks primitives (add, add-canonical, sub, mul, sqr, mul-add, reduce128, x^7,
+ * the three shift twiddles -- in that order) against 128-bit arithmetic by definition, over all pairs of
+ * 48 corner values around 0 / 2^32 / 2^63 / p / 2^64 and 976 pseudo-random ones.  mismatches_out[i] = number
+ * of wrong results of test i (ntests >= 11).  Replaces plonky2_field's goldilocks_field unit tests for the
+ * GPU arithmetic. */
+const char *mp2gpu_debug_field_selftest(uint64_t *mismatches_out, size_t ntests);
+/* Register-only throughput of the two arithmetic inner loops, thread-level operations per (nominal) clock per
+ * SM: out[0] = x^7 S-boxes, out[1] = radix-8 butterfly elements (each butterfly + 7 twiddle multiplications). */
+const char *mp2gpu_debug_field_probe(double *ops_per_clk_per_sm_out);
 
 #ifdef __cplusplus
 }

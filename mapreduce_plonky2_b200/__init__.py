@@ -6,7 +6,7 @@ The package holds only what the hot path needs: ``csrc/`` (hand-written CUDA ker
 (device-pointer stages for resident data) and ``sharded.py`` (multi-GPU driver).
 """
 from ._lib import LIB_PATH, Mp2GpuError  # noqa: F401
-from .plonky2 import (POSEIDON, POSEIDON2, FriCommitPhase, fri_committed_trees, fri_proof_of_work, MerkleCap, MerkleProof, MerkleTree, PolynomialBatch,  # noqa: F401
+from .plonky2 import (POSEIDON, POSEIDON2, FriCommitPhase, fri_committed_trees, fri_proof_of_work, Communicator, MerkleCap, MerkleProof, MerkleTree, PolynomialBatch,  # noqa: F401
                       circuit_digest, device_count, hash_no_pad, hash_no_pad_batch, hash_or_noop, hash_pad, init, launch_count,
                       permute, reverse_bits, two_to_one, two_to_one_batch, verify_merkle_proof_to_cap, read_merkle_tree, write_merkle_tree,
                       read_polynomial_batch, write_polynomial_batch)

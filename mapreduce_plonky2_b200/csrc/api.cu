@@ -12,8 +12,6 @@
 namespace mp2 {
 std::atomic<uint64_t> g_launches{0};
 
-namespace {
-
 // Per calling thread: the device chosen with mp2gpu_init and one (compute, copy) stream pair per device the
 // thread has touched -- a prover thread that also reads a batch living on another device keeps both pairs.
 struct DevStreams {
@@ -25,10 +23,10 @@ struct ThreadCtx {
   int device = 0;
   std::vector<DevStreams> per_device;
 };
-thread_local ThreadCtx t_ctx;
+static thread_local ThreadCtx t_ctx;
 
 // Binds the calling thread to its device and returns its private stream (and, optionally, its copy stream).
-Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr, cudaStream_t *up_out = nullptr) {
+Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out, cudaStream_t *up_out) {
   ThreadCtx &c = t_ctx;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -63,15 +61,15 @@ Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr, cudaStrea
 }
 
 // Runs the rest of the scope on the device a handle lives on, then gives the thread its own device back.
-struct DeviceScope {
-  int saved;
-  explicit DeviceScope(int device) : saved(t_ctx.device) { t_ctx.device = device; }
-  ~DeviceScope() {
-    t_ctx.device = saved;
-    cudaSetDevice(saved);
-  }
-};
+DeviceScope::DeviceScope(int device) : saved(t_ctx.device) { t_ctx.device = device; }
+DeviceScope::~DeviceScope() {
+  t_ctx.device = saved;
+  cudaSetDevice(saved);
+}
+int ctx_device() { return t_ctx.device; }
 
+
+namespace {
 Status pick_stream(void *user, cudaStream_t *out) {
   cudaStream_t own;
   MP2_TRY(ctx_stream(&own));  // also validates the device
@@ -85,6 +83,8 @@ const char *to_c(const Status &s) {
   if (p) memcpy(p, s.c_str(), s.size() + 1);
   return p;
 }
+
+}  // namespace
 
 // Column-wise host<->device copies, merged over runs of columns that are adjacent in host memory (one
 // transfer for a contiguous matrix; one per column for separately allocated Vecs -- each cudaMemcpyAsync
@@ -123,6 +123,7 @@ Status check_commit_args(size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height,
   return "";
 }
 
+namespace {
 Status dev_commit(const u64 *cols, size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind,
                   int from_coeffs, u64 *coeffs, u64 *lde, u64 *leaves, u64 *digests, u64 *cap, cudaStream_t st) {
   MP2_TRY(check_commit_args(ncols, n_log, rate_bits, cap_height, hash_kind));
@@ -137,10 +138,7 @@ Status dev_commit(const u64 *cols, size_t ncols, u32 n_log, u32 rate_bits, u32 c
 }  // namespace
 }  // namespace mp2
 
-using namespace mp2;
-
-namespace {
-
+namespace mp2 {
 Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height,
                    u32 hash_kind, int from_coeffs, uint64_t *const *coeffs_out, uint64_t *leaves_out,
                    uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **handle_out) {
@@ -249,6 +247,12 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
   }
   return "";
 }
+
+}  // namespace mp2
+
+using namespace mp2;
+
+namespace {
 
 Status merkle_prove_indices(size_t nleaves, u32 cap_height, size_t leaf_index, std::vector<size_t> *idx) {
   int lg = log2_exact(nleaves);
@@ -647,6 +651,27 @@ const char *mp2gpu_dev_merkle_colmajor(const uint64_t *lde, size_t lde_stride, s
     MP2_TRY(pick_stream(stream, &st));
     return merkle_colmajor((const u64 *)lde, lde_stride, ncols, nleaves, cap_height, hash_kind, (u64 *)leaves_out,
                            (u64 *)digests_out, (u64 *)cap_out, st);
+  });
+}
+
+const char *mp2gpu_dev_merkle_colmajor_leaves(const uint64_t *lde, size_t lde_stride, size_t ncols, size_t nleaves,
+                                              uint32_t cap_height, uint32_t hash_kind, size_t leaf_begin,
+                                              size_t leaf_end, uint64_t *leaves_out, uint64_t *digests_out,
+                                              uint64_t *cap_out, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    return merkle_colmajor_leaves((const u64 *)lde, lde_stride, ncols, nleaves, cap_height, hash_kind, leaf_begin,
+                                  leaf_end, (u64 *)leaves_out, (u64 *)digests_out, (u64 *)cap_out, st);
+  });
+}
+
+const char *mp2gpu_dev_merkle_levels(size_t nleaves, uint32_t cap_height, uint32_t hash_kind, uint64_t *digests,
+                                     uint64_t *cap, void *stream) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(pick_stream(stream, &st));
+    return merkle_levels(nleaves, cap_height, hash_kind, (u64 *)digests, (u64 *)cap, st);
   });
 }
 

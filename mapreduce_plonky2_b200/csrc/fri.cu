@@ -320,6 +320,7 @@ using namespace mp2;
 // Device-resident state of one fri_committed_trees loop.
 struct mp2gpu_fri {
   int device;
+  cudaStream_t owner_stream;  // stream the stream-ordered buffers below were allocated on (and are freed on)
   u32 n_log;       // log2 of the current (non-padded) coefficient count
   u32 rate_bits, cap_height, hash_kind;
   u64 shift;       // coset shift of the current layer: 7^(prod of arities so far)
@@ -340,10 +341,17 @@ const char *dup_c(const Status &s) {
   if (p) memcpy(p, s.c_str(), s.size() + 1);
   return p;
 }
-Status use_device(const mp2gpu_fri *f, cudaStream_t *st) {
-  if (!f) return "null fri handle";
-  MP2_CUDA(cudaSetDevice(f->device));
-  *st = cudaStreamPerThread;
+// Every entry point runs inside a DeviceScope for the handle's device (the caller's device binding -- the
+// library's and CUDA's -- is restored on return) and on the calling thread's private stream for that device,
+// exactly like the batch entry points of api.cu.
+#define FRI_ON_DEVICE(f, st)                  \
+  if (!(f)) return "null fri handle";         \
+  DeviceScope _scope((f)->device);            \
+  cudaStream_t st;                            \
+  MP2_TRY(ctx_stream(&st))
+// stream-ordered allocation that the handle keeps (released by mp2gpu_fri_free / the next fold)
+Status fri_alloc(u64 **p, size_t elems, cudaStream_t st) {
+  MP2_CUDA(cudaMallocAsync(p, sizeof(u64) * (elems ? elems : 1), st));
   return "";
 }
 template <typename F>
@@ -360,14 +368,13 @@ struct FriDeleter {
   void operator()(mp2gpu_fri *f) const { mp2gpu_fri_free(f); }
 };
 typedef std::unique_ptr<mp2gpu_fri, FriDeleter> FriPtr;
-// device < 0: the calling thread's current device
-Status new_fri(u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind, int device, FriPtr *out, cudaStream_t *st) {
+// must be called inside a DeviceScope for `device`; st = the calling thread's stream on it
+Status new_fri(u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind, int device, FriPtr *out, cudaStream_t st) {
   if (hash_kind > 1) return "unknown hash_kind " + std::to_string(hash_kind);
   if (n_log + rate_bits > 32) return "degree_log + rate_bits exceeds two-adicity 32";
-  cudaError_t e = device < 0 ? cudaGetDevice(&device) : cudaSetDevice(device);
-  if (e != cudaSuccess) return std::string("no usable CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e);
   FriPtr f(new mp2gpu_fri());
   f->device = device;
+  f->owner_stream = st;
   f->n_log = n_log;
   f->rate_bits = rate_bits;
   f->cap_height = cap_height;
@@ -376,8 +383,7 @@ Status new_fri(u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind, int devi
   f->last_arity_bits = 0;
   f->committed = false;
   f->coeffs = nullptr;
-  MP2_CUDA(cudaMalloc(&f->coeffs, sizeof(u64) * 2 * ((size_t)1 << n_log)));
-  *st = cudaStreamPerThread;
+  MP2_TRY(fri_alloc(&f->coeffs, 2 * ((size_t)1 << n_log), st));
   *out = std::move(f);
   return "";
 }
@@ -390,8 +396,10 @@ const char *mp2gpu_fri_begin(const uint64_t *coeffs_ext, uint32_t n_log, uint32_
   return guard([&]() -> Status {
     if (!coeffs_ext || !out) return "null coeffs / out";
     FriPtr f;
+    DeviceScope scope(ctx_device());  // the device this thread chose with mp2gpu_init
     cudaStream_t st;
-    MP2_TRY(new_fri(n_log, rate_bits, cap_height, hash_kind, -1, &f, &st));
+    MP2_TRY(ctx_stream(&st));
+    MP2_TRY(new_fri(n_log, rate_bits, cap_height, hash_kind, ctx_device(), &f, st));
     const size_t n = (size_t)1 << n_log;
     DevBuf tmp;
     MP2_TRY(tmp.alloc(2 * n, st));
@@ -408,8 +416,9 @@ const char *mp2gpu_batch_eval(const mp2gpu_batch *b, const uint64_t *points, siz
     if (!b) return "null batch handle";
     if (npoints && (!points || !out)) return "null points / out";
     if (!npoints) return "";
-    MP2_CUDA(cudaSetDevice(b->device));
-    cudaStream_t st = cudaStreamPerThread;
+    DeviceScope scope(b->device);
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
     DevBuf d_out;
     MP2_TRY(d_out.alloc(2 * npoints * b->ncols, st));
     MP2_TRY(fri_eval_polys(b->coeffs, (size_t)1 << b->n_log, b->ncols, (size_t)1 << b->n_log, (const u64 *)points, npoints,
@@ -460,8 +469,10 @@ const char *mp2gpu_fri_begin_openings(const mp2gpu_batch *const *oracles, size_t
       cur = hx_mul(cur, al);
     }
     FriPtr f;
+    DeviceScope scope(oracles[0]->device);
     cudaStream_t st;
-    MP2_TRY(new_fri(n_log, oracles[0]->rate_bits, cap_height, hash_kind, oracles[0]->device, &f, &st));
+    MP2_TRY(ctx_stream(&st));
+    MP2_TRY(new_fri(n_log, oracles[0]->rate_bits, cap_height, hash_kind, oracles[0]->device, &f, st));
     DevBuf d_ptrs, d_pw, comp;
     MP2_TRY(d_ptrs.alloc(total, st));
     MP2_TRY(d_pw.alloc(2 * max_count, st));
@@ -492,9 +503,9 @@ const char *mp2gpu_fri_begin_openings(const mp2gpu_batch *const *oracles, size_t
 
 const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t *cap_out) {
   return guard([&]() -> Status {
-    cudaStream_t st;
-    MP2_TRY(use_device(f, &st));
+    FRI_ON_DEVICE(f, st);
     if (!cap_out) return "null cap_out";
+    if (f->committed) return "fri_commit_layer called twice without a fold in between";
     const u32 N_log = f->n_log + f->rate_bits;
     if (arity_bits == 0 || arity_bits > N_log) return "bad arity_bits";
     if (f->n_log < arity_bits) return "polynomial shorter than the arity";
@@ -514,9 +525,9 @@ const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t
       MP2_TRY(vals.alloc(2 * N, st));
       // values on the coset shift*<w_N>, leaf (= bit-reversed) order, both components
       MP2_TRY(ntt_coset_lde(f->coeffs, n, vals.p, N, 2, f->n_log, f->rate_bits, 0, 0, st, nullptr, f->shift));
-      MP2_CUDA(cudaMalloc(&L.leaves, sizeof(u64) * 2 * N));
-      MP2_CUDA(cudaMalloc(&L.digests, sizeof(u64) * 4 * (L.ndigests ? L.ndigests : 1)));
-      MP2_CUDA(cudaMalloc(&L.cap, sizeof(u64) * 4 * L.ncap));
+      MP2_TRY(fri_alloc(&L.leaves, 2 * N, st));
+      MP2_TRY(fri_alloc(&L.digests, 4 * L.ndigests, st));
+      MP2_TRY(fri_alloc(&L.cap, 4 * L.ncap, st));
       MP2_TRY(fri_interleave(vals.p, N, L.leaves, N, st));
       MP2_TRY(merkle_rowmajor(L.leaves, L.nleaves, L.leaf_len, cap_h, f->hash_kind, L.digests, L.cap, st));
       MP2_CUDA(cudaMemcpyAsync(cap_out, L.cap, sizeof(u64) * 4 * L.ncap, cudaMemcpyDeviceToHost, st));
@@ -524,9 +535,8 @@ const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t
       return "";
     }();
     if (!built.empty()) {
-      cudaFree(L.leaves);
-      cudaFree(L.digests);
-      cudaFree(L.cap);
+      for (u64 *p : {L.leaves, L.digests, L.cap})
+        if (p) cudaFreeAsync(p, st);
       return built;
     }
     f->layers.push_back(L);
@@ -538,21 +548,20 @@ const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t
 
 const char *mp2gpu_fri_fold(mp2gpu_fri *f, const uint64_t beta[2]) {
   return guard([&]() -> Status {
-    cudaStream_t st;
-    MP2_TRY(use_device(f, &st));
+    FRI_ON_DEVICE(f, st);
     if (!beta) return "null beta";
     if (!f->committed) return "fri_fold without a committed layer";
     const u32 ab = f->last_arity_bits;
     const size_t n = (size_t)1 << f->n_log, n_out = n >> ab;
     u64 *next = nullptr;
-    MP2_CUDA(cudaMalloc(&next, sizeof(u64) * 2 * n_out));
+    MP2_TRY(fri_alloc(&next, 2 * n_out, st));
     Status folded = fri_fold(f->coeffs, n, next, n_out, n_out, ab, beta[0] % kP, beta[1] % kP, st);
-    if (folded.empty() && cudaStreamSynchronize(st) != cudaSuccess) folded = "fri_fold: stream synchronize failed";
     if (!folded.empty()) {
-      cudaFree(next);
+      cudaFreeAsync(next, st);
       return folded;
     }
-    MP2_CUDA(cudaFree(f->coeffs));
+    MP2_CUDA(cudaFreeAsync(f->coeffs, st));  // stream order: after the fold that read it
+    MP2_CUDA(cudaStreamSynchronize(st));      // the handle may be used from another thread (another stream) next
     f->coeffs = next;
     f->n_log -= ab;
     f->shift = h_pow(f->shift, (u64)1 << ab);
@@ -564,8 +573,7 @@ const char *mp2gpu_fri_fold(mp2gpu_fri *f, const uint64_t beta[2]) {
 const char *mp2gpu_fri_fetch_layer(const mp2gpu_fri *f, uint32_t layer, uint64_t *leaves_out, uint64_t *digests_out,
                                    uint64_t *cap_out) {
   return guard([&]() -> Status {
-    cudaStream_t st;
-    MP2_TRY(use_device(f, &st));
+    FRI_ON_DEVICE(f, st);
     if (layer >= f->layers.size()) return "no such FRI layer";
     const mp2gpu_fri::Layer &L = f->layers[layer];
     if (leaves_out) MP2_CUDA(cudaMemcpyAsync(leaves_out, L.leaves, sizeof(u64) * L.nleaves * L.leaf_len, cudaMemcpyDeviceToHost, st));
@@ -579,8 +587,7 @@ const char *mp2gpu_fri_fetch_layer(const mp2gpu_fri *f, uint32_t layer, uint64_t
 const char *mp2gpu_fri_open_layer(const mp2gpu_fri *f, uint32_t layer, const uint64_t *leaf_idx, size_t count,
                                   uint64_t *leaves_out, uint64_t *siblings_out) {
   return guard([&]() -> Status {
-    cudaStream_t st;
-    MP2_TRY(use_device(f, &st));
+    FRI_ON_DEVICE(f, st);
     if (layer >= f->layers.size()) return "no such FRI layer";
     if (count && !leaf_idx) return "null leaf_idx";
     const mp2gpu_fri::Layer &L = f->layers[layer];
@@ -607,8 +614,7 @@ const char *mp2gpu_fri_layer_shape(const mp2gpu_fri *f, uint32_t layer, size_t *
 
 const char *mp2gpu_fri_finish(mp2gpu_fri *f, uint64_t *final_coeffs_out, size_t *len_out) {
   return guard([&]() -> Status {
-    cudaStream_t st;
-    MP2_TRY(use_device(f, &st));
+    FRI_ON_DEVICE(f, st);
     const size_t n = (size_t)1 << f->n_log;
     if (len_out) *len_out = n;
     if (final_coeffs_out) {
@@ -624,13 +630,16 @@ const char *mp2gpu_fri_finish(mp2gpu_fri *f, uint64_t *final_coeffs_out, size_t 
 
 void mp2gpu_fri_free(mp2gpu_fri *f) {
   if (!f) return;
+  // every entry point that touches the handle synchronises or orders its work on the owner's stream; the
+  // buffers go back to the stream-ordered pool on the stream they came from (see mp2gpu_batch_free)
+  int prev = 0;
+  cudaGetDevice(&prev);
   cudaSetDevice(f->device);
-  if (f->coeffs) cudaFree(f->coeffs);
-  for (auto &L : f->layers) {
-    cudaFree(L.leaves);
-    cudaFree(L.digests);
-    cudaFree(L.cap);
-  }
+  if (f->coeffs) cudaFreeAsync(f->coeffs, f->owner_stream);
+  for (auto &L : f->layers)
+    for (u64 *p : {L.leaves, L.digests, L.cap})
+      if (p) cudaFreeAsync(p, f->owner_stream);
+  cudaSetDevice(prev);
   delete f;
 }
 

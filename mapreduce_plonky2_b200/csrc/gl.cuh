@@ -4,9 +4,10 @@
 //
 // The B200 has no 64-bit integer multiplier: a 64x64->128 product is four IMAD.WIDE.U32, and on this
 // part IMAD.WIDE / IMAD.HI issue at ~1/3.2 of the plain 32-bit IMAD rate (measured by
-// tools/intpipe_peak.cu: 20 vs 63 thread-instr/clk/SM).  Everything around the four wide multiplies
-// is therefore written as explicit carry chains (add.cc/addc -> IADD3/IADD3.X), which ptxas spreads
-// over the alu and fma pipes, and reductions use 2^64 = eps, 2^96 = -1 (mod p) with no multiply.
+// tools/intpipe_peak.cu: 20 vs 63 thread-instr/clk/SM).  Additions, subtractions and reductions are
+// written as explicit carry chains (add.cc/addc -> IADD3/IADD3.X), which ptxas spreads over the alu
+// and fma pipes, and reductions use 2^64 = eps, 2^96 = -1 (mod p) with no multiply.  Every asm output
+// that is written before the block's last input read is early-clobber ("=&r").
 //
 // Value conventions used by the kernels:
 //   "canonical"  x <  p          -- what is written to memory that leaves the library
@@ -48,14 +49,23 @@ GL_DEV u64 mul_wide(u32 a, u32 b) {
 // possible only when both inputs are >= 2^64 - 2^32, and is folded the same way.
 GL_DEV u64 gl_add(u64 a, u64 b) {
   u32 r0, r1;
+#ifdef MP2_GL_MIXED_CARRY  // experiment: subc straight after an add chain reads the carry as "-carry" (8 instead of 10)
+  asm("{\n\t.reg .u32 m;\n\t"
+      "add.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\tsubc.u32 m, 0, 0;\n\t"
+      "add.cc.u32 %0, %0, m;\n\taddc.cc.u32 %1, %1, 0;\n\tsubc.u32 m, 0, 0;\n\t"
+      "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+#else
   asm("{\n\t.reg .u32 c, m;\n\t"
       "add.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
       "sub.u32 m, 0, c;\n\t"                                     // eps if carry
       "add.cc.u32 %0, %0, m;\n\taddc.cc.u32 %1, %1, 0;\n\taddc.u32 c, 0, 0;\n\t"
       "sub.u32 m, 0, c;\n\t"
       "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
-      : "=r"(r0), "=r"(r1)
+      : "=&r"(r0), "=&r"(r1)
       : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
+#endif
   return pack64(r0, r1);
 }
 // loose a + CANONICAL b -> loose: the wrapped sum is <= p - 2, so one fold is enough
@@ -65,7 +75,7 @@ GL_DEV u64 gl_add_c(u64 a, u64 b_canonical) {
       "add.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
       "sub.u32 m, 0, c;\n\t"
       "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
-      : "=r"(r0), "=r"(r1)
+      : "=&r"(r0), "=&r"(r1)
       : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b_canonical)), "r"(hi32(b_canonical)));
   return pack64(r0, r1);
 }
@@ -76,81 +86,50 @@ GL_DEV u64 gl_sub(u64 a, u64 b) {
       "sub.cc.u32 %0, %2, %4;\n\tsubc.cc.u32 %1, %3, %5;\n\tsubc.u32 m, 0, 0;\n\t"  // m = eps if borrow
       "sub.cc.u32 %0, %0, m;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 m, 0, 0;\n\t"
       "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
-      : "=r"(r0), "=r"(r1)
+      : "=&r"(r0), "=&r"(r1)
       : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
   return pack64(r0, r1);
 }
 
-// w0 + w1*2^32 + w2*2^64 + w3*2^96  ->  loose.        2^64 = eps, 2^96 = -1:
-//   x = {w0,w1} - w3          (borrow  => - eps; the wrapped value is > eps, no second borrow)
-//   t = w2*eps = {-w2, w2 - (w2 != 0)}
-//   r = x + t                 (carry   => + eps; the wrapped value is < 2^64 - 2^33, no second carry)
+// w0 + w1*2^32 + w2*2^64 + w3*2^96  ->  loose.        2^64 = eps = 2^32 - 1, 2^96 = -1:
+//   value = {w0, w1} + {0, w2} - (w2 + w3)
+// computed as a 64-bit add (carry c) and a 64-bit subtract of the 33-bit a = w2 + w3 (borrow b); the net
+// k = c - b in {-1, 0, 1} is folded once as k*eps = {-k, k >> 1}.  No second fold can be needed:
+//   k = +1: the true value is <= (2^64 - 1) + (2^32 - 1)*2^32, so wrapped + eps <= 2^64 - 2;
+//   k = -1: the true value is >= -(2^33 - 2), so wrapped - eps >= 2^64 - 2^33 - 2^32 + 3 > 0.
+// 11 instructions (the round-1 form -- borrow fold, w2*eps, carry fold -- was 13).
 GL_DEV u64 gl_reduce128w(u32 w0, u32 w1, u32 w2, u32 w3) {
   u32 r0, r1;
-  asm("{\n\t.reg .u32 b, t0, t1, c, m;\n\t"
-      "sub.cc.u32 %0, %2, %5;\n\tsubc.cc.u32 %1, %3, 0;\n\tsubc.u32 b, 0, 0;\n\t"
-      "sub.cc.u32 %0, %0, b;\n\tsubc.u32 %1, %1, 0;\n\t"
-      "sub.cc.u32 t0, 0, %4;\n\tsubc.u32 t1, %4, 0;\n\t"
-      "add.cc.u32 %0, %0, t0;\n\taddc.cc.u32 %1, %1, t1;\n\taddc.u32 c, 0, 0;\n\t"
-      "sub.u32 m, 0, c;\n\t"
-      "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
-      : "=r"(r0), "=r"(r1)
+  asm("{\n\t.reg .u32 x1, k, a0, a1, m0, m1;\n\t"
+      "add.cc.u32 x1, %3, %4;\n\taddc.u32 k, 0, 0;\n\t"
+      "add.cc.u32 a0, %4, %5;\n\taddc.u32 a1, 0, 0;\n\t"
+      "sub.cc.u32 %0, %2, a0;\n\tsubc.cc.u32 %1, x1, a1;\n\tsubc.u32 k, k, 0;\n\t"
+      "neg.s32 m0, k;\n\tshr.s32 m1, k, 1;\n\t"
+      "add.cc.u32 %0, %0, m0;\n\taddc.u32 %1, %1, m1;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
       : "r"(w0), "r"(w1), "r"(w2), "r"(w3));
   return pack64(r0, r1);
-}
-// Same reduction with the w2*eps term on the fma pipe: one IMAD.WIDE replaces four alu instructions
-// (an alu -> fma rebalancing knob for the squarings, see MP2_SQR_REDUCE_FMA below).
-//   x = {w0,w1} - w3 (borrow => -eps);  r = w2*eps + x  wraps iff hi32(r) < hi32(x) because
-//   w2*eps <= 2^64 - 2^33 + 1;  a wrapped r is < 2^64 - 2^33, so +eps cannot wrap again.
-GL_DEV u64 gl_reduce128w_fma(u32 w0, u32 w1, u32 w2, u32 w3) {
-  u32 x0, x1;
-  asm("{\n\t.reg .u32 b;\n\t"
-      "sub.cc.u32 %0, %2, %4;\n\tsubc.cc.u32 %1, %3, 0;\n\tsubc.u32 b, 0, 0;\n\t"
-      "sub.cc.u32 %0, %0, b;\n\tsubc.u32 %1, %1, 0;\n\t}"
-      : "=r"(x0), "=r"(x1)
-      : "r"(w0), "r"(w1), "r"(w3));
-  u64 r = mad_wide(w2, GL_EPS, pack64(x0, x1));
-  return hi32(r) < x1 ? r + GL_EPS : r;
 }
 GL_DEV u64 gl_reduce128(u64 lo, u64 hi) { return gl_reduce128w(lo32(lo), hi32(lo), lo32(hi), hi32(hi)); }
 
 // x = lo + 2^64 * hi (hi < 2^32)  ->  loose
 GL_DEV u64 gl_reduce96(u64 lo, u32 hi) { return gl_reduce128w(lo32(lo), hi32(lo), hi, 0u); }
 
-// loose * loose -> loose: four IMAD.WIDE + two 3-word carry chains + the reduction above
+// loose * loose -> loose.  The 128-bit product is left to the compiler: its lowering chains the carries
+// through the multiplier itself (IMAD.WIDE.U32 with a carry-out predicate, IMAD.WIDE.U32.X with a carry-in),
+// 4 IMAD.WIDE + 3 adds/moves, where four separate mul.wide + two add.cc chains needed 4 + 6.
 GL_DEV u64 gl_mul(u64 a, u64 b) {
-  u32 w0, w1, w2, w3;
-  asm("{\n\t.reg .u64 p00, p01, p10, p11;\n\t.reg .u32 h00, l01, h01, l10, h10, l11, h11;\n\t"
-      "mul.wide.u32 p00, %4, %6;\n\tmul.wide.u32 p01, %4, %7;\n\t"
-      "mul.wide.u32 p10, %5, %6;\n\tmul.wide.u32 p11, %5, %7;\n\t"
-      "mov.b64 {%0, h00}, p00;\n\tmov.b64 {l01, h01}, p01;\n\t"
-      "mov.b64 {l10, h10}, p10;\n\tmov.b64 {l11, h11}, p11;\n\t"
-      "add.cc.u32 %1, h00, l01;\n\taddc.cc.u32 %2, h01, l11;\n\taddc.u32 %3, h11, 0;\n\t"
-      "add.cc.u32 %1, %1, l10;\n\taddc.cc.u32 %2, %2, h10;\n\taddc.u32 %3, %3, 0;\n\t}"
-      : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
-#ifdef MP2_MUL_REDUCE_FMA  // per translation unit: the NTT kernels are alu-bound with the fma pipe half idle
-  return gl_reduce128w_fma(w0, w1, w2, w3);
-#else
-  return gl_reduce128w(w0, w1, w2, w3);
-#endif
+  const unsigned __int128 p = (unsigned __int128)a * b;
+  return gl_reduce128((u64)p, (u64)(p >> 64));
 }
 // loose * loose + loose -> loose: the addend rides on the 128-bit product (a*b + c < 2^128), one reduction
 GL_DEV u64 gl_mul_add(u64 a, u64 b, u64 c) {
-  u32 w0, w1, w2, w3;
-  asm("{\n\t.reg .u64 p00, p01, p10, p11;\n\t.reg .u32 l00, h00, l01, h01, l10, h10, l11, h11;\n\t"
-      "mul.wide.u32 p00, %4, %6;\n\tmul.wide.u32 p01, %4, %7;\n\t"
-      "mul.wide.u32 p10, %5, %6;\n\tmul.wide.u32 p11, %5, %7;\n\t"
-      "mov.b64 {l00, h00}, p00;\n\tmov.b64 {l01, h01}, p01;\n\t"
-      "mov.b64 {l10, h10}, p10;\n\tmov.b64 {l11, h11}, p11;\n\t"
-      "add.cc.u32 %1, h00, l01;\n\taddc.cc.u32 %2, h01, l11;\n\taddc.u32 %3, h11, 0;\n\t"
-      "add.cc.u32 %1, %1, l10;\n\taddc.cc.u32 %2, %2, h10;\n\taddc.u32 %3, %3, 0;\n\t"
-      "add.cc.u32 %0, l00, %8;\n\taddc.cc.u32 %1, %1, %9;\n\taddc.cc.u32 %2, %2, 0;\n\taddc.u32 %3, %3, 0;\n\t}"
-      : "=r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(w3)
-      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)), "r"(lo32(c)), "r"(hi32(c)));
-  return gl_reduce128w(w0, w1, w2, w3);
+  const unsigned __int128 p = (unsigned __int128)a * b + c;
+  return gl_reduce128((u64)p, (u64)(p >> 64));
 }
-// loose^2 -> loose: three IMAD.WIDE (the cross product is added twice)
+// loose^2 -> loose: three IMAD.WIDE (the cross product is added twice).  The compiler's own a*a keeps four
+// wide multiplies, and the quarter-rate multiplier is what bounds the S-box (selftest.cu's probe: the fma pipe
+// saturates first), so the square is spelled out.
 GL_DEV u64 gl_sqr(u64 a) {
   u32 w0, w1, w2, w3;
   asm("{\n\t.reg .u64 p00, p01, p11;\n\t.reg .u32 h00, l01, h01, l11, h11;\n\t"
@@ -158,13 +137,9 @@ GL_DEV u64 gl_sqr(u64 a) {
       "mov.b64 {%0, h00}, p00;\n\tmov.b64 {l01, h01}, p01;\n\tmov.b64 {l11, h11}, p11;\n\t"
       "add.cc.u32 %1, h00, l01;\n\taddc.cc.u32 %2, h01, l11;\n\taddc.u32 %3, h11, 0;\n\t"
       "add.cc.u32 %1, %1, l01;\n\taddc.cc.u32 %2, %2, h01;\n\taddc.u32 %3, %3, 0;\n\t}"
-      : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+      : "=&r"(w0), "=&r"(w1), "=&r"(w2), "=&r"(w3)
       : "r"(lo32(a)), "r"(hi32(a)));
-#ifdef MP2_SQR_REDUCE_FMA  // measured neutral on B200 (and +14 registers on the Poseidon2 kernel): off
-  return gl_reduce128w_fma(w0, w1, w2, w3);
-#else
   return gl_reduce128w(w0, w1, w2, w3);
-#endif
 }
 
 // x^7: 2 squarings + 2 multiplications (S-box of both permutations)

@@ -50,6 +50,28 @@ struct ProfScope {
     MP2_CUDA(cudaGetLastError()); \
   } while (0)
 
+// ---- per-thread device binding (api.cu) ----
+// Binds the calling thread to the device chosen with mp2gpu_init (default 0) and returns that thread's private
+// compute stream on it (optionally also its device->host and host->device copy streams).
+Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out = nullptr, cudaStream_t *up_out = nullptr);
+// the device the calling thread is bound to
+int ctx_device();
+// Runs the rest of the scope on the device a handle lives on, then gives the thread its own device back
+// (both the library's binding and CUDA's current device).
+struct DeviceScope {
+  int saved;
+  explicit DeviceScope(int device);
+  ~DeviceScope();
+  DeviceScope(const DeviceScope &) = delete;
+  DeviceScope &operator=(const DeviceScope &) = delete;
+};
+
+// ---- host-buffer plumbing shared by api.cu and sharded.cu ----
+// Column-wise copies merged over runs of columns that are adjacent in host memory
+Status copy_columns_h2d(u64 *dev, const uint64_t *const *cols, size_t ncols, size_t n, cudaStream_t st);
+Status copy_columns_d2h(uint64_t *const *cols, const u64 *dev, size_t ncols, size_t n, cudaStream_t st);
+Status check_commit_args(size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind);
+
 // Stream-ordered scratch, returned to the pool on every exit path
 struct DevBuf {
   u64 *p = nullptr;
@@ -182,6 +204,14 @@ inline int log2_exact(size_t n) {
   return l;
 }
 
+}  // namespace mp2
+
+struct mp2gpu_batch;
+namespace mp2 {
+// PolynomialBatch::from_values / from_coeffs with host buffers on the calling thread's device (api.cu)
+Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind,
+                   int from_coeffs, uint64_t *const *coeffs_out, uint64_t *leaves_out, uint64_t *digests_out,
+                   uint64_t *cap_out, mp2gpu_batch **handle_out);
 }  // namespace mp2
 
 // Device-resident PolynomialBatch behind the C ABI's opaque handle (api.cu creates it, fri.cu reads coeffs).

@@ -70,7 +70,7 @@ GL_DEV u64 pos_merge3(u32 o0, u32 o1, u32 o2) {
       "add.cc.u32 %0, %0, t0;\n\taddc.cc.u32 %1, %1, t1;\n\taddc.u32 cy, 0, 0;\n\t"
       "sub.u32 m, 0, cy;\n\t"
       "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
-      : "=r"(lo), "=r"(hi)
+      : "=&r"(lo), "=&r"(hi)
       : "r"(o0), "r"(o1), "r"(o2), "r"(s22), "r"(s10), "r"(s11), "r"(s21));
   return pack64(lo, hi);
 }
@@ -131,19 +131,21 @@ GL_DEV void pos_mds_rc(u64 (&s)[12], const u32 *rc3) {
   for (int i = 0; i < 12; i++) s[i] = pos_merge3(o0[i], o1[i], o2[i]);
 }
 
-// Carry-propagates the three plane outputs (each < 2^31) of one lane back into limbs that may enter
-// the next MDS: l0 < 2^22, l1 < 2^21.6, l2 < 2^21.  The bits above 2^64 (ov <= 2^10) are folded with
-// 2^64 = 2^32 - 1: +ov*2^10 on limb 1 (2^32 = 2^10 * 2^22) and -ov on limb 0, borrowing 2^22 from
-// limb 1 (which is >= ov*2^10 >= 1 whenever ov > 0) if limb 0 would go negative.
+// Carry-propagates the three plane outputs of one lane back into limbs that may enter the next MDS.
+//   value = o0 + o1*2^22 + o2*2^43 = (o0 & M22) + (t1 & M21)*2^22 + (t2 & M21)*2^43 + ov*2^64,
+//   t1 = o1 + (o0 >> 22), t2 = o2 + (t1 >> 21), ov = t2 >> 21 (<= 2^11),  and 2^64 = 2^32 - 1 = 2^10*2^22 - 1:
+//   +ov*2^10 on limb 1, -ov on limb 0.  Limb 0 would go negative, so a multiple of p is added in limb form:
+//   p + (2^22, -1, 0) + (0, 2^21, -1) = (2^22 + 1, 2^21 - 2^10 - 1, 2^21 - 1)  (limb weights 1, 2^22, 2^43),
+//   which keeps every limb non-negative with no borrow logic.  Resulting limbs are < 2^23 + 2, so the next
+//   plane outputs stay below 264 * 2^23.01 < 2^32 (tests/test_limb_planes.py pins the identity and the bounds).
+// The round-1 form borrowed conditionally (12 instructions per lane); this one is 10.
 GL_DEV void pos_renorm3(u32 o0, u32 o1, u32 o2, u32 &l0, u32 &l1, u32 &l2) {
   const u32 t1 = o1 + (o0 >> 22);
   const u32 t2 = o2 + (t1 >> 21);
   const u32 ov = t2 >> 21;
-  l2 = t2 & 0x1FFFFFu;
-  const u32 d = (o0 & 0x3FFFFFu) - ov;
-  const u32 neg = (u32)((int)d >> 31);  // all ones if d < 0
-  l0 = d + (neg & 0x400000u);
-  l1 = (t1 & 0x1FFFFFu) + (ov << 10) + neg;
+  l0 = (o0 & 0x3FFFFFu) - ov + 0x400001u;
+  l1 = (t1 & 0x1FFFFFu) + (ov * 1024u + 0x1FFBFFu);
+  l2 = (t2 & 0x1FFFFFu) + 0x1FFFFFu;
 }
 
 // S-box on all 12 lanes.  Fully unrolled this is ~1000 instructions per round and the permutation

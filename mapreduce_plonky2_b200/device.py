@@ -104,6 +104,22 @@ def merkle_colmajor(lde: torch.Tensor, cap_height: int, hash_kind: int, leaves: 
               _stream_ptr())
 
 
+def merkle_colmajor_leaves(lde: torch.Tensor, cap_height: int, hash_kind: int, leaf_begin: int, leaf_end: int,
+                           leaves: Optional[torch.Tensor], digests: torch.Tensor, cap: torch.Tensor) -> None:
+    """Leaf digests (and optional row-major rows) of leaves [leaf_begin, leaf_end) only -- the first half of
+    :func:`merkle_colmajor`, for callers that overlap host copies of one leaf block with the hashing of the next."""
+    ncols, nleaves = lde.shape
+    _lib.call("mp2gpu_dev_merkle_colmajor_leaves", _chk(lde, "lde"), nleaves, ncols, nleaves, cap_height, hash_kind,
+              leaf_begin, leaf_end, _chk(leaves, "leaves") if leaves is not None else None, _chk(digests, "digests"),
+              _chk(cap, "cap"), _stream_ptr())
+
+
+def merkle_levels(nleaves: int, cap_height: int, hash_kind: int, digests: torch.Tensor, cap: torch.Tensor) -> None:
+    """Inner levels + cap once every leaf digest is in place (second half of :func:`merkle_colmajor`)."""
+    _lib.call("mp2gpu_dev_merkle_levels", nleaves, cap_height, hash_kind, _chk(digests, "digests"), _chk(cap, "cap"),
+              _stream_ptr())
+
+
 def merkle_rowmajor(leaves: torch.Tensor, cap_height: int, hash_kind: int, digests: torch.Tensor,
                     cap: torch.Tensor) -> None:
     nleaves, leaf_len = leaves.shape

@@ -305,6 +305,28 @@ def reverse_bits(x: int, bits: int) -> int:
     return int(format(x, "0%db" % bits)[::-1], 2) if bits else 0
 
 
+class Communicator:
+    """The GPUs of this process that share one wide batch (``mp2gpu_comm_init``): a power-of-two number of
+    devices with peer access to each other.  Used by :meth:`PolynomialBatch.from_values_sharded`."""
+
+    def __init__(self, devices: Sequence[int]):
+        devs = (C.c_int * len(devices))(*devices)
+        self._handle = C.c_void_p(None)
+        _lib.call("mp2gpu_comm_init", len(devices), devs, C.byref(self._handle))
+        self.devices = list(devices)
+
+    def free(self) -> None:
+        if self._handle:
+            _lib.load().mp2gpu_comm_free(self._handle)
+            self._handle = C.c_void_p(None)
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class PolynomialBatch:
     """``PolynomialBatch<F, C, D>{ polynomials, merkle_tree, degree_log, rate_bits, blinding }``."""
 
@@ -356,6 +378,32 @@ class PolynomialBatch:
                     fetch_leaves: bool = True) -> "PolynomialBatch":
         return cls._commit("mp2gpu_commit_from_coeffs", polynomials, rate_bits, blinding, cap_height, hash_kind,
                            keep_on_device, fetch_leaves)
+
+    @classmethod
+    def from_values_sharded(cls, comm: "Communicator", values, rate_bits: int, blinding: bool, cap_height: int,
+                            hash_kind: int = POSEIDON2, from_coeffs: bool = False,
+                            fetch_leaves: bool = True) -> "PolynomialBatch":
+        """The same commitment computed by all the devices of ``comm`` (``mp2gpu_commit_from_values_sharded``):
+        columns sharded, the exchange fused into the LDE kernel's peer stores, rows and subtrees sharded.
+        Same result, same layouts as :meth:`from_values` / :meth:`from_coeffs`."""
+        if blinding:
+            raise Mp2GpuError("blinding (salted) batches are not supported: the reference never enables "
+                              "zero_knowledge (mp2-common/src/lib.rs:45-47)")
+        cols = _arr(values, 2)
+        ncols, n = cols.shape
+        n_log = int(n).bit_length() - 1
+        if ncols == 0 or n == 0 or (1 << n_log) != n:
+            raise Mp2GpuError("PolynomialValues length must be a power of two and the batch non-empty")
+        N = n << rate_bits
+        ncap = 1 << cap_height
+        coeffs = np.empty((ncols, n), dtype=np.uint64)
+        leaves = np.empty((N, ncols), dtype=np.uint64) if fetch_leaves else None
+        digests = np.empty((max(2 * (N - ncap), 0), 4), dtype=np.uint64)
+        cap = np.empty((ncap, 4), dtype=np.uint64)
+        _lib.call("mp2gpu_commit_from_values_sharded", comm._handle, _col_ptrs(cols), ncols, n_log, rate_bits,
+                  cap_height, hash_kind, 1 if from_coeffs else 0, _col_ptrs(coeffs), _ptr(leaves),
+                  _ptr(digests) if digests.size else None, _ptr(cap))
+        return cls(coeffs, MerkleTree(leaves, digests, MerkleCap(cap), hash_kind), n_log, rate_bits, False, None)
 
     # -- accessors -----------------------------------------------------------------------------
     def get_lde_values(self, index: int, step: int) -> np.ndarray:

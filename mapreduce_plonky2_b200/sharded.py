@@ -79,6 +79,25 @@ class CudaEngine:
     def merkle_colmajor(self, lde, cap_height, hash_kind, leaves, digests, cap):
         self.d.merkle_colmajor(lde, cap_height, hash_kind, leaves, digests, cap)
 
+    def merkle_colmajor_leaves(self, lde, cap_height, hash_kind, lb, le, leaves, digests, cap):
+        self.d.merkle_colmajor_leaves(lde, cap_height, hash_kind, lb, le, leaves, digests, cap)
+
+    def merkle_levels(self, nleaves, cap_height, hash_kind, digests, cap):
+        self.d.merkle_levels(nleaves, cap_height, hash_kind, digests, cap)
+
+
+@dataclass
+class HostOutputs:
+    """Pinned host buffers that receive this rank's outputs while the commitment is still running (the end-to-end
+    form of the sharded call): coefficients travel back under the LDE, each block of leaf rows under the hashing
+    of the next block, digests and cap at the end -- all on ``copy_stream``.  The caller synchronises."""
+    coeffs: Optional[torch.Tensor]
+    leaves: Optional[torch.Tensor]
+    digests: Optional[torch.Tensor]
+    cap: Optional[torch.Tensor]
+    copy_stream: "torch.cuda.Stream"
+    chunks: int = 8
+
 
 class PeerExchange:
     """Receive buffer of this rank in symmetric memory, mapped into every peer over NVLink/NVSwitch.
@@ -122,14 +141,16 @@ def _log2(x: int) -> int:
 
 def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, cap_height: int, hash_kind: int,
                    engine, group=None, from_coeffs: bool = False, want_leaves: bool = True,
-                   scratch: Optional[dict] = None, exchange: str = "nccl") -> ShardedBatch:
+                   scratch: Optional[dict] = None, exchange: str = "nccl",
+                   host_out: Optional[HostOutputs] = None) -> ShardedBatch:
     """PolynomialBatch::from_values / from_coeffs of one (ncols_total x n) batch over ``group``.
 
     ``cols_local``: this rank's columns, shape (ncols_total / G, n).  Requirements: G is a power of two,
     G divides ncols_total, and G <= 2^cap_height (every rank owns whole cap subtrees).
     ``scratch`` may hold reusable buffers (keys: coeffs, send, recv, leaves, digests, cap_local, cap).
     ``exchange``: "nccl" = LDE into a send buffer + ``all_to_all_single``; "peer" = the LDE kernel stores
-    straight into the peers' receive buffers (symmetric memory over NVLink), no all-to-all."""
+    straight into the peers' receive buffers (symmetric memory over NVLink), no all-to-all.
+    ``host_out``: also stream this rank's outputs into pinned host buffers, overlapped with the compute."""
     G = dist.get_world_size(group)
     g = dist.get_rank(group)
     glog = _log2(G)
@@ -160,6 +181,17 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
         engine.canonical_copy(cols_local, coeffs)
     else:
         engine.intt(cols_local, coeffs)
+    def to_host(dst, src):
+        # dst <- src on the copy stream, ordered after everything queued on the compute stream so far
+        if host_out is None or dst is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        host_out.copy_stream.wait_event(ev)
+        with torch.cuda.stream(host_out.copy_stream):
+            dst.copy_(src, non_blocking=True)
+
+    to_host(host_out.coeffs if host_out else None, coeffs)
     if exchange == "peer" and G > 1:
         # 2+3 fused: every rank's LDE kernel writes block s of its output into rank s's receive buffer
         ex = sc.get("peer_exchange")
@@ -194,7 +226,20 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
     leaves = buf("leaves", (n_loc, ncols_total)) if want_leaves else None
     digests = buf("digests", (max(ndig_loc, 1), 4))
     cap_local = buf("cap_local", (ncap_loc, 4))
-    engine.merkle_colmajor(lde_rows, cap_height - glog, hash_kind, leaves, digests, cap_local)
+    nchunks = host_out.chunks if (host_out is not None and host_out.leaves is not None and leaves is not None
+                                  and n_loc >= (1 << 16)) else 1
+    if nchunks > 1:
+        # block j of the rows goes to the host while block j+1 is hashed
+        for j in range(nchunks):
+            lb, le = j * (n_loc // nchunks), (j + 1) * (n_loc // nchunks)
+            engine.merkle_colmajor_leaves(lde_rows, cap_height - glog, hash_kind, lb, le, leaves, digests, cap_local)
+            to_host(host_out.leaves[lb:le], leaves[lb:le])
+        engine.merkle_levels(n_loc, cap_height - glog, hash_kind, digests, cap_local)
+    else:
+        engine.merkle_colmajor(lde_rows, cap_height - glog, hash_kind, leaves, digests, cap_local)
+        if host_out is not None and leaves is not None:
+            to_host(host_out.leaves, leaves)
+    to_host(host_out.digests if host_out else None, digests[:ndig_loc])
     tm.mark("merkle")
     # 5. everyone gets the whole cap
     cap = buf("cap", (1 << cap_height, 4))
@@ -203,4 +248,5 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
     else:
         cap.copy_(cap_local)
     tm.mark("cap")
+    to_host(host_out.cap if host_out else None, cap)
     return ShardedBatch(coeffs, leaves, digests[:ndig_loc], cap, g, G)

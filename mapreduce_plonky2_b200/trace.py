@@ -25,6 +25,8 @@ from typing import List
 RATE_BITS, CAP_HEIGHT, NUM_WIRES, ZS_PP_COLS, QUOTIENT_COLS, FRI_LEAF_LEN = 3, 4, 135, 20, 16, 32
 ARITY_BITS, FINAL_POLY_BITS = 4, 5
 
+TRACE_INCLUDES = "per prove(): from_values(135 cols), from_values(20), from_coeffs(16), one Merkle tree per FRI layer"
+
 LEAF_PROOF_DEGREES = (14, 13, 12)          # assumed: base circuit + two wrap steps (BASELINE config 2)
 AGGREGATION_DEGREES = (13, 12)             # assumed: 2-proof branch circuit + one wrap (BASELINE config 4)
 

@@ -75,3 +75,54 @@ def test_sharded_from_coeffs_nccl(tmp_path, oracle):
     assert np.array_equal(np.concatenate([p["coeffs"] for p in parts]), ref["coeffs"])
     assert np.array_equal(np.concatenate([p["leaves"] for p in parts]), ref["leaves"])
     assert np.array_equal(parts[0]["cap"], ref["cap"])
+
+
+# ---- the same path behind the C ABI: one process, one host thread per device, peer stores, no NCCL -------------
+def _build_cpp(tmp_path, name):
+    import subprocess
+
+    exe = os.path.join(str(tmp_path), name)
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    pkg = os.path.join(ROOT, "mapreduce_plonky2_b200")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
+                    "-L" + pkg, "-lmp2gpu", "-L" + os.path.join(ROOT, "oracle"), "-lmp2oracle",
+                    "-Wl,-rpath," + pkg, "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-fopenmp"], check=True, env=env)
+    return exe
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_cpp_sharded_c_abi_equals_oracle(tmp_path, oracle, ndev):
+    """tests/cpp/test_sharded_abi.cpp: mp2gpu_comm_init + mp2gpu_commit_from_values_sharded vs the oracle."""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.device_count() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    exe = _build_cpp(tmp_path, "test_sharded_abi")
+    r = subprocess.run([exe, str(ndev)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sharded C ABI OK on %d device(s)" % ndev in r.stdout
+
+
+@pytest.mark.parametrize("ndev", [1, 2])
+def test_python_mirror_from_values_sharded(oracle, ndev):
+    import torch
+
+    import mapreduce_plonky2_b200 as G
+    from util import field_elems
+
+    if torch.cuda.device_count() < ndev:
+        pytest.skip("needs %d GPUs" % ndev)
+    comm = G.Communicator(list(range(ndev)))
+    cols = field_elems(0xC0FFEE, (12, 1 << 11))
+    for kind in (G.POSEIDON, G.POSEIDON2):
+        pb = G.PolynomialBatch.from_values_sharded(comm, cols, 3, False, 4, hash_kind=kind)
+        ref = oracle.commit(cols, 3, 4, kind)
+        assert np.array_equal(pb.polynomials, ref["coeffs"])
+        assert np.array_equal(pb.merkle_tree.leaves, ref["leaves"])
+        assert np.array_equal(pb.merkle_tree.digests, ref["digests"])
+        assert np.array_equal(pb.merkle_tree.cap.hashes, ref["cap"])
+    with pytest.raises(G.Mp2GpuError):
+        G.PolynomialBatch.from_values_sharded(comm, cols, 3, True, 4)
+    comm.free()

@@ -25,7 +25,24 @@ def run(ncols, n_log, rate_bits=3, cap=4, kind=0, from_coeffs=False, iters=5, wa
     print("c=%d n=2^%d kind=%d: intt %.3f ms, lde %.3f ms, merkle %.3f ms, total %.3f ms -> %.2f Gelem/s" % (
         ncols, n_log, kind, best[0], best[1], best[2], sum(best), elems / sum(best) / 1e6), flush=True)
 
+def field_checks():
+    import ctypes as C
+    from mapreduce_plonky2_b200 import _lib
+    torch.cuda.set_device(0); D.bind_current_device()
+    bad = (C.c_uint64 * 11)()
+    _lib.call("mp2gpu_debug_field_selftest", bad, 11)
+    print("field selftest mismatches:", list(bad), flush=True)
+    out = (C.c_double * 2)()
+    _lib.call("mp2gpu_debug_field_probe", out)
+    print("field probe: %.3f x^7/clk/SM, %.3f dft8-elements/clk/SM" % (out[0], out[1]), flush=True)
+
+
 if __name__ == "__main__":
+    print("lib:", os.environ.get("MP2GPU_LIB", "default"), flush=True)
+    try:
+        field_checks()
+    except Exception as e:  # older library variants have no self-test
+        print("field checks unavailable:", e, flush=True)
     for kind in (0, 1):
         run(135, 14, kind=kind)
         run(20, 14, kind=kind)
