@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--ncols", type=int, default=256)
     ap.add_argument("--rate-bits", type=int, default=3)
     ap.add_argument("--cap-height", type=int, default=4)
-    ap.add_argument("--cpu-sample-log", type=int, default=15, help="rows (log2) of the CPU-baseline sample")
+    ap.add_argument("--cpu-sample-log", type=int, default=16,
+                    help="rows (log2) of the CPU sample; 20 = the whole wide batch (one step takes minutes on 16 cores)")
     ap.add_argument("--workload", default="wide", choices=["wide", "trace"],
                     help="wide: one 2^20 x 256 batch (BASELINE configs[2], the contract line); trace: mp2 leaf-proof "
                          "commitment traces, independent proofs per GPU (configs[1]/[4])")
@@ -143,8 +144,12 @@ def run_reference(a, rank):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64 (Goldilocks field)",
         "data": "synthetic", "config": {"workload": workload_name(a), "sample": sample},
         "cpu_baseline": {"value": value, "unit": "Gelem/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "CPU restatement of plonky2's rayon path (oracle/mp2_oracle.c, OpenMP); the "
-                                 "reference is Rust with un-vendored crates and cannot be compiled here"},
+                         "same_config": sample_log == a.n_log,
+                         "note": "CPU restatement of plonky2's rayon path (oracle/mp2_oracle.c, OpenMP, one task per "
+                                 "column / per subtree, shared root tables, split-half MDS, lazy reductions); the "
+                                 "reference is Rust with un-vendored crates and cannot be compiled here.  ESTIMATED "
+                                 "(not measured) gap to plonky2's AVX2 Poseidon + packed FFT on the same cores: 3-6x "
+                                 "slower, so divide any GPU/CPU ratio by that before quoting it against plonky2"},
         "e2e": {"value": value, "unit": "Gelem/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -393,7 +398,8 @@ def run_ours(a):
         line["cpu_baseline"] = {
             "value": s_elems / times[0] / 1e9, "unit": "Gelem/s", "cores": threads, "kind": "port",
             "sample": "2^%d of 2^%d rows x %d columns, one commitment (%.1f s)" % (sample_log, a.n_log, a.ncols, times[0]),
-            "note": "restated CPU oracle (oracle/mp2_oracle.c, OpenMP) -- not plonky2 itself"}
+            "note": "restated CPU oracle (oracle/mp2_oracle.c, OpenMP) -- not plonky2 itself; estimated 3-6x slower "
+                    "than plonky2's AVX2 path on the same cores"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

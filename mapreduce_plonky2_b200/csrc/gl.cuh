@@ -47,16 +47,11 @@ GL_DEV u64 mul_wide(u32 a, u32 b) {
 
 // loose + loose -> loose.  2^64 = eps, so a carry out is folded back as +eps; a second carry is
 // possible only when both inputs are >= 2^64 - 2^32, and is folded the same way.
+// (Reading the carry of an add chain with `subc m, 0, 0` to get -carry in one instruction -- 8 instead of 10 --
+// is NOT usable: ptxas 12.9 miscompiles the mixed add.cc -> subc chain; the device self-test counted 514 470
+// wrong sums out of 1 048 576 with it, profiles/r2_field_variants.txt.)
 GL_DEV u64 gl_add(u64 a, u64 b) {
   u32 r0, r1;
-#ifdef MP2_GL_MIXED_CARRY  // experiment: subc straight after an add chain reads the carry as "-carry" (8 instead of 10)
-  asm("{\n\t.reg .u32 m;\n\t"
-      "add.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\tsubc.u32 m, 0, 0;\n\t"
-      "add.cc.u32 %0, %0, m;\n\taddc.cc.u32 %1, %1, 0;\n\tsubc.u32 m, 0, 0;\n\t"
-      "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
-      : "=&r"(r0), "=&r"(r1)
-      : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
-#else
   asm("{\n\t.reg .u32 c, m;\n\t"
       "add.cc.u32 %0, %2, %4;\n\taddc.cc.u32 %1, %3, %5;\n\taddc.u32 c, 0, 0;\n\t"
       "sub.u32 m, 0, c;\n\t"                                     // eps if carry
@@ -65,7 +60,6 @@ GL_DEV u64 gl_add(u64 a, u64 b) {
       "add.cc.u32 %0, %0, m;\n\taddc.u32 %1, %1, 0;\n\t}"
       : "=&r"(r0), "=&r"(r1)
       : "r"(lo32(a)), "r"(hi32(a)), "r"(lo32(b)), "r"(hi32(b)));
-#endif
   return pack64(r0, r1);
 }
 // loose a + CANONICAL b -> loose: the wrapped sum is <= p - 2, so one fold is enough

@@ -37,10 +37,10 @@ static inline uint64_t gl_reduce128(u128 x) {
   uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
   uint64_t hh = hi >> 32, hl = hi & GL_EPS;
   uint64_t t0 = lo - hh;
-  if (lo < hh) t0 -= GL_EPS;
+  t0 -= (0 - (uint64_t)(lo < hh)) & GL_EPS; /* branchless: the borrow is a coin flip, a branch mispredicts */
   uint64_t t1 = hl * GL_EPS;
   uint64_t r = t0 + t1;
-  if (r < t0) r += GL_EPS;
+  r += (0 - (uint64_t)(r < t0)) & GL_EPS;
   return r >= GL_P ? r - GL_P : r;
 }
 static inline uint64_t gl_mul(uint64_t a, uint64_t b) { return gl_reduce128((u128)a * b); }
@@ -141,10 +141,10 @@ static inline uint64_t gl_reduce128_loose(u128 x) {
   uint64_t lo = (uint64_t)x, hi = (uint64_t)(x >> 64);
   uint64_t hh = hi >> 32, hl = hi & GL_EPS;
   uint64_t t0 = lo - hh;
-  if (lo < hh) t0 -= GL_EPS;
+  t0 -= (0 - (uint64_t)(lo < hh)) & GL_EPS; /* branchless: the borrow is a coin flip, a branch mispredicts */
   uint64_t t1 = (hl << 32) - hl;
   uint64_t r = t0 + t1;
-  if (r < t0) r += GL_EPS;
+  r += (0 - (uint64_t)(r < t0)) & GL_EPS;
   return r;
 }
 static inline uint64_t gl_mul_loose(uint64_t a, uint64_t b) { return gl_reduce128_loose((u128)a * b); }
@@ -163,17 +163,29 @@ static inline void sbox7_layer_loose(uint64_t s[12]) {
   for (int i = 0; i < 12; i++) s[i] = gl_mul_loose(x3[i], x4[i]);
 }
 
-/* out[r] = sum_i state[(i+r)%12] * CIRC[i] + state[r] * DIAG[r] + rc[r]   (mds_row_shf) */
+/* out[r] = sum_i state[(i+r)%12] * CIRC[i] + state[r] * DIAG[r] + rc[r]   (mds_row_shf).
+ * The matrix entries are tiny (<= 41, row sum 264), so -- as plonky2's scalar code does -- the state is cut
+ * into 32-bit halves and each half goes through the matrix in plain 64-bit arithmetic (2^32 * 264 < 2^41, no
+ * overflow); the two planes are recombined as lo + hi * 2^32 (< 2^74) and reduced once.  gcc vectorises the
+ * two inner products.  (The first version accumulated twelve 128-bit products per row: ~2.5x slower.) */
 static inline void pos_mds_rc(uint64_t s[12], const uint64_t *rc) {
-  uint64_t d[24], o[12];
-  memcpy(d, s, 96);
-  memcpy(d + 12, s, 96);
-  for (int r = 0; r < 12; r++) {
-    u128 acc = (u128)rc[r] + (u128)s[r] * POS_DIAG[r];
-    for (int i = 0; i < 12; i++) acc += (u128)d[i + r] * POS_CIRC[i];
-    o[r] = gl_reduce128_loose(acc);
+  uint32_t lo[24], hi[24];
+  uint64_t al[12], ah[12];
+  for (int i = 0; i < 12; i++) {
+    lo[i] = lo[i + 12] = (uint32_t)s[i];
+    hi[i] = hi[i + 12] = (uint32_t)(s[i] >> 32);
+    al[i] = ah[i] = 0;
   }
-  memcpy(s, o, sizeof o);
+  al[0] = (uint64_t)lo[0] * (uint32_t)POS_DIAG[0];
+  ah[0] = (uint64_t)hi[0] * (uint32_t)POS_DIAG[0];
+  for (int i = 0; i < 12; i++) { /* outer-product order: the inner loop is 12 independent 32x32->64 multiply-adds */
+    const uint32_t c = (uint32_t)POS_CIRC[i];
+    for (int r = 0; r < 12; r++) {
+      al[r] += (uint64_t)lo[i + r] * c;
+      ah[r] += (uint64_t)hi[i + r] * c;
+    }
+  }
+  for (int r = 0; r < 12; r++) s[r] = gl_reduce128_loose((u128)al[r] + ((u128)ah[r] << 32) + rc[r]);
 }
 
 static const uint64_t POS_ZERO_RC[12] = {0};
@@ -362,12 +374,47 @@ void orc_two_to_one(uint32_t kind, const uint64_t a[4], const uint64_t b[4], uin
 /* A.2 transforms                                                             */
 /* ------------------------------------------------------------------------- */
 static inline size_t bitrev(size_t x, uint32_t bits) {
-  size_t r = 0;
-  for (uint32_t i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
-  return r;
+  if (bits == 0) return 0;
+  uint64_t v = (uint64_t)x; /* byte swap + in-byte swaps: O(1) instead of a loop over the bits */
+  v = __builtin_bswap64(v);
+  v = ((v & 0xF0F0F0F0F0F0F0F0ULL) >> 4) | ((v & 0x0F0F0F0F0F0F0F0FULL) << 4);
+  v = ((v & 0xCCCCCCCCCCCCCCCCULL) >> 2) | ((v & 0x3333333333333333ULL) << 2);
+  v = ((v & 0xAAAAAAAAAAAAAAAAULL) >> 1) | ((v & 0x5555555555555555ULL) << 1);
+  return (size_t)(v >> (64 - bits));
 }
 
-void orc_fft(uint64_t *v, uint32_t log_n) {
+/* FftRootTable (plonky2_field fft_root_table): per layer s the powers w_{2^s}^k, k < 2^(s-1), computed once per
+ * size and shared by every column and thread -- what plonky2 passes down as `fft_root_table`.  Layout: the
+ * table of layer s starts at offset 2^(s-1) - 1 (layers 1..32 would need 2^32 entries; sizes are built on demand
+ * up to the largest transform seen). */
+static uint64_t *g_roots = NULL;
+static uint32_t g_roots_log = 0;
+static const uint64_t *root_table(uint32_t log_n) {
+  uint32_t have = __atomic_load_n(&g_roots_log, __ATOMIC_ACQUIRE);
+  if (have >= log_n && g_roots) return g_roots;
+#pragma omp critical(orc_root_table)
+  {
+    if (g_roots_log < log_n || !g_roots) {
+      uint64_t *t = (uint64_t *)malloc(sizeof(uint64_t) * ((size_t)1 << log_n));
+      for (uint32_t s = 1; s <= log_n; s++) {
+        size_t half = (size_t)1 << (s - 1);
+        uint64_t w = orc_gl_root_of_unity(s), *row = t + half - 1;
+        row[0] = 1;
+        for (size_t k = 1; k < half; k++) row[k] = gl_mul(row[k - 1], w);
+      }
+      /* the old table (if any) is leaked on purpose: another thread may still be reading it */
+      __atomic_store_n(&g_roots, t, __ATOMIC_RELEASE);
+      __atomic_store_n(&g_roots_log, log_n, __ATOMIC_RELEASE);
+    }
+  }
+  return g_roots;
+}
+
+/* radix-2 decimation in time on the bit-reversed input (fft_classic).  `zero_log`: the caller promises that
+ * only the first 2^(log_n - zero_log) inputs are non-zero (fft_with_options' zero_factor): after the bit reversal
+ * every aligned group of 2^zero_log entries holds one value followed by zeros, so the first zero_log layers are a
+ * broadcast -- plonky2 skips them the same way. */
+static void fft_zero_padded(uint64_t *v, uint32_t log_n, uint32_t zero_log) {
   size_t n = (size_t)1 << log_n;
   for (size_t i = 0; i < n; i++) {
     size_t j = bitrev(i, log_n);
@@ -378,12 +425,15 @@ void orc_fft(uint64_t *v, uint32_t log_n) {
     }
   }
   for (size_t i = 0; i < n; i++) v[i] = orc_gl_canon(v[i]);
-  uint64_t *tw = (uint64_t *)malloc(sizeof(uint64_t) * (n / 2 + 1));
-  for (uint32_t s = 1; s <= log_n; s++) {
+  const uint64_t *roots = root_table(log_n);
+  if (zero_log) {
+    size_t g = (size_t)1 << zero_log;
+    for (size_t base = 0; base < n; base += g)
+      for (size_t k = 1; k < g; k++) v[base + k] = v[base];
+  }
+  for (uint32_t s = zero_log + 1; s <= log_n; s++) {
     size_t half = (size_t)1 << (s - 1);
-    uint64_t w = orc_gl_root_of_unity(s);
-    tw[0] = 1;
-    for (size_t k = 1; k < half; k++) tw[k] = gl_mul(tw[k - 1], w);
+    const uint64_t *tw = roots + half - 1;
     for (size_t base = 0; base < n; base += 2 * half)
       for (size_t k = 0; k < half; k++) {
         uint64_t a = v[base + k], b = gl_mul(v[base + k + half], tw[k]);
@@ -391,8 +441,9 @@ void orc_fft(uint64_t *v, uint32_t log_n) {
         v[base + k + half] = gl_sub(a, b);
       }
   }
-  free(tw);
 }
+
+void orc_fft(uint64_t *v, uint32_t log_n) { fft_zero_padded(v, log_n, 0); }
 
 /* ifft = fft, then coeffs[i] = fft[(n-i)%n] * n^-1 */
 void orc_ifft(uint64_t *v, uint32_t log_n) {
@@ -417,7 +468,7 @@ void orc_coset_lde(const uint64_t *coeffs, uint32_t log_n, uint32_t rate_bits, u
     pw = gl_mul(pw, shift);
   }
   memset(out + n, 0, (N - n) * sizeof(uint64_t));
-  orc_fft(out, log_n + rate_bits);
+  fft_zero_padded(out, log_n + rate_bits, rate_bits);
 }
 
 void orc_eval_naive(const uint64_t *coeffs, size_t n, uint64_t shift, uint64_t w, size_t n_out,
