@@ -14,4 +14,6 @@ from .plonky2 import (POSEIDON, POSEIDON2, FriCommitPhase, fri_committed_trees, 
 from .fri import (Challenger, FriBatchInfo, FriConfig, FriParams, FriProof, fri_proof, open_batches,  # noqa: F401,E402
                   prove_openings)
 
-__version__ = "0.1.0"
+from . import wire  # noqa: F401,E402  (bincode mirrors of FriProof / ProofWithPublicInputs / ProofWithVK)
+
+__version__ = "0.2.0"

@@ -247,6 +247,18 @@ def test_fri_proof_matches_oracle_and_verifies(oracle, kind, degree_bits, widths
             assert np.array_equal(row, rrow) and np.array_equal(mp.siblings, rsib)
         for st, (rev, rsib) in zip(rnd.steps, rr["steps"]):
             assert np.array_equal(st.evals, rev) and np.array_equal(st.merkle_proof.siblings, rsib)
+    # GPU proof -> bincode bytes -> parse -> identical proof -> identical bytes (wire.py, mp2-common/src/proof.rs:41-57)
+    from mapreduce_plonky2_b200 import wire as W
+
+    data = W.write_fri_proof(proof)
+    back = W.read_fri_proof(data)
+    assert W.write_fri_proof(back) == data
+    assert back.pow_witness == proof.pow_witness and np.array_equal(back.final_poly, proof.final_poly)
+    for ra, rb in zip(back.query_round_proofs, proof.query_round_proofs):
+        for (ea, pa), (eb, pb) in zip(ra.initial_trees_proof, rb.initial_trees_proof):
+            assert np.array_equal(ea, eb) and np.array_equal(pa.siblings, pb.siblings)
+        for sa, sb in zip(ra.steps, rb.steps):
+            assert np.array_equal(sa.evals, sb.evals) and np.array_equal(sa.merkle_proof.siblings, sb.merkle_proof.siblings)
     # and accepted by the by-definition verifier with its own transcript
     vch = pyref.Challenger(kind)
     caps = [o.merkle_tree.cap.hashes.tolist() for o in oracles]
