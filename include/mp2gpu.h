@@ -205,11 +205,13 @@ const char *mp2gpu_dev_coset_lde(const uint64_t *coeffs, size_t in_stride, uint6
  * their own barrier (sharded.py: symmetric-memory barrier before and after).  first_shard: the destination this
  * launch stores to first, the others following in rotated order -- every rank passes its own index, so that at
  * any moment the ranks write to different peers (all starting with shard 0 serialises the exchange on one
- * NVLink ingress). */
+ * NVLink ingress).  scratch: ncols * (n << rate_bits) elements of LOCAL device memory for the four-step
+ * intermediate when n > 2^14 (NULL: taken from the stream-ordered pool for the call -- avoid that in a loop, a
+ * multi-GB pool allocation per step is what stalled the first step after an idle period in round 1). */
 const char *mp2gpu_dev_coset_lde_peer(const uint64_t *coeffs, size_t in_stride,
                                       uint64_t *const *shard_bases, size_t lde_stride, size_t ncols,
                                       uint32_t n_log, uint32_t rate_bits, uint32_t shard_log,
-                                      uint32_t first_shard, void *stream);
+                                      uint32_t first_shard, uint64_t *scratch, void *stream);
 /* The two halves of mp2gpu_dev_merkle_colmajor, for callers that overlap the hashing of one leaf range with
  * the device->host copy of the previous one: leaf digests (and optional row-major rows) of leaves
  * [leaf_begin, leaf_end) only; then the inner levels + cap once every leaf has been hashed. */

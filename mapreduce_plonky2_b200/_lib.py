@@ -62,7 +62,7 @@ SIGNATURES = {
     "mp2gpu_dev_coset_lde": (_ERR, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32,
                                     C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p]),
     "mp2gpu_dev_coset_lde_peer": (_ERR, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.c_size_t, C.c_size_t,
-                                         C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+                                         C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]),
     "mp2gpu_dev_merkle_colmajor": (_ERR, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mp2gpu_dev_merkle_colmajor_leaves": (_ERR, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint32, C.c_uint32,

@@ -633,12 +633,12 @@ const char *mp2gpu_dev_coset_lde(const uint64_t *coeffs, size_t in_stride, uint6
 
 const char *mp2gpu_dev_coset_lde_peer(const uint64_t *coeffs, size_t in_stride, uint64_t *const *shard_bases,
                                       size_t lde_stride, size_t ncols, uint32_t n_log, uint32_t rate_bits,
-                                      uint32_t shard_log, uint32_t first_shard, void *stream) {
+                                      uint32_t shard_log, uint32_t first_shard, uint64_t *scratch, void *stream) {
   return guarded([&]() -> Status {
     cudaStream_t st;
     MP2_TRY(pick_stream(stream, &st));
     if (!shard_bases) return "null shard_bases";
-    return ntt_coset_lde((const u64 *)coeffs, in_stride, nullptr, lde_stride, ncols, n_log, rate_bits, shard_log, 0, st,
+    return ntt_coset_lde((const u64 *)coeffs, in_stride, (u64 *)scratch, lde_stride, ncols, n_log, rate_bits, shard_log, 0, st,
                          (u64 *const *)shard_bases, kCosetShift, LDE_ALL, 0, 0, first_shard);
   });
 }

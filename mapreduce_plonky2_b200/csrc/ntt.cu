@@ -490,8 +490,13 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     mid_map = LdeMap{};
     mid_map.ls_log = N_log;
     mid_map.col_stride = N;
-    MP2_TRY(scratch.alloc(N * ncols, st));
-    mid = scratch.p;
+    if (lde) {
+      mid = lde;  // caller-provided N * ncols scratch (a per-call multi-GB pool allocation is what stalled the first
+                  // step after an idle period: profiles/bench/r2_peer_stall_2gpu.txt)
+    } else {
+      MP2_TRY(scratch.alloc(N * ncols, st));
+      mid = scratch.p;
+    }
   }
   tp.coset0 = 0;
   if (phase != LDE_PASS2) {

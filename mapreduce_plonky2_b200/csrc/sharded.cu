@@ -32,6 +32,8 @@ struct mp2gpu_comm {
     cudaStream_t st = nullptr, cp = nullptr, up = nullptr;
     u64 *recv = nullptr;  // G x c_loc x n_loc: block s = rank s's columns restricted to MY leaves (peer-writable)
     size_t recv_elems = 0;
+    u64 *mid = nullptr;   // c_loc x N: four-step intermediate of the LDE (persistent: no multi-GB pool traffic per call)
+    size_t mid_elems = 0;
   };
   std::vector<Rank> ranks;
   std::mutex call_mu;  // one sharded commitment at a time per communicator
@@ -112,6 +114,14 @@ Status rank_stage_a(mp2gpu_comm *c, int g, const ShardedArgs &a, RankState &rs) 
     MP2_CUDA(cudaMalloc(&r.recv, need * sizeof(u64)));
     r.recv_elems = need;
   }
+  if (ntt_lde_is_two_pass(a.n_log) && r.mid_elems < c_loc * N) {
+    MP2_CUDA(cudaStreamSynchronize(r.st));
+    if (r.mid) MP2_CUDA(cudaFree(r.mid));
+    r.mid = nullptr;
+    r.mid_elems = 0;
+    MP2_CUDA(cudaMalloc(&r.mid, c_loc * N * sizeof(u64)));
+    r.mid_elems = c_loc * N;
+  }
   MP2_TRY(rs.in.alloc(c_loc * n, r.st));
   MP2_TRY(rs.coeffs.alloc(c_loc * n, r.st));
   if (a.leaves_out) MP2_TRY(rs.leaves.alloc(n_loc * a.ncols, r.st));
@@ -152,7 +162,7 @@ Status rank_stage_b(mp2gpu_comm *c, int g, const ShardedArgs &a, RankState &rs) 
   std::vector<u64 *> bases(G);
   for (size_t s = 0; s < G; s++) bases[s] = c->ranks[s].recv + (size_t)g * c_loc * n_loc;  // MY block in rank s's buffer
   // rank g stores to rank g first, then g+1, ...: at any moment the ranks target different peers
-  MP2_TRY(ntt_coset_lde(rs.coeffs.p, n, nullptr, n_loc, c_loc, a.n_log, a.rate_bits, glog, 0, r.st, bases.data(),
+  MP2_TRY(ntt_coset_lde(rs.coeffs.p, n, ntt_lde_is_two_pass(a.n_log) ? r.mid : nullptr, n_loc, c_loc, a.n_log, a.rate_bits, glog, 0, r.st, bases.data(),
                         kCosetShift, LDE_ALL, 0, 0, (u32)g));
   MP2_CUDA(cudaStreamSynchronize(r.st));
   return "";
@@ -293,6 +303,7 @@ void mp2gpu_comm_free(mp2gpu_comm *c) {
     cudaSetDevice(r.device);
     if (r.st) cudaStreamSynchronize(r.st);
     if (r.recv) cudaFree(r.recv);
+    if (r.mid) cudaFree(r.mid);
     for (cudaStream_t s : {r.st, r.cp, r.up})
       if (s) cudaStreamDestroy(s);
   }

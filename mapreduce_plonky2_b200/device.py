@@ -82,17 +82,22 @@ def coset_lde(coeffs: torch.Tensor, lde: torch.Tensor, rate_bits: int, shard_log
               n.bit_length() - 1, rate_bits, shard_log, shard_stride, _stream_ptr())
 
 
-def coset_lde_peer(coeffs: torch.Tensor, shard_ptrs, n_loc: int, rate_bits: int, first_shard: int = 0) -> None:
+def coset_lde_peer(coeffs: torch.Tensor, shard_ptrs, n_loc: int, rate_bits: int, first_shard: int = 0,
+                   scratch: Optional[torch.Tensor] = None) -> None:
     """coeffs (ncols, n) -> LDE whose shard g is stored at device address ``shard_ptrs[g]`` (column c at
     + c*n_loc elements): the peers' receive buffers, i.e. the all-to-all happens in the kernel's store.
-    ``first_shard``: destination written first (pass the caller's rank: the ranks then never share a target)."""
+    ``first_shard``: destination written first (pass the caller's rank: the ranks then never share a target).
+    ``scratch``: local (ncols * N)-element buffer for the four-step intermediate (reused across calls)."""
     import ctypes as C
 
     ncols, n = coeffs.shape
     G = len(shard_ptrs)
     arr = (C.c_void_p * G)(*[C.c_void_p(int(p)) for p in shard_ptrs])
+    if scratch is not None and scratch.numel() < ncols * (n << rate_bits):
+        raise ValueError("scratch must hold ncols * N elements")
     _lib.call("mp2gpu_dev_coset_lde_peer", _chk(coeffs, "coeffs"), n, arr, n_loc, ncols, n.bit_length() - 1,
-              rate_bits, G.bit_length() - 1, first_shard, _stream_ptr())
+              rate_bits, G.bit_length() - 1, first_shard, _chk(scratch, "scratch") if scratch is not None else None,
+              _stream_ptr())
 
 
 def merkle_colmajor(lde: torch.Tensor, cap_height: int, hash_kind: int, leaves: Optional[torch.Tensor],

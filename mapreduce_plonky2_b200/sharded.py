@@ -73,8 +73,8 @@ class CudaEngine:
     def coset_lde(self, coeffs, lde, rate_bits, shard_log):
         self.d.coset_lde(coeffs, lde, rate_bits, shard_log)
 
-    def coset_lde_peer(self, coeffs, shard_ptrs, n_loc, rate_bits, first_shard=0):
-        self.d.coset_lde_peer(coeffs, shard_ptrs, n_loc, rate_bits, first_shard)
+    def coset_lde_peer(self, coeffs, shard_ptrs, n_loc, rate_bits, first_shard=0, scratch=None):
+        self.d.coset_lde_peer(coeffs, shard_ptrs, n_loc, rate_bits, first_shard, scratch)
 
     def merkle_colmajor(self, lde, cap_height, hash_kind, leaves, digests, cap):
         self.d.merkle_colmajor(lde, cap_height, hash_kind, leaves, digests, cap)
@@ -202,7 +202,10 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
         ex.barrier()   # peers are done reading what the previous step put into my buffer
         tm.mark("barrier1")
         # rank g stores to rank g first, then g+1, ...: at any moment the ranks target different peers
-        engine.coset_lde_peer(coeffs, ex.shard_ptrs, n_loc, rate_bits, g)
+        # the four-step intermediate lives in a buffer that persists across calls (same shape as the NCCL path's
+        # send buffer): allocating its 8*c_loc*N bytes from the pool on every call stalled the first step after idle
+        mid = buf("send", (G, c_loc, n_loc))
+        engine.coset_lde_peer(coeffs, ex.shard_ptrs, n_loc, rate_bits, g, scratch=mid)
         tm.mark("lde_peer")
         ex.barrier()   # every block of my receive buffer has landed
         tm.mark("barrier2")
