@@ -281,9 +281,10 @@ const char *mp2gpu_debug_int_pipe_peak(double *imad_per_clk_per_sm, double *sm_c
                                        double *t_imad_per_s);
 
 /* Device self-test of the Goldilocks primitives (add, add-canonical, sub, mul, sqr, mul-add, reduce128, x^7,
- * the three shift twiddles -- in that order) against 128-bit arithmetic by definition, over all pairs of
- * 48 corner values around 0 / 2^32 / 2^63 / p / 2^64 and 976 pseudo-random ones.  mismatches_out[i] = number
- * of wrong results of test i (ntests >= 11).  Replaces plonky2_field's goldilocks_field unit tests for the
+ * the three shift twiddles, every 2^(12 j) shift, the 8- and 16-point shift-twiddle butterflies -- in that
+ * order) against 128-bit arithmetic / the DFT by definition, over all pairs of 48 corner values around
+ * 0 / 2^32 / 2^63 / p / 2^64 and 976 pseudo-random ones.  mismatches_out[i] = number of wrong results of
+ * test i (ntests >= 14).  Replaces plonky2_field's goldilocks_field unit tests for the
  * GPU arithmetic. */
 const char *mp2gpu_debug_field_selftest(uint64_t *mismatches_out, size_t ntests);
 /* Register-only throughput of the two arithmetic inner loops, thread-level operations per (nominal) clock per

@@ -31,6 +31,26 @@ GL_DEV u64 gl_mul_2_72(u64 x) {
   return pack64(r0, r1);
 }
 
+// x * 2^K for a compile-time 0 < K < 96 that is not a multiple of 32 (the 16th roots of unity are +-2^(12 j))
+template <int K>
+GL_DEV u64 gl_mul_pow2(u64 x) {
+  static_assert(K > 0 && K < 96 && K % 32 != 0, "shift must be in (0, 96) and not a whole word");
+  const u32 x0 = lo32(x), x1 = hi32(x);
+  constexpr int S = K % 32;
+  const u32 a = x0 << S, b = __funnelshift_l(x0, x1, S), c = x1 >> (32 - S);  // x << S = {a, b, c}
+  if (K < 32) return gl_reduce128w(a, b, c, 0u);
+  if (K < 64) return gl_reduce128w(0u, a, b, c);
+  // K >= 64: a*2^64 + b*2^96 + c*2^128 = a*eps - {b, c}   (2^96 = -1, 2^128 = -2^32), as in gl_mul_2_72
+  u32 r0, r1;
+  asm("{\n\t.reg .u32 t0, t1, m;\n\t"
+      "sub.cc.u32 t0, 0, %2;\n\tsubc.u32 t1, %2, 0;\n\t"
+      "sub.cc.u32 %0, t0, %3;\n\tsubc.cc.u32 %1, t1, %4;\n\tsubc.u32 m, 0, 0;\n\t"
+      "sub.cc.u32 %0, %0, m;\n\tsubc.u32 %1, %1, 0;\n\t}"
+      : "=&r"(r0), "=&r"(r1)
+      : "r"(a), "r"(b), "r"(c));
+  return pack64(r0, r1);
+}
+
 // ---- small DFTs with shift twiddles; output position j holds frequency bitrev(j) -------------------
 GL_DEV void gl_dft2(u64 (&x)[2]) {
   u64 a = gl_add(x[0], x[1]), b = gl_sub(x[0], x[1]);
@@ -62,6 +82,29 @@ GL_DEV void gl_dft8(u64 (&x)[8]) {  // w_8 = -2^24, w_8^2 = 2^48, w_8^3 = -2^72
   x[6] = gl_add(f0, f1);
   x[7] = gl_sub(f0, f1);
 }
+// 16 points: w_16 = -2^60 (plonky2's primitive_root_of_unity(4) = 2^156), so
+//   w_16^k, k = 0..7:  1, -2^60, -2^24, 2^84, 2^48, 2^12, -2^72, -2^36
+// (a negative sign is taken by swapping the operands of the subtraction that feeds the shift).
+GL_DEV void gl_dft16(u64 (&x)[16]) {
+  u64 lo[8], hi[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) lo[i] = gl_add(x[i], x[i + 8]);
+  hi[0] = gl_sub(x[0], x[8]);
+  hi[1] = gl_mul_pow2<60>(gl_sub(x[9], x[1]));
+  hi[2] = gl_mul_pow2<24>(gl_sub(x[10], x[2]));
+  hi[3] = gl_mul_pow2<84>(gl_sub(x[3], x[11]));
+  hi[4] = gl_mul_pow2<48>(gl_sub(x[4], x[12]));
+  hi[5] = gl_mul_pow2<12>(gl_sub(x[5], x[13]));
+  hi[6] = gl_mul_pow2<72>(gl_sub(x[14], x[6]));
+  hi[7] = gl_mul_pow2<36>(gl_sub(x[15], x[7]));
+  gl_dft8(lo);
+  gl_dft8(hi);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    x[i] = lo[i];
+    x[i + 8] = hi[i];
+  }
+}
 template <int RHO>
 struct Dft;
 template <>
@@ -75,5 +118,9 @@ struct Dft<2> {
 template <>
 struct Dft<3> {
   static GL_DEV void run(u64 (&x)[8]) { gl_dft8(x); }
+};
+template <>
+struct Dft<4> {
+  static GL_DEV void run(u64 (&x)[16]) { gl_dft16(x); }
 };
 

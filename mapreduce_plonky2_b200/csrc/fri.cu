@@ -294,6 +294,7 @@ Status fri_eval_polys(const u64 *coeffs, size_t stride, size_t ncols, size_t n, 
   MP2_CUDA(cudaMemcpyAsync(d_tab.p, tab.data(), sizeof(u64) * tab.size(), cudaMemcpyHostToDevice, st));
   // the table is pageable host memory: the copy above has been staged when the call returns
   if (ncols > 0x7fffffffull) return "too many polynomials";
+  if (npoints > 65535) return "too many evaluation points for one launch (more than 65535)";
   dim3 grid((unsigned)ncols, (unsigned)npoints, 1);
   { ProfScope _p("k_eval_polys", st); k_eval_polys<<<grid, kEvalT, 0, st>>>(coeffs, stride, n, d_tab.p, out, ncols); }
   MP2_LAUNCH_CHECK();

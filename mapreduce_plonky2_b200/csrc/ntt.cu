@@ -81,9 +81,6 @@ struct LdeMap {  // (column c, leaf L) -> address in the leaf-ordered, column-ma
 #ifndef MP2_NTT_SKEW
 #define MP2_NTT_SKEW 0
 #endif
-#ifndef MP2_NTT_TW_PREFETCH
-#define MP2_NTT_TW_PREFETCH 0
-#endif
 #if MP2_NTT_SKEW
 GL_DEV size_t sidx(size_t a) { return a + (a >> 4); }
 #else
@@ -98,37 +95,26 @@ static inline size_t smem_bytes_for(u32 tile_log) {
 // sm[p*LINES + l].  The current sub-transform length is L = 2^ell; a work item is the R points
 // p = blk*L + j*(L/R) + lo.  After the DFT, the output of frequency r (stored at j = bitrev(r)) is
 // multiplied by w_L^(r*lo) = W[r*lo << (s - ell)], W the root table of the line size 2^s.
+// All tile indices fit 32 bits (a tile is at most 2^14 elements).
 template <int RHO>
 GL_DEV void ntt_pass(u64 *sm, u32 ell, u32 s, u32 lines_log, const u64 *__restrict__ W) {
   constexpr int R = 1 << RHO;
   const u32 sub_log = ell - RHO;
   const u32 items = 1u << (s - RHO + lines_log);
   const u32 lmask = (1u << lines_log) - 1, lomask = (1u << sub_log) - 1;
-  const size_t jstride = (size_t)1 << (sub_log + lines_log);
+  const u32 jstride = 1u << (sub_log + lines_log);
   for (u32 w = threadIdx.x; w < items; w += blockDim.x) {
     const u32 l = w & lmask, q = w >> lines_log;
     const u32 lo = q & lomask, blk = q >> sub_log;
-    // twiddles first: their (L1-resident) loads overlap the shared-memory loads and the DFT
     const u32 e1 = lo << (s - ell);
-#if MP2_NTT_TW_PREFETCH
-    u64 tw[R];
-    if (sub_log) {  // lo == 0 for the last pass: all twiddles are 1
-#pragma unroll
-      for (int j = 1; j < R; j++) tw[j] = __ldg(W + (__brev((u32)j) >> (32 - RHO)) * e1);
-    }
-#endif
-    const size_t a0 = ((((size_t)blk << ell) + lo) << lines_log) + l;
+    const u32 a0 = (((blk << ell) + lo) << lines_log) + l;
     u64 x[R];
 #pragma unroll
     for (int j = 0; j < R; j++) x[j] = sm[sidx(a0 + j * jstride)];
     Dft<RHO>::run(x);
-    if (sub_log) {
+    if (sub_log) {  // lo == 0 for the last pass: all twiddles are 1
 #pragma unroll
-#if MP2_NTT_TW_PREFETCH
-      for (int j = 1; j < R; j++) x[j] = gl_mul(x[j], tw[j]);
-#else
       for (int j = 1; j < R; j++) x[j] = gl_mul(x[j], __ldg(W + (__brev((u32)j) >> (32 - RHO)) * e1));
-#endif
     }
 #pragma unroll
     for (int j = 0; j < R; j++) sm[sidx(a0 + j * jstride)] = x[j];
@@ -136,9 +122,34 @@ GL_DEV void ntt_pass(u64 *sm, u32 ell, u32 s, u32 lines_log, const u64 *__restri
   __syncthreads();
 }
 
-// Full network on a tile: passes of 3 stages while possible; a remainder of 4 is split 2+2.
+// Full network on a tile in ceil(s/4) passes: radix 16 where the stage count needs it, radix 8 otherwise
+// (10 stages = 4+3+3, 12 = 4+4+4, 14 = 4+4+3+3, 9 = 3+3+3): one shared-memory round trip and one general twiddle
+// multiplication per element and PASS, so fewer passes is fewer of both (round 1 ran 3+3+2+2 for 10 stages).
+#ifndef MP2_NTT_RADIX16
+#define MP2_NTT_RADIX16 1
+#endif
 GL_DEV void smem_ntt(u64 *sm, u32 s, u32 lines_log, const u64 *__restrict__ W) {
   u32 ell = s;
+#if MP2_NTT_RADIX16
+  u32 passes = (s + 3) / 4;
+  int fours = (int)s - 3 * (int)passes;  // how many of the passes must be radix 16
+  while (ell) {
+    if (fours > 0 && ell >= 4) {
+      ntt_pass<4>(sm, ell, s, lines_log, W);
+      ell -= 4;
+      fours--;
+    } else if (ell >= 3) {
+      ntt_pass<3>(sm, ell, s, lines_log, W);
+      ell -= 3;
+    } else if (ell == 2) {
+      ntt_pass<2>(sm, ell, s, lines_log, W);
+      ell -= 2;
+    } else {
+      ntt_pass<1>(sm, ell, s, lines_log, W);
+      ell -= 1;
+    }
+  }
+#else
   while (ell) {
     if (ell == 4 || ell == 2) {
       ntt_pass<2>(sm, ell, s, lines_log, W);
@@ -151,6 +162,7 @@ GL_DEV void smem_ntt(u64 *sm, u32 s, u32 lines_log, const u64 *__restrict__ W) {
       ell -= 1;
     }
   }
+#endif
 }
 
 // ---- single pass over global memory: lines are columns ------------------------------------------
@@ -171,7 +183,7 @@ k_intt_single(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ ou
 #pragma unroll
     for (int b = 0; b < MP2_NTT_BATCH; b++) {
       u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> s;
-      if (e < total) sm[sidx(((size_t)p << lines_log) + l)] = v[b];
+      if (e < total) sm[sidx((p << lines_log) + l)] = v[b];
     }
   }
   __syncthreads();
@@ -180,7 +192,7 @@ k_intt_single(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ ou
     u32 i = e & (S - 1), l = e >> s, c = c0 + l;
     u32 k = (S - i) & (S - 1);  // coeffs[i] = fft[(n - i) % n] / n
     if (c < ncols)
-      out[(size_t)c * out_stride + i] = gl_canon(gl_mul(sm[sidx(((size_t)brev_bits(k, s) << lines_log) + l)], n_inv));
+      out[(size_t)c * out_stride + i] = gl_canon(gl_mul(sm[sidx((brev_bits(k, s) << lines_log) + l)], n_inv));
   }
 }
 
@@ -205,15 +217,21 @@ k_lde_single(const u64 *__restrict__ coeffs, size_t in_stride, u64 *__restrict__
 #pragma unroll
     for (int b = 0; b < MP2_NTT_BATCH; b++) {
       u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> s;
-      if (e < total) sm[sidx(((size_t)p << lines_log) + l)] = gl_mul(v[b], f[b]);
+      if (e < total) sm[sidx((p << lines_log) + l)] = gl_mul(v[b], f[b]);
     }
   }
   __syncthreads();
   smem_ntt(sm, s, lines_log, W);
   const size_t block_base = (size_t)brev_bits(k, rate_bits) << s;
+  if (lines_log == 0 && ((block_base ^ (block_base + S - 1)) >> map.ls_log) == 0) {
+    // one column per CTA whose coset block sits in one shard block: base pointer + 32-bit offset
+    u64 *__restrict__ dst = map.ptr(lde, block_base, c0);
+    for (u32 p = threadIdx.x; p < S; p += blockDim.x) dst[p] = gl_canon(sm[sidx(p)]);
+    return;
+  }
   for (u32 e = threadIdx.x; e < (S << lines_log); e += blockDim.x) {
     u32 p = e & (S - 1), l = e >> s, c = c0 + l;
-    if (c < ncols) *map.ptr(lde, block_base + p, c) = gl_canon(sm[sidx(((size_t)p << lines_log) + l)]);
+    if (c < ncols) *map.ptr(lde, block_base + p, c) = gl_canon(sm[sidx((p << lines_log) + l)]);
   }
 }
 
@@ -236,95 +254,116 @@ struct TwoPass {
 //   * 4 adjacent tiles (4 x 32-byte sectors = one 128-byte line of every row) run together, so no fetched
 //     sector is left unused (ordering by column first lost that: 21.5 GB at 256 columns);
 //   * the coset-scale slices of a tile group (1 MB) stay in L2 while the columns sweep over them.
+// Staging note (both passes): a tile's global addresses are base + a 32-bit offset, the base computed once per
+// CTA -- whenever the tile lies inside one shard block of the output map, which is every case except more shards
+// than cosets.  The first version evaluated the 64-bit LdeMap per element: 63 of the 305 instructions per output
+// element in pass 2 were this address arithmetic (profiles/r1f_lde_pass2_opcode_mix.txt).
+GL_DEV bool within_shard(const LdeMap &m, size_t L0, size_t len) { return ((L0 ^ (L0 + len - 1)) >> m.ls_log) == 0; }
+
 __global__ void __launch_bounds__(1024)
 k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
         TwoPass tp, const u64 *__restrict__ W1, const u64 *__restrict__ Wn, const u64 *__restrict__ scale) {
   extern __shared__ u64 sm[];
-  const u32 LINES = 1u << tp.lines_log, S = 1u << tp.a;
-  const size_t n2 = (size_t)1 << tp.b;
+  const u32 lines_log = tp.lines_log, LINES = 1u << lines_log, S = 1u << tp.a, b_log = tp.b;
   const u32 t4 = blockIdx.x & ((1u << tp.tg_log) - 1);
-  const size_t k = (blockIdx.x >> tp.tg_log) & ((1u << tp.rate_bits) - 1);
+  const u32 k = (blockIdx.x >> tp.tg_log) & ((1u << tp.rate_bits) - 1);
   const u32 rest = blockIdx.x >> (tp.tg_log + tp.rate_bits), tg = rest / tp.ncols;
-  const size_t c = rest - tg * tp.ncols;
-  const size_t q0 = (size_t)((tg << tp.tg_log) + t4) * LINES;
-  const u64 *sc = tp.inverse ? nullptr : scale + (k << tp.n_log);
-  const u32 total = S << tp.lines_log, nthr = blockDim.x;
+  const u32 c = rest - tg * tp.ncols;
+  const u32 q0 = ((tg << tp.tg_log) + t4) << lines_log;
+  const u32 total = S << lines_log, nthr = blockDim.x;
+  // element e = p*LINES + l of the tile is input j = p*n2 + q0 + l
+  const u64 *__restrict__ src = in + (size_t)c * in_stride + q0;
+  const u64 *__restrict__ sc = tp.inverse ? nullptr : scale + ((size_t)k << tp.n_log) + q0;
   for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
     u64 v[MP2_NTT_BATCH], f[MP2_NTT_BATCH];
 #pragma unroll
     for (int b = 0; b < MP2_NTT_BATCH; b++) {
-      u32 e = e0 + b * nthr, l = e & (LINES - 1), p = e >> tp.lines_log;
-      size_t j = (size_t)p * n2 + q0 + l;
-      v[b] = e < total ? in[c * in_stride + j] : 0;
-      f[b] = (e < total && !tp.inverse) ? __ldg(sc + j) : 1;
+      const u32 e = e0 + b * nthr, off = ((e >> lines_log) << b_log) + (e & (LINES - 1));
+      v[b] = e < total ? src[off] : 0;
+      f[b] = (e < total && !tp.inverse) ? __ldg(sc + off) : 1;
     }
 #pragma unroll
     for (int b = 0; b < MP2_NTT_BATCH; b++) {
-      u32 e = e0 + b * nthr;
-      if (e < total) sm[sidx(e)] = tp.inverse ? v[b] : gl_mul(v[b], f[b]);  // element p*LINES + l
+      const u32 e = e0 + b * nthr;
+      if (e < total) sm[sidx(e)] = tp.inverse ? v[b] : gl_mul(v[b], f[b]);
     }
   }
   __syncthreads();
-  smem_ntt(sm, tp.a, tp.lines_log, W1);
-  const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
+  smem_ntt(sm, tp.a, lines_log, W1);
+  const size_t block_base = (size_t)brev_bits(k, tp.rate_bits) << tp.n_log;
+  // output: inverse -> row k1 (natural) of the scratch matrix; LDE -> row p = bitrev(k1) of leaf block bitrev_r(k)
+  const bool fast = tp.inverse || map.ls_log >= tp.n_log;  // the whole coset block sits in one shard block
+  u64 *__restrict__ dst = tp.inverse ? out + (size_t)c * out_stride + q0 : fast ? out + map(block_base + q0, c) : out;
+  if (!fast) {  // more shards than cosets: per-element map
+    for (u32 e = threadIdx.x; e < total; e += nthr) {
+      const u32 l = e & (LINES - 1), p = e >> lines_log;
+      out[map(block_base + ((size_t)p << b_log) + q0 + l, c)] = gl_mul(sm[sidx(e)], __ldg(Wn + (q0 + l) * brev_bits(p, tp.a)));
+    }
+    return;
+  }
   for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
     u64 w[MP2_NTT_BATCH];
+    u32 row[MP2_NTT_BATCH];
 #pragma unroll
     for (int b = 0; b < MP2_NTT_BATCH; b++) {
-      u32 e = e0 + b * nthr, l = e & (LINES - 1), p = e >> tp.lines_log;
-      w[b] = e < total ? __ldg(Wn + (q0 + l) * (size_t)brev_bits(p, tp.a)) : 0;  // w_n^(j2*k1), j2*k1 < n
+      const u32 e = e0 + b * nthr, l = e & (LINES - 1), p = e >> lines_log, k1 = brev_bits(p, tp.a);
+      w[b] = e < total ? __ldg(Wn + (q0 + l) * k1) : 0;  // w_n^(j2*k1), j2*k1 < n <= 2^26
+      row[b] = ((tp.inverse ? k1 : p) << b_log) + l;
     }
 #pragma unroll
     for (int b = 0; b < MP2_NTT_BATCH; b++) {
-      u32 e = e0 + b * nthr, l = e & (LINES - 1), p = e >> tp.lines_log;
-      if (e >= total) continue;
-      size_t j2 = q0 + l, k1 = brev_bits(p, tp.a);
-      u64 v = gl_mul(sm[sidx(e)], w[b]);
-      if (tp.inverse) out[c * out_stride + k1 * n2 + j2] = v;       // row k1 (natural)
-      else out[map(block_base + (size_t)p * n2 + j2, c)] = v;       // row bitrev(k1) = p
+      const u32 e = e0 + b * nthr;
+      if (e < total) dst[row[b]] = gl_mul(sm[sidx(e)], w[b]);
     }
   }
 }
 
-// pass 2: tile = LINES adjacent rows; size-n2 transform along each (contiguous) row.
-// grid = (n1 / LINES, ncols, cosets)
+// pass 2: tile = LINES adjacent rows; size-n2 transform along each (contiguous) row: the tile is `total`
+// consecutive elements on both sides.  grid = (n1 / LINES, ncols, cosets)
 __global__ void __launch_bounds__(1024)
 k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
         LdeMap out_map, TwoPass tp, const u64 *__restrict__ W2) {
   extern __shared__ u64 sm[];
-  const u32 LINES = 1u << tp.lines_log, S = 1u << tp.b;
-  const size_t n = (size_t)1 << tp.n_log, n1 = (size_t)1 << tp.a, n2 = (size_t)1 << tp.b;
-  const size_t c = blockIdx.y, r0 = (size_t)blockIdx.x * LINES;
-  const size_t k = out_map.peer ? brev_bits((blockIdx.z + out_map.coset_rot) & ((1u << tp.rate_bits) - 1), tp.rate_bits)
-                                : blockIdx.z + tp.coset0;
-  const size_t block_base = (size_t)brev_bits((u32)k, tp.rate_bits) << tp.n_log;
-  const u32 total = S << tp.lines_log, nthr = blockDim.x;
-  for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
-    u64 v[MP2_NTT_BATCH];
+  const u32 lines_log = tp.lines_log, LINES = 1u << lines_log, S = 1u << tp.b, b_log = tp.b;
+  const u32 n = 1u << tp.n_log;
+  const u32 c = blockIdx.y, r0 = blockIdx.x << lines_log;
+  const u32 k = out_map.peer ? brev_bits((blockIdx.z + out_map.coset_rot) & ((1u << tp.rate_bits) - 1), tp.rate_bits)
+                             : blockIdx.z + tp.coset0;
+  const size_t block_base = (size_t)brev_bits(k, tp.rate_bits) << tp.n_log;
+  const size_t L0 = block_base + ((size_t)r0 << b_log);  // first element of the tile
+  const u32 total = S << lines_log, nthr = blockDim.x;
+  const bool in_fast = tp.inverse || within_shard(map, L0, total);
+  if (in_fast) {  // (uniform per CTA) the tile is `total` consecutive elements
+    const u64 *__restrict__ src = tp.inverse ? in + (size_t)c * in_stride + ((size_t)r0 << b_log) : in + map(L0, c);
+    for (u32 e0 = threadIdx.x; e0 < total; e0 += MP2_NTT_BATCH * nthr) {
+      u64 v[MP2_NTT_BATCH];
 #pragma unroll
-    for (int b = 0; b < MP2_NTT_BATCH; b++) {
-      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> tp.b;
-      size_t row = r0 + l;
-      v[b] = e >= total ? 0 : tp.inverse ? in[c * in_stride + row * n2 + p] : in[map(block_base + row * n2 + p, c)];
-    }
+      for (int b = 0; b < MP2_NTT_BATCH; b++) v[b] = e0 + b * nthr < total ? src[e0 + b * nthr] : 0;
 #pragma unroll
-    for (int b = 0; b < MP2_NTT_BATCH; b++) {
-      u32 e = e0 + b * nthr, p = e & (S - 1), l = e >> tp.b;
-      if (e < total) sm[sidx(((size_t)p << tp.lines_log) + l)] = v[b];
-    }
-  }
-  __syncthreads();
-  smem_ntt(sm, tp.b, tp.lines_log, W2);
-  if (tp.inverse) {
-    for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
-      u32 l = e & (LINES - 1), p = e >> tp.lines_log;
-      size_t kk = (r0 + l) + n1 * brev_bits(p, tp.b);  // forward frequency k = k1 + n1*k2
-      out[c * out_stride + ((n - kk) & (n - 1))] = gl_canon(gl_mul(sm[sidx(e)], tp.n_inv));
+      for (int b = 0; b < MP2_NTT_BATCH; b++) {
+        const u32 e = e0 + b * nthr;
+        if (e < total) sm[sidx(((e & (S - 1)) << lines_log) + (e >> b_log))] = v[b];
+      }
     }
   } else {
-    for (u32 e = threadIdx.x; e < (S << tp.lines_log); e += blockDim.x) {
-      u32 p = e & (S - 1), l = e >> tp.b;
-      *out_map.ptr(out, block_base + (r0 + l) * n2 + p, c) = gl_canon(sm[sidx(((size_t)p << tp.lines_log) + l)]);
+    for (u32 e = threadIdx.x; e < total; e += nthr) sm[sidx(((e & (S - 1)) << lines_log) + (e >> b_log))] = in[map(L0 + e, c)];
+  }
+  __syncthreads();
+  smem_ntt(sm, tp.b, lines_log, W2);
+  if (tp.inverse) {
+    u64 *__restrict__ dst = out + (size_t)c * out_stride;
+    for (u32 e = threadIdx.x; e < total; e += nthr) {
+      const u32 l = e & (LINES - 1), p = e >> lines_log;
+      const u32 kk = (r0 + l) + (brev_bits(p, tp.b) << tp.a);  // forward frequency k = k1 + n1*k2
+      dst[(n - kk) & (n - 1)] = gl_canon(gl_mul(sm[sidx(e)], tp.n_inv));
+    }
+  } else {
+    if (within_shard(out_map, L0, total)) {
+      u64 *__restrict__ dst = out_map.ptr(out, L0, c);
+      for (u32 e = threadIdx.x; e < total; e += nthr) dst[e] = gl_canon(sm[sidx(((e & (S - 1)) << lines_log) + (e >> b_log))]);
+    } else {
+      for (u32 e = threadIdx.x; e < total; e += nthr)
+        *out_map.ptr(out, L0 + e, c) = gl_canon(sm[sidx(((e & (S - 1)) << lines_log) + (e >> b_log))]);
     }
   }
 }
@@ -394,6 +433,7 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
   }
   TwoPass tp;
   MP2_TRY(split_two_pass(n_log, &tp));
+  if (ncols > 65535) return "batch too wide for one iNTT launch (more than 65535 columns at this degree): split the columns";
   tp.rate_bits = 0;
   tp.inverse = 1;
   tp.n_inv = n_inv;
@@ -499,6 +539,7 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     }
   }
   tp.coset0 = 0;
+  if (ncols > 65535) return "batch too wide for one LDE launch (more than 65535 columns at this degree): split the columns";
   if (phase != LDE_PASS2) {
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);

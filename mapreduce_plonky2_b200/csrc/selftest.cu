@@ -46,7 +46,7 @@ __device__ u32 corner32(u32 i) {
   return tab[i & 7];
 }
 
-enum { T_ADD, T_ADDC, T_SUB, T_MUL, T_SQR, T_MULADD, T_REDUCE, T_POW7, T_SHIFT24, T_SHIFT48, T_SHIFT72, T_COUNT };
+enum { T_ADD, T_ADDC, T_SUB, T_MUL, T_SQR, T_MULADD, T_REDUCE, T_POW7, T_SHIFT24, T_SHIFT48, T_SHIFT72, T_POW2, T_DFT8, T_DFT16, T_COUNT };
 
 // one thread per (i, j) pair of an NV x NV grid of corner/random values
 __global__ void k_field_selftest(u32 nv, u64 seed, unsigned long long *bad) {
@@ -76,6 +76,42 @@ __global__ void k_field_selftest(u32 nv, u64 seed, unsigned long long *bad) {
     const u64 x = a ^ (b << 1);
     const u64 x72 = ref_mod((u128)ref_mod((u128)x << 48) << 24);
     check(T_SHIFT72, gl_mul_2_72(x), x72);
+  }
+  {  // every shift the radix-16 butterfly uses
+    const u64 x = a ^ (b >> 1);
+    auto sh = [&](int k) { u64 r = ref_mod((u128)x); for (int i = 0; i < k; i++) r = ref_mod((u128)r << 1); return r; };
+    check(T_POW2, gl_mul_pow2<12>(x), sh(12));
+    check(T_POW2, gl_mul_pow2<24>(x), sh(24));
+    check(T_POW2, gl_mul_pow2<36>(x), sh(36));
+    check(T_POW2, gl_mul_pow2<48>(x), sh(48));
+    check(T_POW2, gl_mul_pow2<60>(x), sh(60));
+    check(T_POW2, gl_mul_pow2<72>(x), sh(72));
+    check(T_POW2, gl_mul_pow2<84>(x), sh(84));
+  }
+  if ((t & 15) == 0) {  // the shift-twiddle butterflies against the DFT by definition, w_16 = 2^156 = -2^60, w_8 = w_16^2
+    u64 w16 = 1;
+    for (int k = 0; k < 156; k++) w16 = ref_mod((u128)w16 << 1);
+    u64 in[16], pw[16];
+    pw[0] = 1;
+    for (int k = 1; k < 16; k++) pw[k] = ref_mod((u128)pw[k - 1] * w16);
+    for (int k = 0; k < 16; k++) in[k] = corner64((i + 3 * k) % nv, seed) ^ corner64((j + 5 * k) % nv, seed ^ 0x77);
+    u64 x16[16], x8[8];
+    for (int k = 0; k < 16; k++) x16[k] = in[k];
+    for (int k = 0; k < 8; k++) x8[k] = in[k];
+    gl_dft16(x16);
+    gl_dft8(x8);
+    for (int pos = 0; pos < 16; pos++) {
+      const int f = (int)(__brev((u32)pos) >> 28);
+      u64 acc = 0;
+      for (int k = 0; k < 16; k++) acc = ref_mod((u128)acc + (u128)ref_mod((u128)in[k]) * pw[(f * k) & 15]);
+      check(T_DFT16, x16[pos], acc);
+    }
+    for (int pos = 0; pos < 8; pos++) {
+      const int f = (int)(__brev((u32)pos) >> 29);
+      u64 acc = 0;
+      for (int k = 0; k < 8; k++) acc = ref_mod((u128)acc + (u128)ref_mod((u128)in[k]) * pw[(2 * f * k) & 15]);
+      check(T_DFT8, x8[pos], acc);
+    }
   }
   // reduce128w over all 8^4 corner-word combinations (first 4096 threads) and over the value grid
   {
@@ -139,7 +175,7 @@ const char *mp2gpu_debug_field_selftest(uint64_t *mismatches_out, size_t ntests)
     if (p) memcpy(p, s.c_str(), s.size() + 1);
     return p;
   };
-  if (!mismatches_out || ntests < T_COUNT) return fail("mismatches_out must hold at least 11 counters");
+  if (!mismatches_out || ntests < T_COUNT) return fail("mismatches_out must hold at least 14 counters");
   unsigned long long *bad = nullptr;
   if (cudaMalloc(&bad, sizeof(unsigned long long) * T_COUNT) != cudaSuccess)
     return fail("no usable CUDA device (this library has no CPU fallback)");

@@ -8,7 +8,8 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ["add", "add_canonical", "sub", "mul", "sqr", "mul_add", "reduce128", "pow7", "mul_2^24", "mul_2^48", "mul_2^72"]
+NAMES = ["add", "add_canonical", "sub", "mul", "sqr", "mul_add", "reduce128", "pow7", "mul_2^24", "mul_2^48", "mul_2^72",
+         "mul_2^(12j)", "dft8", "dft16"]
 
 
 def test_field_primitives_exact_on_corner_and_random_operands():
