@@ -281,12 +281,16 @@ const char *mp2gpu_debug_int_pipe_peak(double *imad_per_clk_per_sm, double *sm_c
                                        double *t_imad_per_s);
 
 /* Device self-test of the Goldilocks primitives (add, add-canonical, sub, mul, sqr, mul-add, reduce128, x^7,
- * the three shift twiddles, every 2^(12 j) shift, the 8- and 16-point shift-twiddle butterflies -- in that
- * order) against 128-bit arithmetic / the DFT by definition, over all pairs of 48 corner values around
- * 0 / 2^32 / 2^63 / p / 2^64 and 976 pseudo-random ones.  mismatches_out[i] = number of wrong results of
- * test i (ntests >= 14).  Replaces plonky2_field's goldilocks_field unit tests for the
+ * the three shift twiddles, every 2^(12 j) shift -- in that order) against 128-bit arithmetic by definition,
+ * over all pairs of 48 corner values around 0 / 2^32 / 2^63 / p / 2^64 and 976 pseudo-random ones.
+ * mismatches_out[i] = number of wrong results of test i (ntests >= 12).  (The 8- and 16-point butterflies are
+ * checked from the host through mp2gpu_debug_dft.)  Replaces plonky2_field's goldilocks_field unit tests for the
  * GPU arithmetic. */
 const char *mp2gpu_debug_field_selftest(uint64_t *mismatches_out, size_t ntests);
+/* Runs `count` independent 2^log_points-point shift-twiddle butterflies (log_points = 3 or 4; csrc/dft.cuh) in
+ * place on io (count * 2^log_points elements, any u64 in, canonical out): output position j holds the DFT value of
+ * frequency bitrev(j) for plonky2's primitive_root_of_unity(log_points).  Test hook. */
+const char *mp2gpu_debug_dft(uint64_t *io, uint32_t log_points, size_t count);
 /* Register-only throughput of the two arithmetic inner loops, thread-level operations per (nominal) clock per
  * SM: out[0] = x^7 S-boxes, out[1] = radix-8 butterfly elements (each butterfly + 7 twiddle multiplications). */
 const char *mp2gpu_debug_field_probe(double *ops_per_clk_per_sm_out);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mp2gpu_profile_report": (_ERR, [C.c_char_p, C.c_size_t]),
     "mp2gpu_debug_int_pipe_peak": (_ERR, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mp2gpu_debug_field_selftest": (_ERR, [u64p, C.c_size_t]),
+    "mp2gpu_debug_dft": (_ERR, [u64p, C.c_uint32, C.c_size_t]),
     "mp2gpu_debug_field_probe": (_ERR, [C.POINTER(C.c_double)]),
     "mp2gpu_launch_count": (C.c_uint64, []),
 }

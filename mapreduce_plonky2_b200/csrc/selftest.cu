@@ -46,7 +46,7 @@ __device__ u32 corner32(u32 i) {
   return tab[i & 7];
 }
 
-enum { T_ADD, T_ADDC, T_SUB, T_MUL, T_SQR, T_MULADD, T_REDUCE, T_POW7, T_SHIFT24, T_SHIFT48, T_SHIFT72, T_POW2, T_DFT8, T_DFT16, T_COUNT };
+enum { T_ADD, T_ADDC, T_SUB, T_MUL, T_SQR, T_MULADD, T_REDUCE, T_POW7, T_SHIFT24, T_SHIFT48, T_SHIFT72, T_POW2, T_COUNT };
 
 // one thread per (i, j) pair of an NV x NV grid of corner/random values
 __global__ void k_field_selftest(u32 nv, u64 seed, unsigned long long *bad) {
@@ -87,31 +87,6 @@ __global__ void k_field_selftest(u32 nv, u64 seed, unsigned long long *bad) {
     check(T_POW2, gl_mul_pow2<60>(x), sh(60));
     check(T_POW2, gl_mul_pow2<72>(x), sh(72));
     check(T_POW2, gl_mul_pow2<84>(x), sh(84));
-  }
-  if ((t & 15) == 0) {  // the shift-twiddle butterflies against the DFT by definition, w_16 = 2^156 = -2^60, w_8 = w_16^2
-    u64 w16 = 1;
-    for (int k = 0; k < 156; k++) w16 = ref_mod((u128)w16 << 1);
-    u64 in[16], pw[16];
-    pw[0] = 1;
-    for (int k = 1; k < 16; k++) pw[k] = ref_mod((u128)pw[k - 1] * w16);
-    for (int k = 0; k < 16; k++) in[k] = corner64((i + 3 * k) % nv, seed) ^ corner64((j + 5 * k) % nv, seed ^ 0x77);
-    u64 x16[16], x8[8];
-    for (int k = 0; k < 16; k++) x16[k] = in[k];
-    for (int k = 0; k < 8; k++) x8[k] = in[k];
-    gl_dft16(x16);
-    gl_dft8(x8);
-    for (int pos = 0; pos < 16; pos++) {
-      const int f = (int)(__brev((u32)pos) >> 28);
-      u64 acc = 0;
-      for (int k = 0; k < 16; k++) acc = ref_mod((u128)acc + (u128)ref_mod((u128)in[k]) * pw[(f * k) & 15]);
-      check(T_DFT16, x16[pos], acc);
-    }
-    for (int pos = 0; pos < 8; pos++) {
-      const int f = (int)(__brev((u32)pos) >> 29);
-      u64 acc = 0;
-      for (int k = 0; k < 8; k++) acc = ref_mod((u128)acc + (u128)ref_mod((u128)in[k]) * pw[(2 * f * k) & 15]);
-      check(T_DFT8, x8[pos], acc);
-    }
   }
   // reduce128w over all 8^4 corner-word combinations (first 4096 threads) and over the value grid
   {
@@ -162,6 +137,27 @@ __global__ void __launch_bounds__(256) k_probe_dft8(u64 *out, int trips) {
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// one butterfly per thread on caller data (host-checked against the DFT by definition in tests/test_gpu_field.py)
+__global__ void k_debug_dft(u64 *io, u32 log_points, size_t count) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  if (log_points == 4) {
+    u64 x[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = io[16 * t + k];
+    gl_dft16(x);
+#pragma unroll
+    for (int k = 0; k < 16; k++) io[16 * t + k] = gl_canon(x[k]);
+  } else {
+    u64 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) x[k] = io[8 * t + k];
+    gl_dft8(x);
+#pragma unroll
+    for (int k = 0; k < 8; k++) io[8 * t + k] = gl_canon(x[k]);
+  }
+}
+
 }  // namespace
 }  // namespace mp2
 
@@ -175,7 +171,7 @@ const char *mp2gpu_debug_field_selftest(uint64_t *mismatches_out, size_t ntests)
     if (p) memcpy(p, s.c_str(), s.size() + 1);
     return p;
   };
-  if (!mismatches_out || ntests < T_COUNT) return fail("mismatches_out must hold at least 14 counters");
+  if (!mismatches_out || ntests < T_COUNT) return fail("mismatches_out must hold at least 12 counters");
   unsigned long long *bad = nullptr;
   if (cudaMalloc(&bad, sizeof(unsigned long long) * T_COUNT) != cudaSuccess)
     return fail("no usable CUDA device (this library has no CPU fallback)");
@@ -193,6 +189,22 @@ const char *mp2gpu_debug_field_selftest(uint64_t *mismatches_out, size_t ntests)
   cudaFree(bad);
   for (size_t i = 0; i < ntests; i++) mismatches_out[i] = i < T_COUNT ? h[i] : 0;
   return nullptr;
+}
+
+const char *mp2gpu_debug_dft(uint64_t *io, uint32_t log_points, size_t count) {
+  auto fail = [](const char *s) -> const char * { return strdup(s); };
+  if (!io || (log_points != 3 && log_points != 4)) return fail("mp2gpu_debug_dft: io must be non-null and log_points 3 or 4");
+  if (!count) return nullptr;
+  const size_t elems = count << log_points;
+  u64 *d = nullptr;
+  if (cudaMalloc(&d, elems * sizeof(u64)) != cudaSuccess) return fail("no usable CUDA device (this library has no CPU fallback)");
+  cudaMemcpy(d, io, elems * sizeof(u64), cudaMemcpyHostToDevice);
+  k_debug_dft<<<(unsigned)((count + 127) / 128), 128>>>(d, log_points, count);
+  count_launch();
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) cudaMemcpy(io, d, elems * sizeof(u64), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return e == cudaSuccess ? nullptr : fail(cudaGetErrorString(e));
 }
 
 // thread-level operations per clock per SM: out[0] = x^7 (S-box layer shape), out[1] = radix-8 butterfly

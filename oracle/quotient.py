@@ -1,0 +1,116 @@
+"""CPU ORACLE (test infrastructure, NOT the product): plonky2 0.2.2 `compute_quotient_polys` restated
+(plonk/prover.rs + plonk/vanishing_poly.rs `eval_vanishing_poly_base_batch`).
+
+The prover evaluates, at every point x_i = g * w_{8n}^i of the coset LDE the three committed batches already hold
+(`get_lde_values(i, step)` = leaf bitrev(i * step)):
+
+    terms_i = [ L_0(x)(Z_c(x) - 1) ]_c  ++  [ check_partial_products(...) ]_c  ++  gate constraints
+    q_c(x_i) = reduce_with_powers(terms_i, alpha_c) / Z_H(x_i)
+
+then `coset_ifft` turns each q_c into coefficients and cuts it into `quotient_degree_factor` chunks of n, which are
+committed with `from_coeffs`.  Gate set restated here (the staged subset of
+mp2-common/src/serialization/circuit_data_serialization.rs:234-266): ArithmeticGate, ConstantGate, PublicInputGate,
+NoopGate behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
+
+Pinned by definition, not by the Rust prover (absent): tests/plonk_ref.py restates the VERIFIER's
+`eval_vanishing_poly` + final identity, and the quotients computed here must pass it at random points
+(tests/test_quotient_oracle.py) -- prove, then verify, as every `run_circuit` test of the reference does.
+`desc` is any object with the attributes of tests/plonk_ref.Circuit / mapreduce_plonky2_b200.quotient.CircuitDesc.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as O
+
+P = O.P
+UNUSED_SELECTOR = (1 << 32) - 1
+COSET_SHIFT = 7
+
+
+def _gate_constraints(desc, local_constants, local_wires, pi_hash):
+    out = [0] * desc.num_gate_constraints
+    many = desc.num_selectors > 1
+    gc = local_constants[desc.num_selectors:]
+    for g, gate in enumerate(desc.gates):
+        sel = desc.selector_indices[g]
+        s = local_constants[sel]
+        a, b = desc.groups[sel]
+        filt = 1
+        for j in range(a, b):
+            if j != g:
+                filt = filt * (j - s) % P
+        if many:
+            filt = filt * (UNUSED_SELECTOR - s) % P
+        if gate.kind == "arithmetic":
+            cons = [(local_wires[4 * i + 3] - (gc[0] * local_wires[4 * i] * local_wires[4 * i + 1] + gc[1] * local_wires[4 * i + 2])) % P
+                    for i in range(gate.num_ops)]
+        elif gate.kind == "constant":
+            cons = [(gc[i] - local_wires[i]) % P for i in range(gate.num_ops)]
+        elif gate.kind == "public_input":
+            cons = [(local_wires[i] - pi_hash[i]) % P for i in range(4)]
+        elif gate.kind == "noop":
+            cons = []
+        else:
+            raise ValueError("gate kind %r is outside the staged subset" % gate.kind)
+        for i, v in enumerate(cons):
+            out[i] = (out[i] + filt * v) % P
+    return out
+
+
+def compute_quotient_polys(desc, constants_sigmas_coeffs, wires_coeffs, zs_pp_coeffs, betas, gammas, alphas, pi_hash):
+    """-> (num_challenges * quotient_degree_factor, n) coefficient chunks, challenge-major (what `from_coeffs` commits).
+    Inputs: coefficient matrices (ncols, n) of the three committed batches; constants_sigmas columns are
+    [selectors, gate constants, sigmas]; zs_pp columns are [Z_c..., partial products of c = 0, of c = 1, ...]."""
+    n = 1 << desc.degree_bits
+    qb = desc.quotient_degree_bits
+    N, md, nch, R, npp = n << qb, 1 << qb, desc.num_challenges, desc.num_routed_wires, desc.num_partial_products
+    lde = lambda m: np.stack([O.coset_lde(np.asarray(col, dtype=np.uint64), qb) for col in m])   # values at g*w_N^i, natural i
+    cs, wi, zp = lde(constants_sigmas_coeffs), lde(wires_coeffs), lde(zs_pp_coeffs)
+    w_N = O.root_of_unity(desc.degree_bits + qb)
+    k_is = [pow(COSET_SHIFT, j, P) for j in range(R)]
+    # ZeroPolyOnCoset: Z_H(g w_N^i) = g^n * w_{2^qb}^(i mod 2^qb) - 1
+    g_pow_n = pow(COSET_SHIFT, n, P)
+    w_rate = O.root_of_unity(qb)
+    zh = [(g_pow_n * pow(w_rate, i, P) - 1) % P for i in range(md)]
+    zh_inv = [pow(v, P - 2, P) for v in zh]
+    n_inv_dummy = None  # noqa: F841 (L_0 uses n * (x - 1), inverted per point)
+    out = np.zeros((nch, N), dtype=np.uint64)
+    x = 1
+    for i in range(N):
+        sx = COSET_SHIFT * x % P                      # shifted_x
+        i_next = (i + md) % N                         # next_step = 2^quotient_degree_bits
+        local_constants = [int(v) for v in cs[:desc.num_constants, i]]
+        s_sigmas = [int(v) for v in cs[desc.num_constants:desc.num_constants + R, i]]
+        local_wires = [int(v) for v in wi[:, i]]
+        l_0 = zh[i % md] * pow(n * (sx - 1) % P, P - 2, P) % P
+        z1, pp_terms = [], []
+        for c in range(nch):
+            z_x, z_gx = int(zp[c, i]), int(zp[c, i_next])
+            z1.append(l_0 * (z_x - 1) % P)
+            accs = [z_x] + [int(zp[nch + c * npp + k, i]) for k in range(npp)] + [z_gx]
+            for q, s in enumerate(range(0, R, md)):
+                pn = pd = 1
+                for j in range(s, min(s + md, R)):
+                    pn = pn * ((local_wires[j] + betas[c] * (k_is[j] * sx % P) + gammas[c]) % P) % P
+                    pd = pd * ((local_wires[j] + betas[c] * s_sigmas[j] + gammas[c]) % P) % P
+                pp_terms.append((accs[q] * pn - accs[q + 1] * pd) % P)
+        terms = z1 + pp_terms + _gate_constraints(desc, local_constants, local_wires, pi_hash)
+        for c in range(nch):
+            acc = 0
+            for t in reversed(terms):
+                acc = (acc * alphas[c] + t) % P
+            out[c, i] = acc * zh_inv[i % md] % P
+        x = x * w_N % P
+    # coset_ifft(g): interpolate on the subgroup, then undo the shift coefficient by coefficient
+    chunks = []
+    g_inv = pow(COSET_SHIFT, P - 2, P)
+    for c in range(nch):
+        co = O.ifft(out[c])
+        sc, scaled = 1, np.zeros(N, dtype=np.uint64)
+        for j in range(N):
+            scaled[j] = int(co[j]) * sc % P
+            sc = sc * g_inv % P
+        # quotient_poly.trim_to_len(quotient_degree) is a no-op at length 8n; chunks(degree)
+        chunks.extend(scaled[k * n:(k + 1) * n] for k in range(md))
+    return np.stack(chunks)

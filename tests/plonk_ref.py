@@ -1,0 +1,303 @@
+"""By-definition PLONK pieces around the quotient polynomial (plonky2 0.2.2 `plonk/prover.rs`, `plonk/vanishing_poly.rs`,
+`plonk/permutation_argument.rs`) -- TEST INFRASTRUCTURE, pure Python integers.
+
+What is here, and why it can judge the GPU's quotient polynomials without the Rust prover:
+
+* :func:`synthetic_instance` builds a small circuit in plonky2's shape (arithmetic / constant / public-input / noop
+  gates behind selector polynomials, copy constraints as a permutation of the routed wire cells, `k_i = 7^i` coset
+  shifts) together with a witness that satisfies it, the sigma polynomials, and -- for given betas / gammas -- the
+  Z and partial-product columns exactly as `wires_permutation_partial_products_and_zs` lays them out.
+* :func:`eval_vanishing_poly` restates the VERIFIER's `eval_vanishing_poly` at one point zeta from polynomial
+  openings, and :func:`check_quotient_identity` its final check
+  `vanishing(zeta) == Z_H(zeta) * sum_k zeta^(k n) t_k(zeta)` per challenge.
+  A quotient (the prover's output) passes that check at random points iff it is the right polynomial, so the
+  prover-side code (oracle restatement and CUDA kernel, which work pointwise on the 8n coset) is pinned to the
+  verifier's equation the same way every `run_circuit` test of the reference pins it: prove, then verify.
+
+Gate semantics restated (plonky2 `gates/`): ArithmeticGate `out - (c0 * x * y + c1 * z)` per op on wires 4i..4i+3;
+ConstantGate `const_i - wire_i`; PublicInputGate `wire_i - public_inputs_hash[i]`; NoopGate nothing.  Selector
+filter of gate g in group [a, b): `prod_{j in [a, b), j != g} (j - s) * (UNUSED - s if several groups)`,
+UNUSED_SELECTOR = 2^32 - 1; gate constants follow the selector columns.
+"""
+from __future__ import annotations
+
+import random
+from dataclasses import dataclass, field
+from typing import Dict, List, Tuple
+
+import pyref as R
+
+P = R.P
+UNUSED_SELECTOR = (1 << 32) - 1
+COSET_SHIFT = 7
+
+
+@dataclass
+class Gate:
+    kind: str           # "arithmetic" | "constant" | "public_input" | "noop"
+    num_ops: int = 0    # arithmetic: ops per row (4 wires each); constant: number of constants
+
+    @property
+    def num_constraints(self) -> int:
+        return {"arithmetic": self.num_ops, "constant": self.num_ops, "public_input": 4, "noop": 0}[self.kind]
+
+    @property
+    def num_constants(self) -> int:
+        return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0}[self.kind]
+
+
+@dataclass
+class Circuit:
+    degree_bits: int
+    num_wires: int
+    num_routed_wires: int
+    gates: List[Gate]
+    selector_indices: List[int]            # per gate: which selector column
+    groups: List[Tuple[int, int]]          # per selector column: the gate index range it encodes
+    quotient_degree_bits: int = 3
+    num_challenges: int = 2
+
+    @property
+    def n(self) -> int:
+        return 1 << self.degree_bits
+
+    @property
+    def max_degree(self) -> int:           # quotient_degree_factor
+        return 1 << self.quotient_degree_bits
+
+    @property
+    def num_selectors(self) -> int:
+        return len(self.groups)
+
+    @property
+    def num_gate_constants(self) -> int:
+        return max(g.num_constants for g in self.gates)
+
+    @property
+    def num_constants(self) -> int:        # CommonCircuitData::num_constants (selectors included)
+        return self.num_selectors + self.num_gate_constants
+
+    @property
+    def num_gate_constraints(self) -> int:
+        return max(g.num_constraints for g in self.gates)
+
+    @property
+    def num_partial_products(self) -> int:
+        return -(-self.num_routed_wires // self.max_degree) - 1
+
+    @property
+    def k_is(self) -> List[int]:           # get_unique_coset_shifts: powers of the multiplicative generator
+        return [pow(COSET_SHIFT, i, P) for i in range(self.num_routed_wires)]
+
+
+@dataclass
+class Instance:
+    circuit: Circuit
+    row_gate: List[int]                    # gate index per row
+    constants: List[List[int]]             # num_constants columns x n   (selectors first)
+    sigmas: List[List[int]]                # num_routed_wires columns x n
+    wires: List[List[int]]                 # num_wires columns x n
+    public_inputs_hash: List[int]
+    sigma_map: Dict[Tuple[int, int], Tuple[int, int]] = field(default_factory=dict)
+
+
+def subgroup(bits: int) -> List[int]:
+    w = R.root_of_unity(bits)
+    out, x = [], 1
+    for _ in range(1 << bits):
+        out.append(x)
+        x = x * w % P
+    return out
+
+
+def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num_routed_wires: int = 8,
+                       two_groups: bool = False) -> Instance:
+    rng = random.Random(seed)
+    n = 1 << degree_bits
+    num_ops = num_routed_wires // 4
+    gates = [Gate("arithmetic", num_ops), Gate("constant", 2), Gate("noop"), Gate("public_input")]
+    if two_groups:
+        selector_indices, groups = [0, 0, 1, 1], [(0, 2), (2, 4)]
+    else:
+        selector_indices, groups = [0, 0, 0, 0], [(0, 4)]
+    c = Circuit(degree_bits, num_wires, num_routed_wires, gates, selector_indices, groups)
+    pi_hash = [rng.randrange(P) for _ in range(4)]
+    row_gate = [3] + [rng.choice([0, 0, 0, 1, 2]) for _ in range(n - 1)]     # row 0: the public-input gate
+    consts = [[0] * n for _ in range(c.num_constants)]
+    for row, g in enumerate(row_gate):
+        for s, (a, b) in enumerate(groups):
+            consts[s][row] = g if a <= g < b else UNUSED_SELECTOR
+        for k in range(c.num_gate_constants):
+            consts[c.num_selectors + k][row] = rng.randrange(P) if k < gates[g].num_constants else rng.randrange(P)
+    wires = [[rng.randrange(P) for _ in range(n)] for _ in range(num_wires)]
+    # copy constraints: some inputs of later arithmetic rows are wired to outputs of earlier ones; noop rows take copies
+    parent: Dict[Tuple[int, int], Tuple[int, int]] = {}
+
+    def find(x):
+        while parent.get(x, x) != x:
+            x = parent[x]
+        return x
+
+    outputs: List[Tuple[int, int]] = []
+    for row, g in enumerate(row_gate):
+        if g == 0:
+            for op in range(num_ops):
+                for slot in range(3):
+                    if outputs and rng.random() < 0.4:
+                        src = rng.choice(outputs)
+                        cell = (4 * op + slot, row)
+                        wires[cell[0]][row] = wires[src[0]][src[1]]
+                        parent[find(cell)] = find(src)
+                c0, c1 = consts[c.num_selectors][row], consts[c.num_selectors + 1][row]
+                x, y, z = (wires[4 * op + k][row] for k in range(3))
+                wires[4 * op + 3][row] = (c0 * x * y + c1 * z) % P
+                outputs.append((4 * op + 3, row))
+        elif g == 1:
+            for k in range(2):
+                wires[k][row] = consts[c.num_selectors + k][row]
+        elif g == 2:
+            for j in range(num_routed_wires):
+                if outputs and rng.random() < 0.3:
+                    src = rng.choice(outputs)
+                    wires[j][row] = wires[src[0]][src[1]]
+                    parent[find((j, row))] = find(src)
+        else:
+            for k in range(4):
+                wires[k][row] = pi_hash[k]
+    classes: Dict[Tuple[int, int], List[Tuple[int, int]]] = {}
+    for j in range(num_routed_wires):
+        for row in range(n):
+            classes.setdefault(find((j, row)), []).append((j, row))
+    sigma_map = {}
+    for cells in classes.values():
+        for a, b in zip(cells, cells[1:] + cells[:1]):
+            assert wires[a[0]][a[1]] == wires[b[0]][b[1]]
+            sigma_map[a] = b
+    sub = subgroup(degree_bits)
+    k_is = c.k_is
+    sigmas = [[k_is[sigma_map[(j, row)][0]] * sub[sigma_map[(j, row)][1]] % P for row in range(n)]
+              for j in range(num_routed_wires)]
+    return Instance(c, row_gate, consts, sigmas, wires, pi_hash, sigma_map)
+
+
+def zs_partial_products(inst: Instance, betas: List[int], gammas: List[int]) -> List[List[int]]:
+    """Columns [Z_0, Z_1, pp(ch 0)..., pp(ch 1)...] over the subgroup (wires_permutation_partial_products_and_zs)."""
+    c = inst.circuit
+    n, sub, k_is, md, np_ = c.n, subgroup(c.degree_bits), c.k_is, c.max_degree, c.num_partial_products
+    zs, pps = [], []
+    for beta, gamma in zip(betas, gammas):
+        z_col, pp_cols = [0] * n, [[0] * n for _ in range(np_)]
+        z_x = 1
+        for row in range(n):
+            q = []
+            for j in range(c.num_routed_wires):
+                w = inst.wires[j][row]
+                num = (w + beta * (k_is[j] * sub[row] % P) + gamma) % P
+                den = (w + beta * inst.sigmas[j][row] + gamma) % P
+                q.append(num * pow(den, P - 2, P) % P)
+            chunk_products = []
+            for s in range(0, len(q), md):
+                prod = 1
+                for v in q[s:s + md]:
+                    prod = prod * v % P
+                chunk_products.append(prod)
+            acc, running = z_x, []
+            for cp in chunk_products:
+                acc = acc * cp % P
+                running.append(acc)
+            z_col[row] = z_x
+            for k in range(np_):
+                pp_cols[k][row] = running[k]
+            z_x = running[-1]
+        assert z_x == 1, "the grand product must close: the witness violates a copy constraint"
+        zs.append(z_col)
+        pps.extend(pp_cols)
+    return zs + pps
+
+
+# ---- the verifier's side (by definition, one point) ---------------------------------------------------------
+def gate_constraints(c: Circuit, local_constants: List[int], local_wires: List[int], pi_hash: List[int]) -> List[int]:
+    """evaluate_gate_constraints: sum over gates of filter * unfiltered constraints, per constraint index."""
+    out = [0] * c.num_gate_constraints
+    many = c.num_selectors > 1
+    gate_consts = local_constants[c.num_selectors:]
+    for g, gate in enumerate(c.gates):
+        s = local_constants[c.selector_indices[g]]
+        a, b = c.groups[c.selector_indices[g]]
+        filt = 1
+        for j in range(a, b):
+            if j != g:
+                filt = filt * (j - s) % P
+        if many:
+            filt = filt * (UNUSED_SELECTOR - s) % P
+        if gate.kind == "arithmetic":
+            cons = [(local_wires[4 * i + 3] - (gate_consts[0] * local_wires[4 * i] * local_wires[4 * i + 1]
+                                              + gate_consts[1] * local_wires[4 * i + 2])) % P for i in range(gate.num_ops)]
+        elif gate.kind == "constant":
+            cons = [(gate_consts[i] - local_wires[i]) % P for i in range(gate.num_ops)]
+        elif gate.kind == "public_input":
+            cons = [(local_wires[i] - pi_hash[i]) % P for i in range(4)]
+        else:
+            cons = []
+        for i, v in enumerate(cons):
+            out[i] = (out[i] + filt * v) % P
+    return out
+
+
+def eval_vanishing_poly(c: Circuit, x: int, local_constants, local_wires, pi_hash, local_zs, next_zs, partial_products,
+                        s_sigmas, betas, gammas, alphas) -> List[int]:
+    """plonky2 `eval_vanishing_poly` at one point x (any field element outside the subgroup)."""
+    n, md, np_ = c.n, c.max_degree, c.num_partial_products
+    z_h = (pow(x, n, P) - 1) % P
+    l_0 = z_h * pow(n * (x - 1) % P, P - 2, P) % P
+    z1_terms, pp_terms = [], []
+    for i in range(c.num_challenges):
+        z_x, z_gx = local_zs[i], next_zs[i]
+        z1_terms.append(l_0 * (z_x - 1) % P)
+        nums = [(local_wires[j] + betas[i] * (c.k_is[j] * x % P) + gammas[i]) % P for j in range(c.num_routed_wires)]
+        dens = [(local_wires[j] + betas[i] * s_sigmas[j] + gammas[i]) % P for j in range(c.num_routed_wires)]
+        accs = [z_x] + list(partial_products[i * np_:(i + 1) * np_]) + [z_gx]
+        for q, s in enumerate(range(0, c.num_routed_wires, md)):
+            pn = pd = 1
+            for v in nums[s:s + md]:
+                pn = pn * v % P
+            for v in dens[s:s + md]:
+                pd = pd * v % P
+            pp_terms.append((accs[q] * pn - accs[q + 1] * pd) % P)
+    terms = z1_terms + pp_terms + gate_constraints(c, local_constants, local_wires, pi_hash)
+    out = []
+    for alpha in alphas:
+        acc = 0
+        for t in reversed(terms):          # reduce_with_powers: sum_j terms[j] * alpha^j
+            acc = (acc * alpha + t) % P
+        out.append(acc)
+    return out
+
+
+def check_quotient_identity(inst: Instance, zs_pp_cols, quotient_chunks, betas, gammas, alphas, zeta: int) -> bool:
+    """The verifier's final check at zeta, with every opening computed from the committed columns by interpolation.
+    quotient_chunks: num_challenges * max_degree coefficient vectors of length n (challenge-major)."""
+    c = inst.circuit
+    n = c.n
+    g = R.root_of_unity(c.degree_bits)
+
+    def open_cols(cols, x):
+        return [R.horner(R.ifft(col), x) for col in cols]
+
+    local_constants = open_cols(inst.constants, zeta)
+    s_sigmas = open_cols(inst.sigmas, zeta)
+    local_wires = open_cols(inst.wires, zeta)
+    zs_pp = open_cols(zs_pp_cols, zeta)
+    next_zs = open_cols(zs_pp_cols[:c.num_challenges], g * zeta % P)
+    van = eval_vanishing_poly(c, zeta, local_constants, local_wires, inst.public_inputs_hash, zs_pp[:c.num_challenges], next_zs,
+                              zs_pp[c.num_challenges:], s_sigmas, betas, gammas, alphas)
+    z_h = (pow(zeta, n, P) - 1) % P
+    zeta_n = pow(zeta, n, P)
+    for i in range(c.num_challenges):
+        chunk = quotient_chunks[i * c.max_degree:(i + 1) * c.max_degree]
+        t = 0
+        for k in reversed(range(len(chunk))):
+            t = (t * zeta_n + R.horner(chunk[k], zeta)) % P
+        if van[i] != z_h * t % P:
+            return False
+    return True

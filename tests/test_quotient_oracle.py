@@ -1,0 +1,55 @@
+"""The oracle's restatement of plonky2's `compute_quotient_polys` (oracle/quotient.py) against the VERIFIER's
+equation evaluated by definition (tests/plonk_ref.py): prove, then verify -- the way every `run_circuit` test of
+the reference pins its prover.  CPU only."""
+import random
+
+import numpy as np
+import pytest
+
+import plonk_ref as PR
+from oracle import quotient as OQ
+
+P = PR.P
+
+
+def _coeffs(cols):
+    import pyref as R
+    return np.array([R.ifft(list(c)) for c in cols], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("seed,degree_bits,two_groups", [(1, 3, False), (2, 4, False), (3, 4, True), (4, 5, True)])
+def test_quotient_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups):
+    rng = random.Random(0x5151 + seed)
+    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups)
+    c = inst.circuit
+    betas, gammas, alphas = ([rng.randrange(P) for _ in range(c.num_challenges)] for _ in range(3))
+    zs_pp = PR.zs_partial_products(inst, betas, gammas)
+    chunks = OQ.compute_quotient_polys(c, _coeffs(inst.constants + inst.sigmas), _coeffs(inst.wires), _coeffs(zs_pp),
+                                       betas, gammas, alphas, inst.public_inputs_hash)
+    assert chunks.shape == (c.num_challenges * c.max_degree, c.n)
+    for _ in range(3):
+        zeta = rng.randrange(2, P)
+        assert PR.check_quotient_identity(inst, zs_pp, [list(map(int, ch)) for ch in chunks], betas, gammas, alphas, zeta)
+    # a quotient of the right shape but wrong content is rejected
+    bad = [list(map(int, ch)) for ch in chunks]
+    bad[1][0] = (bad[1][0] + 1) % P
+    assert not PR.check_quotient_identity(inst, zs_pp, bad, betas, gammas, alphas, rng.randrange(2, P))
+
+
+def test_violated_gate_makes_the_vanishing_polynomial_indivisible(oracle):
+    """With a broken witness Z_H does not divide the vanishing polynomial: the 'quotient' computed pointwise on the
+    8n coset has degree >= 8n - ... and fails the identity (plonky2 panics in trim_to_len at this point)."""
+    rng = random.Random(7)
+    inst = PR.synthetic_instance(9, degree_bits=4)
+    c = inst.circuit
+    row = inst.row_gate.index(0)
+    inst.wires[3][row] = (inst.wires[3][row] + 1) % P        # break one arithmetic output (its copy class may break too)
+    betas, gammas, alphas = ([rng.randrange(P) for _ in range(2)] for _ in range(3))
+    try:
+        zs_pp = PR.zs_partial_products(inst, betas, gammas)
+    except AssertionError:
+        return  # the grand product already refuses the witness
+    chunks = OQ.compute_quotient_polys(c, _coeffs(inst.constants + inst.sigmas), _coeffs(inst.wires), _coeffs(zs_pp),
+                                       betas, gammas, alphas, inst.public_inputs_hash)
+    assert not PR.check_quotient_identity(inst, zs_pp, [list(map(int, ch)) for ch in chunks], betas, gammas, alphas,
+                                          rng.randrange(2, P))

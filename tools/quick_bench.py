@@ -29,8 +29,8 @@ def field_checks():
     import ctypes as C
     from mapreduce_plonky2_b200 import _lib
     torch.cuda.set_device(0); D.bind_current_device()
-    bad = (C.c_uint64 * 14)()
-    _lib.call("mp2gpu_debug_field_selftest", bad, 14)
+    bad = (C.c_uint64 * 12)()
+    _lib.call("mp2gpu_debug_field_selftest", bad, 12)
     print("field selftest mismatches:", list(bad), flush=True)
     out = (C.c_double * 2)()
     _lib.call("mp2gpu_debug_field_probe", out)
