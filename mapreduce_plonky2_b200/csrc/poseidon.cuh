@@ -178,7 +178,7 @@ GL_DEV void sbox_layer(u64 (&s)[12]) {
 // round constants are pushed through the linear layers, leaving one constant per round on lane 0 and one
 // correction vector at the end (the algebra and its self-check are in tools/gen_poseidon_constants.py).
 template <bool SYNC>
-GL_DEV void poseidon_permute(u64 (&s)[12]) {
+GL_DEV void poseidon_permute_int(u64 (&s)[12]) {
 #pragma unroll
   for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pos_rc[i]);
   // The two groups of four full rounds share ONE copy of the full-round code (phase loop): with
@@ -216,6 +216,183 @@ GL_DEV void poseidon_permute(u64 (&s)[12]) {
       for (int i = 1; i < 12; i++) s[i] = gl_add_c(pos_merge3(l0[i], l1[i], l2[i]), c_pos_d[i]);
     }
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// The same permutation with the linear layers on the FP64 pipe (MP2_POSEIDON_F64, the default).
+//
+// B200 has a full-rate FP64 pipe (tools/intpipe_peak.cu: DADD 63, DFMA 57-59 thread-instr/clk/SM) that the
+// integer formulation leaves idle while the alu and fma-heavy pipes are both ~80 % busy.  A double holds
+// 53-bit integers exactly, so a state element is cut into TWO 32-bit planes (the words of the u64: no
+// split arithmetic at all), each plane goes through the circulant as exact double additions / FMAs by small
+// powers of two (|y| <= 272 |x|: 32-bit inputs give 41-bit outputs), and the result is read back with the
+// 2^52 bias trick: y + (2^52 + c) has the integer y + c in its low mantissa words, so the round constant
+// rides on the conversion.  The two 41-bit planes are folded into a loose u64 with 2^64 = 2^32 - 1 (11
+// integer instructions, pos_merge_d).
+//   In the partial rounds lanes 1..11 never leave the FP64 domain: they stay as signed plane values and are
+// carry-normalised to |.| <= 2^31 + 2^16 only every SECOND round (41 -> 49 bits of a 53-bit mantissa), with
+// the round-to-multiple-of-2^32 trick t = (x + 1.5*2^84) - 1.5*2^84 -- 9 FP64 instructions per lane and
+// renormalisation, none on the integer pipes.  Lane 0 is the only value converted per round.
+//   Offsets that keep the converted values non-negative are multiples of p in plane form:
+//   OA + 2^32 OB = k p  for  OA = k + j 2^32, OB = k (2^32 - 1) - j   (tests/test_limb_planes.py).
+// ------------------------------------------------------------------------------------------------
+#define MP2_D_2_52 4503599627370496.0
+// u32 -> double, exact: the word becomes the low mantissa bits of 2^52 + w
+GL_DEV double pos_u32_to_d(u32 w) { return __hiloint2double(0x43300000, (int)w) - MP2_D_2_52; }
+
+// tA, tB: plane values already biased (2^52 + a, 2^52 + b, 0 <= a, b < 2^52)  ->  loose u64 = a + 2^32 b mod p.
+//   a + 2^32 b = aL + 2^32 (aH + bL) + 2^64 bH = (aL - bH) + 2^32 (aH + bH + bL)   (2^64 = 2^32 - 1)
+// with the net carry k in {-1, 0, 1} folded once as k*eps (same argument as gl_reduce128w: aH, bH < 2^20).
+GL_DEV u64 pos_merge_d(double tA, double tB) {
+  u32 lo, hi;
+  asm("{\n\t.reg .u32 u, bh, c, k, m0, m1;\n\t"
+      "add.u32 u, %3, %5;\n\tadd.u32 u, u, 0x79A00000;\n\t"   // aH + bH  (hi words carry 0x43300000 each)
+      "add.u32 bh, %5, 0xBCD00000;\n\t"                       // bH
+      "add.cc.u32 %1, %4, u;\n\taddc.u32 c, 0, 0;\n\t"
+      "sub.cc.u32 %0, %2, bh;\n\tsubc.cc.u32 %1, %1, 0;\n\tsubc.u32 k, c, 0;\n\t"
+      "neg.s32 m0, k;\n\tshr.s32 m1, k, 1;\n\t"
+      "add.cc.u32 %0, %0, m0;\n\taddc.u32 %1, %1, m1;\n\t}"
+      : "=&r"(lo), "=&r"(hi)
+      : "r"((u32)__double2loint(tA)), "r"((u32)__double2hiint(tA)), "r"((u32)__double2loint(tB)),
+        "r"((u32)__double2hiint(tB)));
+  return pack64(lo, hi);
+}
+
+// One plane through the circulant (same CRT decomposition as pos_mds_plane, shifts written as products).
+GL_DEV void pos_mds_plane_d(const double (&x)[12], double (&y)[12]) {
+  double a[6], b[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    a[k] = x[k] + x[k + 6];
+    b[k] = x[k] - x[k + 6];
+  }
+  double aa[3], ab[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    aa[k] = a[k] + a[k + 3];
+    ab[k] = a[k] - a[k + 3];
+  }
+  const double S = aa[0] + aa[1] + aa[2];
+  const double q0 = S + aa[2], q1 = S + aa[0], q2 = S + aa[1];  // yaa_k = 16 q_k
+  const double yab0 = ab[2] * 8.0 - ab[0] - ab[1] * 2.0;
+  const double yab1 = -(ab[0] * 8.0) - ab[1] - ab[2] * 2.0;
+  const double yab2 = ab[0] * 2.0 - ab[1] * 8.0 - ab[2];
+  const double ya[6] = {q0 * 16.0 + yab0, q1 * 16.0 + yab1, q2 * 16.0 + yab2,
+                        q0 * 16.0 - yab0, q1 * 16.0 - yab1, q2 * 16.0 - yab2};
+  const double yb[6] = {
+      b[0] * 2.0 + b[1] + b[2] - b[3] - b[4] * 16.0 + b[5] * 4.0,
+      b[1] * 2.0 + b[2] + b[3] - b[4] - b[5] * 16.0 - b[0] * 4.0,
+      b[2] * 2.0 + b[3] + b[4] - b[5] + b[0] * 16.0 - b[1] * 4.0,
+      b[3] * 2.0 + b[4] + b[5] + b[0] + b[1] * 16.0 - b[2] * 4.0,
+      b[4] * 2.0 + b[5] - b[0] + b[1] + b[2] * 16.0 - b[3] * 4.0,
+      b[5] * 2.0 - b[0] - b[1] + b[2] + b[3] * 16.0 - b[4] * 4.0};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    y[k] = ya[k] + yb[k];
+    y[k + 6] = ya[k] - yb[k];
+  }
+  y[0] = x[0] * 8.0 + y[0];  // DIAG[0] = 8
+}
+
+// Carry-normalises one lane's planes: |A|, |B| < 2^50 in, |A|, |B| <= 2^31 + 2^19 out, same value mod p.
+GL_DEV void pos_renorm_d(double &A, double &B) {
+  const double K = 29014219670751100192948224.0;  // 1.5 * 2^84: ulp 2^32
+  const double I32 = 2.3283064365386962890625e-10;  // 2^-32
+  const double cA = (A + K) - K;      // A rounded to a multiple of 2^32
+  const double A1 = A - cA;
+  const double B1 = cA * I32 + B;
+  const double cB = (B1 + K) - K;
+  const double B2 = B1 - cB;
+  // 2^32 * cB = 2^64 * ov, ov = cB / 2^32, and 2^64 = 2^32 - 1
+  B = cB * I32 + B2;
+  A = A1 - cB * I32;
+}
+
+// Biases of the plane -> integer conversions (tools/gen_poseidon_constants.py):
+//   c_pos_dbias[(12*round + lane)*2 + plane] = 2^52 + word `plane` of the constant added after the layer of
+//     round `round` - 1 (full rounds; round 30 = zeros);
+//   c_pos_t0bias[2*(r-4) + plane] = 2^52 + offset + word of t_{r+1}[0] (partial rounds, lane 0);
+//   c_pos_exbias[2*lane + plane]  = 2^52 + offset + word of d_26[lane] (leaving the partial rounds).
+static __constant__ double c_pos_dbias[MP2_POSEIDON_DBIAS_LEN] = {MP2_POSEIDON_DBIAS_LIST};
+static __constant__ double c_pos_t0bias[MP2_POSEIDON_T0BIAS_LEN] = {MP2_POSEIDON_T0BIAS_LIST};
+static __constant__ double c_pos_exbias[MP2_POSEIDON_EXBIAS_LEN] = {MP2_POSEIDON_EXBIAS_LIST};
+static __constant__ double c_pos_r4[MP2_POSEIDON_R4D_LEN] = {MP2_POSEIDON_R4D_LIST};  // round-4 constants as plane doubles
+
+template <bool SYNC>
+GL_DEV void poseidon_permute_f64(u64 (&s)[12]) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = gl_add_c(s[i], c_pos_rc[i]);
+  double A[12], B[12];
+#pragma unroll 1
+  for (int phase = 0; phase < 2; phase++) {
+    const int r0 = phase ? 26 : 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      sbox_layer(s);
+      double YA[12], YB[12];
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        A[i] = pos_u32_to_d(lo32(s[i]));
+        B[i] = pos_u32_to_d(hi32(s[i]));
+      }
+      pos_mds_plane_d(A, YA);
+      pos_mds_plane_d(B, YB);
+      if (phase == 0 && k == 3) {
+        // entering the partial rounds: lanes 1..11 stay in plane form (+ the constants of round 4)
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+          A[i] = YA[i] + c_pos_r4[2 * i];
+          B[i] = YB[i] + c_pos_r4[2 * i + 1];
+        }
+        const double *bias = c_pos_dbias + 24 * 4;
+        s[0] = pos_merge_d(YA[0] + bias[0], YB[0] + bias[1]);
+      } else {
+        const double *bias = c_pos_dbias + 24 * (r0 + k + 1);
+#pragma unroll
+        for (int i = 0; i < 12; i++) s[i] = pos_merge_d(YA[i] + bias[2 * i], YB[i] + bias[2 * i + 1]);
+      }
+      MP2_ROUND_SYNC();
+    }
+    if (phase == 0) {
+      u64 s0 = s[0];
+#pragma unroll 1
+      for (int r = 4; r < 26; r++) {
+        s0 = gl_pow7(s0);
+        A[0] = pos_u32_to_d(lo32(s0));
+        B[0] = pos_u32_to_d(hi32(s0));
+        double YA[12], YB[12];
+        pos_mds_plane_d(A, YA);
+        pos_mds_plane_d(B, YB);
+        s0 = pos_merge_d(YA[0] + c_pos_t0bias[2 * (r - 4)], YB[0] + c_pos_t0bias[2 * (r - 4) + 1]);
+#pragma unroll
+        for (int i = 1; i < 12; i++) {
+          A[i] = YA[i];
+          B[i] = YB[i];
+        }
+        if ((r & 1) == 0) {  // 41 -> 49 bits on even rounds: renormalise; odd rounds go 31 -> 39 -> (next) 47
+#pragma unroll
+          for (int i = 1; i < 12; i++) pos_renorm_d(A[i], B[i]);
+        }
+        MP2_ROUND_SYNC();
+      }
+      s[0] = s0;
+#pragma unroll
+      for (int i = 1; i < 12; i++) s[i] = pos_merge_d(A[i] + c_pos_exbias[2 * i], B[i] + c_pos_exbias[2 * i + 1]);
+    }
+  }
+}
+
+#ifndef MP2_POSEIDON_F64
+#define MP2_POSEIDON_F64 1
+#endif
+template <bool SYNC>
+GL_DEV void poseidon_permute(u64 (&s)[12]) {
+#if MP2_POSEIDON_F64
+  poseidon_permute_f64<SYNC>(s);
+#else
+  poseidon_permute_int<SYNC>(s);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,6 +33,39 @@ def limbs3(v):
     return [v & 0x3FFFFF, (v >> 22) & 0x1FFFFF, v >> 43]
 
 
+def tabled(name, vals, per_line=4):
+    """Integer-valued doubles (all < 2^53, exact) for the FP64 linear layers."""
+    assert all(0 <= v < 1 << 53 for v in vals)
+    out = ["#define %s_LEN %d" % (name, len(vals)), "#define %s_LIST \\" % name]
+    rows = [" ".join("%d.0," % v for v in vals[i:i + per_line]) for i in range(0, len(vals), per_line)]
+    out.append(" \\\n".join("    " + r for r in rows))
+    return "\n".join(out)
+
+
+def plane_offsets(bits):
+    """(OA, OB) with OA + 2^32*OB = k*p, both ~2^bits: added to signed plane values |.| < 2^bits so that the
+    biased conversions see non-negative integers.  OA = k + j*2^32, OB = k*(2^32 - 1) - j with j = k = 2^(bits-32)."""
+    k = j = 1 << (bits - 32)
+    oa, ob = k + (j << 32), k * ((1 << 32) - 1) - j
+    assert (oa + (ob << 32)) % R.P == 0 and oa > 1 << (bits - 1) and ob > 1 << (bits - 1)
+    return oa, ob
+
+
+def poseidon_f64_tables():
+    """Bias tables of poseidon_permute_f64 (poseidon.cuh): 2^52 + offset + 32-bit word of the constant."""
+    rc = R.poseidon_round_constants() + [0] * 12
+    t0, d = poseidon_partial_constants()
+    B52 = 1 << 52
+    words = lambda v: (v & 0xFFFFFFFF, v >> 32)
+    dbias = [B52 + w for v in rc for w in words(v)]
+    oa, ob = plane_offsets(49)      # lane 0 inside the partial rounds: |Y| < 2^48.4
+    t0bias = [x for v in t0 for x in (B52 + oa + words(v)[0], B52 + ob + words(v)[1])]
+    oa, ob = plane_offsets(40)      # leaving the partial rounds: |A|, |B| < 2^39.2
+    exbias = [x for v in d for x in (B52 + oa + words(v)[0], B52 + ob + words(v)[1])]
+    r4 = [w for v in rc[48:60] for w in words(v)]
+    return dbias, t0bias, exbias, r4
+
+
 def poseidon_partial_constants():
     """Constants of the 22 partial rounds pushed through the linear layers so that only lane 0 receives one per
     round (plus one correction vector when the partial rounds end).  With x_r the true state before the S-box
@@ -100,6 +133,11 @@ def main():
         "// Poseidon partial rounds: lane-0 constants t_5[0]..t_26[0] and the correction vector d_26 (see generator)",
         table("MP2_POSEIDON_PARTIAL_T0", poseidon_partial_constants()[0]),
         table("MP2_POSEIDON_PARTIAL_D", poseidon_partial_constants()[1]),
+        "// FP64 linear layers: conversion biases (2^52 + offset + constant word), see poseidon_permute_f64",
+        tabled("MP2_POSEIDON_DBIAS", poseidon_f64_tables()[0]),
+        tabled("MP2_POSEIDON_T0BIAS", poseidon_f64_tables()[1]),
+        tabled("MP2_POSEIDON_EXBIAS", poseidon_f64_tables()[2]),
+        tabled("MP2_POSEIDON_R4D", poseidon_f64_tables()[3]),
         "// Poseidon2 external-round constants as 22|21|21-bit limbs, index ((12*slot + lane)*3 + limb); see generator",
         table32("MP2_POSEIDON2_RC3", p2_rc3),
         table("MP2_POSEIDON2_DIAG", R.P2_DIAG),
