@@ -44,8 +44,9 @@ GL_DEV u64 *leaf_digest_ptr(size_t L, u32 h, u64 *digests, u64 *cap) {
 // ---- K4: leaf sponge.  One thread per leaf; rate 8, overwrite absorb (A.5). ---------------------
 // COLMAJOR: element (column c, leaf L) at in[c*stride + L]  -> loads coalesce across the warp.
 // !COLMAJOR: element at in[L*stride + c] (row-major user leaves, FRI layers).
+// 5 CTAs of 128 threads per SM (<= 96 registers): the FP64 partial rounds fit without spills (ptxas -v)
 #ifndef MP2_HASH_MIN_CTAS
-#define MP2_HASH_MIN_CTAS 1
+#define MP2_HASH_MIN_CTAS 5
 #endif
 template <u32 KIND, bool COLMAJOR, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, BLOCK == 128 ? MP2_HASH_MIN_CTAS : 1)

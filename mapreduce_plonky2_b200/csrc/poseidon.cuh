@@ -319,6 +319,11 @@ static __constant__ double c_pos_t0bias[MP2_POSEIDON_T0BIAS_LEN] = {MP2_POSEIDON
 static __constant__ double c_pos_exbias[MP2_POSEIDON_EXBIAS_LEN] = {MP2_POSEIDON_EXBIAS_LIST};
 static __constant__ double c_pos_r4[MP2_POSEIDON_R4D_LEN] = {MP2_POSEIDON_R4D_LIST};  // round-4 constants as plane doubles
 
+// MP2_POSEIDON_F64_FULL = 1: the eight full rounds use the FP64 planes too; 0: they keep the 22|21|21-bit integer
+// planes and only the 22 partial rounds (where FP64 removes the per-round renormalisation) run on the FP64 pipe.
+#ifndef MP2_POSEIDON_F64_FULL
+#define MP2_POSEIDON_F64_FULL 0
+#endif
 template <bool SYNC>
 GL_DEV void poseidon_permute_f64(u64 (&s)[12]) {
 #pragma unroll
@@ -330,6 +335,7 @@ GL_DEV void poseidon_permute_f64(u64 (&s)[12]) {
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
       sbox_layer(s);
+#if MP2_POSEIDON_F64_FULL
       double YA[12], YB[12];
 #pragma unroll
       for (int i = 0; i < 12; i++) {
@@ -352,9 +358,25 @@ GL_DEV void poseidon_permute_f64(u64 (&s)[12]) {
 #pragma unroll
         for (int i = 0; i < 12; i++) s[i] = pos_merge_d(YA[i] + bias[2 * i], YB[i] + bias[2 * i + 1]);
       }
+#else
+      pos_mds_rc(s, c_pos_rc3 + 36 * (r0 + k + 1));
+#endif
       MP2_ROUND_SYNC();
     }
     if (phase == 0) {
+#if !MP2_POSEIDON_F64_FULL
+#pragma unroll
+      for (int i = 1; i < 12; i++) {
+        A[i] = pos_u32_to_d(lo32(s[i]));
+        B[i] = pos_u32_to_d(hi32(s[i]));
+      }
+#endif
+      // plane magnitudes: F64_FULL enters with 41-bit planes (renormalise after rounds 4, 6, ..., 24; leave with
+      // 39 bits), the integer full rounds hand over 32-bit planes (renormalise after rounds 5, 7, ..., 25)
+      constexpr int kRenormParity = MP2_POSEIDON_F64_FULL ? 0 : 1;
+      // (Splitting the layer as M (0, x_1..x_11) + z0 * column 0, so that the lanes' FP64 work overlaps the serial
+      // x^7 chain of lane 0, was measured and is slower, 2.11 vs 2.08 ms at config 1 -- profiles/r2_poseidon_f64.txt:
+      // the kernel is issue-bound, not latency-bound.)
       u64 s0 = s[0];
 #pragma unroll 1
       for (int r = 4; r < 26; r++) {
@@ -370,7 +392,7 @@ GL_DEV void poseidon_permute_f64(u64 (&s)[12]) {
           A[i] = YA[i];
           B[i] = YB[i];
         }
-        if ((r & 1) == 0) {  // 41 -> 49 bits on even rounds: renormalise; odd rounds go 31 -> 39 -> (next) 47
+        if ((r & 1) == kRenormParity) {
 #pragma unroll
           for (int i = 1; i < 12; i++) pos_renorm_d(A[i], B[i]);
         }

@@ -89,6 +89,10 @@ def mds_plane_d(x):
     return y
 
 
+def mds_by_definition(s):
+    return [(sum(s[(i + row) % 12] * R.POS_CIRC[i] for i in range(12)) + s[row] * R.POS_DIAG[row]) % P for row in range(12)]
+
+
 def renorm_d(A, B):
     cA = (A + K84) - K84
     A1 = exact(A - cA)
@@ -98,7 +102,9 @@ def renorm_d(A, B):
     return exact(A1 - cB * I32), exact(cB * I32 + B2)
 
 
-def poseidon_f64(state, track=None):
+def poseidon_f64(state, track=None, f64_full=False):
+    """poseidon_permute_f64; f64_full mirrors MP2_POSEIDON_F64_FULL (0 = the shipped default: integer planes in the
+    full rounds, whose result is by definition `mds(state) + constants`, FP64 planes in the partial rounds)."""
     rc = utable("MP2_POSEIDON_RC")
     dbias, t0bias = dtable("MP2_POSEIDON_DBIAS"), dtable("MP2_POSEIDON_T0BIAS")
     exbias, r4 = dtable("MP2_POSEIDON_EXBIAS"), dtable("MP2_POSEIDON_R4D")
@@ -108,6 +114,10 @@ def poseidon_f64(state, track=None):
         r0 = 26 if phase else 0
         for k in range(4):
             s = [pow(v, 7, P) for v in s]
+            if not f64_full:
+                nxt = (rc + [0] * 12)[12 * (r0 + k + 1):12 * (r0 + k + 2)]
+                s = [(a + b) % P for a, b in zip(mds_by_definition(s), nxt)]
+                continue
             A = [u32_to_d(v & 0xFFFFFFFF) for v in s]
             B = [u32_to_d(v >> 32) for v in s]
             YA, YB = mds_plane_d(A), mds_plane_d(B)
@@ -119,6 +129,10 @@ def poseidon_f64(state, track=None):
                 o = 24 * (r0 + k + 1)
                 s = [merge_d(YA[i] + dbias[o + 2 * i], YB[i] + dbias[o + 2 * i + 1]) for i in range(12)]
         if phase == 0:
+            if not f64_full:
+                A = [None] + [u32_to_d(v & 0xFFFFFFFF) for v in s[1:]]
+                B = [None] + [u32_to_d(v >> 32) for v in s[1:]]
+            parity = 0 if f64_full else 1
             s0 = s[0]
             for r in range(4, 26):
                 s0 = pow(s0, 7, P)
@@ -128,7 +142,7 @@ def poseidon_f64(state, track=None):
                     track["y0"] = max(track.get("y0", 0), abs(YA[0]), abs(YB[0]))
                 s0 = merge_d(exact(YA[0] + t0bias[2 * (r - 4)]), exact(YB[0] + t0bias[2 * (r - 4) + 1]))
                 A, B = list(YA), list(YB)
-                if r % 2 == 0:
+                if r % 2 == parity:
                     for i in range(1, 12):
                         A[i], B[i] = renorm_d(A[i], B[i])
                         assert abs(A[i]) <= 2 ** 31 + 2 ** 19 and abs(B[i]) <= 2 ** 31 + 2 ** 19
@@ -152,10 +166,11 @@ def test_f64_model_equals_the_permutation():
     rng = random.Random(0xF64)
     cases = [[0] * 12, [P - 1] * 12, [(1 << 64) - 1] * 12, list(range(12))]
     cases += [[rng.randrange(1 << 64) for _ in range(12)] for _ in range(40)]
-    track = {}
-    for st in cases:
-        assert poseidon_f64(st, track) == R.poseidon([v % P for v in st])
-    assert track["y0"] < 2.0 ** 48.5 and track["exit"] < 2.0 ** 39.3
+    for full in (False, True):
+        track = {}
+        for st in cases:
+            assert poseidon_f64(st, track, full) == R.poseidon([v % P for v in st])
+        assert track["y0"] < 2.0 ** 48.5 and track["exit"] < 2.0 ** 39.3
 
 
 def test_worst_case_magnitudes_fit_the_mantissa():
