@@ -269,6 +269,48 @@ const char *mp2gpu_commit_from_values_sharded(mp2gpu_comm *comm, const uint64_t 
                                               uint32_t hash_kind, int from_coeffs, uint64_t *const *coeffs_out,
                                               uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out);
 
+/* ---- quotient polynomials on the device ------------------------------------
+ * plonky2 0.2.2 `compute_quotient_polys` (plonk/prover.rs, with plonk/vanishing_poly.rs
+ * eval_vanishing_poly_base_batch) followed by the prover's `PolynomialBatch::from_coeffs(all_quotient_poly_chunks,
+ * rate_bits, blinding = false, cap_height, ...)`: step 5 of every `circuit_data.prove(pw)` the reference issues
+ * (recursion-framework/src/circuit_builder.rs:308, .../universal_verifier_gadget/wrap_circuit.rs:143).  The three
+ * input batches are the device-resident handles returned by mp2gpu_commit_from_values (constants+sigmas, wires,
+ * Zs + partial products); their LDE rows are read in HBM -- with this call no batch needs `leaves_out`.
+ * Gate set: the staged subset of mp2-common/src/serialization/circuit_data_serialization.rs:234-266 below; any
+ * other kind is rejected with an error (never silently skipped).  No lookups, no blinding (zero_knowledge = false,
+ * mp2-common/src/lib.rs:45-47). */
+#define MP2GPU_GATE_NOOP 0u          /* NoopGate: no constraints */
+#define MP2GPU_GATE_ARITHMETIC 1u    /* ArithmeticGate{num_ops}: w[4i+3] - (c0 w[4i] w[4i+1] + c1 w[4i+2]) */
+#define MP2GPU_GATE_CONSTANT 2u      /* ConstantGate{num_consts = num_ops}: c_i - w_i */
+#define MP2GPU_GATE_PUBLIC_INPUT 3u  /* PublicInputGate: w_i - public_inputs_hash[i], i < 4 */
+typedef struct mp2gpu_gate {
+  uint32_t kind;            /* MP2GPU_GATE_* */
+  uint32_t num_ops;         /* see the kinds above */
+  uint32_t selector_index;  /* SelectorsInfo::selector_indices[gate] */
+  uint32_t group_begin;     /* SelectorsInfo::groups[selector_index] = group_begin..group_end (gate indices) */
+  uint32_t group_end;
+} mp2gpu_gate;
+typedef struct mp2gpu_circuit {   /* the CommonCircuitData fields the vanishing polynomial depends on */
+  uint32_t degree_bits;
+  uint32_t quotient_degree_bits;  /* log2(quotient_degree_factor), <= the batches' rate_bits */
+  uint32_t num_challenges;
+  uint32_t num_wires, num_routed_wires;
+  uint32_t num_constants;         /* selectors + gate constants (columns before the sigmas) */
+  uint32_t num_selectors;
+  uint32_t num_gates;
+  const mp2gpu_gate *gates;       /* in CommonCircuitData::gates order (the order selector values refer to) */
+} mp2gpu_circuit;
+/* betas / gammas / alphas: num_challenges elements each; public_inputs_hash: 4 elements (may be NULL without a
+ * PublicInputGate).  Outputs: chunks_out[c * 2^qb + k] = chunk k of challenge c (n coefficients; the array or any
+ * entry may be NULL), then the outputs of mp2gpu_commit_from_coeffs for that batch (leaves_out / digests_out may be
+ * NULL, cap_out is required, quotient_batch_out optionally receives the device-resident batch). */
+const char *mp2gpu_quotient_polys(const mp2gpu_circuit *circuit, const mp2gpu_batch *constants_sigmas,
+                                  const mp2gpu_batch *wires, const mp2gpu_batch *zs_partial_products,
+                                  const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas,
+                                  const uint64_t *public_inputs_hash, uint32_t rate_bits, uint32_t cap_height,
+                                  uint32_t hash_kind, uint64_t *const *chunks_out, uint64_t *leaves_out,
+                                  uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **quotient_batch_out);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
 /* While enabled, every kernel launch is bracketed by CUDA events on its own stream. */
 const char *mp2gpu_profile_enable(int on);

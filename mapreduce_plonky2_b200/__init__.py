@@ -15,5 +15,6 @@ from .fri import (Challenger, FriBatchInfo, FriConfig, FriParams, FriProof, fri_
                   prove_openings)
 
 from . import wire  # noqa: F401,E402  (bincode mirrors of FriProof / ProofWithPublicInputs / ProofWithVK)
+from . import quotient  # noqa: F401,E402  (compute_quotient_polys on device-resident batches)
 
 __version__ = "0.2.0"

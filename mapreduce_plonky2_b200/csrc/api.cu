@@ -250,6 +250,51 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
 
 }  // namespace mp2
 
+namespace mp2 {
+// from_values / from_coeffs of columns that are already on the device (quotient.cu): whole-batch, no pipelining
+// (these batches are a few columns wide); requested outputs are copied to the host, the rest stays behind the handle.
+Status commit_device_columns(const u64 *d_cols, size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind,
+                             int from_coeffs, uint64_t *const *coeffs_out, uint64_t *leaves_out, uint64_t *digests_out,
+                             uint64_t *cap_out, mp2gpu_batch **handle_out, cudaStream_t st) {
+  MP2_TRY(check_commit_args(ncols, n_log, rate_bits, cap_height, hash_kind));
+  if (!cap_out) return "null cap_out";
+  const size_t n = (size_t)1 << n_log, N = n << rate_bits, ncap = (size_t)1 << cap_height, ndig = 2 * (N - ncap);
+  const bool want_rows = leaves_out != nullptr || handle_out != nullptr;
+  DevBuf d_coeffs, d_lde, d_leaves, d_dig, d_cap;
+  MP2_TRY(d_coeffs.alloc(ncols * n, st));
+  MP2_TRY(d_lde.alloc(ncols * N, st));
+  if (want_rows) MP2_TRY(d_leaves.alloc(ncols * N, st));
+  MP2_TRY(d_dig.alloc(ndig * 4, st));
+  MP2_TRY(d_cap.alloc(ncap * 4, st));
+  MP2_TRY(dev_commit(d_cols, ncols, n_log, rate_bits, cap_height, hash_kind, from_coeffs, d_coeffs.p, d_lde.p, d_leaves.p,
+                     d_dig.p, d_cap.p, st));
+  if (coeffs_out) MP2_TRY(copy_columns_d2h(coeffs_out, d_coeffs.p, ncols, n, st));
+  if (leaves_out) MP2_CUDA(cudaMemcpyAsync(leaves_out, d_leaves.p, ncols * N * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  if (digests_out && ndig) MP2_CUDA(cudaMemcpyAsync(digests_out, d_dig.p, ndig * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  MP2_CUDA(cudaMemcpyAsync(cap_out, d_cap.p, ncap * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  MP2_CUDA(cudaStreamSynchronize(st));
+  if (handle_out) {
+    int device = 0;
+    MP2_CUDA(cudaGetDevice(&device));
+    mp2gpu_batch *b = new mp2gpu_batch();
+    b->device = device;
+    b->ncols = ncols;
+    b->n_log = n_log;
+    b->rate_bits = rate_bits;
+    b->cap_height = cap_height;
+    b->hash_kind = hash_kind;
+    b->coeffs = d_coeffs.release();
+    b->lde = nullptr;
+    b->leaves = d_leaves.release();
+    b->digests = d_dig.release();
+    b->cap = d_cap.release();
+    b->owner_stream = st;
+    *handle_out = b;
+  }
+  return "";
+}
+}  // namespace mp2
+
 using namespace mp2;
 
 namespace {

@@ -1,0 +1,286 @@
+// Quotient-polynomial evaluation on the device: plonky2 0.2.2 `compute_quotient_polys` (plonk/prover.rs) with
+// `eval_vanishing_poly_base_batch` (plonk/vanishing_poly.rs) -- SURVEY.md 8(f) row 3.  Reached from every
+// `circuit_data.prove(pw)` of the reference (recursion-framework/src/circuit_builder.rs:308,
+// .../universal_verifier_gadget/wrap_circuit.rs:143) between the second and the third commitment; it is the last
+// host-side reader of `merkle_tree.leaves`, so with it on the device the LDE rows of the three batches never leave
+// HBM (the 17.2 GB / 141 MB D2H of the drop-in call).
+//
+// One thread per point x_i = g * w_{N_q}^i of the quotient coset, N_q = n * 2^quotient_degree_bits:
+//   * the rows it needs are leaves bitrev(i * step) of the batches' own LDE (`get_lde_values(i, step)`); because
+//     step = 2^(rate_bits - quotient_degree_bits), those are exactly the FIRST N_q leaves, in order -- thread L reads
+//     row L of each batch (row-major leaves) and is point i = bitrev(L);
+//   * terms = [L_0(x)(Z_c(x) - 1)]_c ++ [partial-product checks]_c ++ gate constraints (selector-filtered);
+//     q_c(x_i) = (sum_j terms_j alpha_c^j) / Z_H(x_i), written to natural position i;
+//   * then the library's own iNTT (size N_q) + coefficient scaling by g^-j = `coset_ifft`, and the N_q coefficients
+//     of challenge c ARE its 2^qb chunks of n, back to back -- the chunk matrix is committed in place with
+//     `from_coeffs` (the prover's quotient_polys_commitment).
+// Gate set: the staged subset of mp2-common/src/serialization/circuit_data_serialization.rs:234-266 that
+// oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate; anything else is an error.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/mp2gpu.h"
+#include "internal.h"
+#include "gl.cuh"
+
+namespace mp2 {
+namespace {
+
+constexpr u32 kMaxGates = 32, kMaxChallenges = 4, kMaxQuotientBits = 4;
+constexpr u64 kUnusedSelector = 0xFFFFFFFFull;
+
+struct QGate {
+  u32 kind, num_ops, selector, group_begin, group_end;
+};
+struct QParams {
+  u32 n_log, qb, nch, num_wires, R, num_constants, num_selectors, npp, num_gates, gate_term_base, nterms;
+  u32 cs_cols, wi_cols, zp_cols;
+  const u64 *cs, *wi, *zp;          // row-major leaves of the three batches (N_lde rows each, first N_q used)
+  const u64 *apow;                  // nch x nterms: alpha_c^j
+  const u64 *k_is;                  // R coset shifts 7^j
+  u64 betas[kMaxChallenges], gammas[kMaxChallenges], pi_hash[4];
+  u64 zh[1u << kMaxQuotientBits], zh_inv[1u << kMaxQuotientBits];
+  u64 w_nq, n_field;                // w_{N_q};  n as a field element
+  QGate gates[kMaxGates];
+};
+
+GL_DEV u64 gl_neg(u64 a) { return gl_sub(0, a); }
+GL_DEV u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
+
+__global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__ QParams P, u64 *__restrict__ out) {
+  const u32 nq_log = P.n_log + P.qb;
+  const u32 L = blockIdx.x * blockDim.x + threadIdx.x;
+  if (L >= (1u << nq_log)) return;
+  const u32 i = brev_bits(L, nq_log);
+  const u32 md = 1u << P.qb;
+  const u32 L_next = brev_bits((i + md) & ((1u << nq_log) - 1), nq_log);  // next_step = 2^quotient_degree_bits
+  const u64 *cs = P.cs + (size_t)L * P.cs_cols, *wi = P.wi + (size_t)L * P.wi_cols;
+  const u64 *zp = P.zp + (size_t)L * P.zp_cols, *zp_next = P.zp + (size_t)L_next * P.zp_cols;
+  const u64 sx = gl_mul(kCosetShift, gl_pow(P.w_nq, i));  // shifted_x
+  const u64 zh = P.zh[i & (md - 1)];
+  const u64 l_0 = gl_mul(zh, gl_inv(gl_mul(P.n_field, gl_sub(sx, 1))));
+  u64 acc[kMaxChallenges];
+#pragma unroll
+  for (u32 c = 0; c < kMaxChallenges; c++) acc[c] = 0;
+  auto add_term = [&](u32 j, u64 t) {
+#pragma unroll
+    for (u32 c = 0; c < kMaxChallenges; c++)
+      if (c < P.nch) acc[c] = gl_mul_add(t, P.apow[c * P.nterms + j], acc[c]);
+  };
+  // vanishing_z_1_terms, then the partial-product checks challenge by challenge
+  for (u32 c = 0; c < P.nch; c++) add_term(c, gl_mul(l_0, gl_sub(zp[c], 1)));
+  const u32 nchunks = P.npp + 1;
+  const u64 *sig = cs + P.num_constants;
+  for (u32 c = 0; c < P.nch; c++) {
+    const u64 beta = P.betas[c], gamma = P.gammas[c];
+    u64 prev = zp[c];  // accs[q]: Z(x), partial products..., Z(g x)
+    for (u32 q = 0; q < nchunks; q++) {
+      const u64 next = q + 1 < nchunks ? zp[P.nch + c * P.npp + q] : zp_next[c];
+      u64 pn = 1, pd = 1;
+      const u32 j1 = min((q + 1) * md, P.R);
+      for (u32 j = q * md; j < j1; j++) {
+        const u64 w = gl_add(wi[j], gamma);
+        pn = gl_mul(pn, gl_mul_add(beta, gl_mul(P.k_is[j], sx), w));
+        pd = gl_mul(pd, gl_mul_add(beta, sig[j], w));
+      }
+      add_term(P.nch + c * nchunks + q, gl_sub(gl_mul(prev, pn), gl_mul(next, pd)));
+      prev = next;
+    }
+  }
+  // evaluate_gate_constraints_base_batch: sum_g filter_g * sum_i alpha^(base + i) * constraint_{g,i}
+  const u64 *gc = cs + P.num_selectors;
+  for (u32 g = 0; g < P.num_gates; g++) {
+    const QGate gate = P.gates[g];
+    const u64 s = cs[gate.selector];
+    u64 filt = 1;
+    for (u32 j = gate.group_begin; j < gate.group_end; j++)
+      if (j != g) filt = gl_mul(filt, gl_sub((u64)j, s));
+    if (P.num_selectors > 1) filt = gl_mul(filt, gl_sub(kUnusedSelector, s));
+    u64 inner[kMaxChallenges];
+#pragma unroll
+    for (u32 c = 0; c < kMaxChallenges; c++) inner[c] = 0;
+    auto cons = [&](u32 idx, u64 v) {
+#pragma unroll
+      for (u32 c = 0; c < kMaxChallenges; c++)
+        if (c < P.nch) inner[c] = gl_mul_add(v, P.apow[c * P.nterms + P.gate_term_base + idx], inner[c]);
+    };
+    if (gate.kind == MP2GPU_GATE_ARITHMETIC) {
+      const u64 c0 = gc[0], c1 = gc[1];
+      for (u32 op = 0; op < gate.num_ops; op++) {
+        const u64 *w = wi + 4 * op;
+        cons(op, gl_sub(w[3], gl_mul_add(gl_mul(c0, w[0]), w[1], gl_mul(c1, w[2]))));
+      }
+    } else if (gate.kind == MP2GPU_GATE_CONSTANT) {
+      for (u32 k = 0; k < gate.num_ops; k++) cons(k, gl_sub(gc[k], wi[k]));
+    } else if (gate.kind == MP2GPU_GATE_PUBLIC_INPUT) {
+      for (u32 k = 0; k < 4; k++) cons(k, gl_sub(wi[k], P.pi_hash[k]));
+    }
+#pragma unroll
+    for (u32 c = 0; c < kMaxChallenges; c++)
+      if (c < P.nch) acc[c] = gl_mul_add(filt, inner[c], acc[c]);
+  }
+  const u64 zi = P.zh_inv[i & (md - 1)];
+#pragma unroll
+  for (u32 c = 0; c < kMaxChallenges; c++)
+    if (c < P.nch) out[((size_t)c << nq_log) + i] = gl_mul(acc[c], zi);
+}
+
+// coset_ifft's second half: coefficient j *= g^-j
+__global__ void k_coset_unshift(u64 *__restrict__ coeffs, u32 len_log, size_t total, u64 g_inv) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const u32 j = (u32)(t & (((size_t)1 << len_log) - 1));
+  coeffs[t] = gl_canon(gl_mul(coeffs[t], gl_pow(g_inv, j)));
+}
+
+}  // namespace
+
+Status commit_device_columns(const u64 *d_cols, size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind,
+                             int from_coeffs, uint64_t *const *coeffs_out, uint64_t *leaves_out, uint64_t *digests_out,
+                             uint64_t *cap_out, mp2gpu_batch **handle_out, cudaStream_t st);
+
+Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const mp2gpu_batch *bwi, const mp2gpu_batch *bzp,
+                      const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas, const uint64_t *pi_hash,
+                      u32 rate_bits, u32 cap_height, u32 hash_kind, uint64_t *const *chunks_out, uint64_t *leaves_out,
+                      uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **handle_out) {
+  if (!ci || !bcs || !bwi || !bzp || !betas || !gammas || !alphas || !cap_out) return "quotient_polys: null argument";
+  if (!ci->gates && ci->num_gates) return "quotient_polys: null gate list";
+  const u32 n_log = ci->degree_bits, qb = ci->quotient_degree_bits, nch = ci->num_challenges, R = ci->num_routed_wires;
+  if (nch == 0 || nch > kMaxChallenges) return "quotient_polys: num_challenges must be 1.." + std::to_string(kMaxChallenges);
+  if (qb == 0 || qb > kMaxQuotientBits) return "quotient_polys: quotient_degree_bits must be 1.." + std::to_string(kMaxQuotientBits);
+  if (ci->num_gates > kMaxGates) return "quotient_polys: more than " + std::to_string(kMaxGates) + " gate types";
+  if (R == 0 || R > ci->num_wires) return "quotient_polys: num_routed_wires out of range";
+  if (ci->num_selectors > ci->num_constants) return "quotient_polys: num_selectors > num_constants";
+  for (const mp2gpu_batch *b : {bcs, bwi, bzp}) {
+    if (b->n_log != n_log) return "quotient_polys: batch degree differs from the circuit's degree_bits";
+    if (b->rate_bits < qb) return "quotient_polys: quotient_degree_bits exceeds a batch's rate_bits (max_quotient_degree_factor <= 2^rate_bits)";
+    if (b->device != bcs->device) return "quotient_polys: the three batches live on different devices";
+    if (!b->leaves) return "quotient_polys: batch holds no leaf rows";
+  }
+  const u32 md = 1u << qb, npp = (R + md - 1) / md - 1;
+  if (bcs->ncols != ci->num_constants + R) return "quotient_polys: constants_sigmas batch must hold num_constants + num_routed_wires columns";
+  if (bwi->ncols != ci->num_wires) return "quotient_polys: wires batch must hold num_wires columns";
+  if (bzp->ncols != (size_t)nch * (1 + npp)) return "quotient_polys: zs_partial_products batch must hold num_challenges * (1 + num_partial_products) columns";
+  QParams P = {};
+  u32 ngc = 0, max_gate_constants = 0;
+  for (u32 g = 0; g < ci->num_gates; g++) {
+    const mp2gpu_gate &s = ci->gates[g];
+    QGate &d = P.gates[g];
+    d.kind = s.kind;
+    d.num_ops = s.num_ops;
+    d.selector = s.selector_index;
+    d.group_begin = s.group_begin;
+    d.group_end = s.group_end;
+    if (s.selector_index >= ci->num_selectors) return "quotient_polys: gate selector_index out of range";
+    if (s.group_begin > g || s.group_end <= g || s.group_end > ci->num_gates) return "quotient_polys: gate is outside its selector group";
+    u32 nc = 0, nk = 0;
+    switch (s.kind) {
+      case MP2GPU_GATE_NOOP: break;
+      case MP2GPU_GATE_ARITHMETIC:
+        nc = s.num_ops;
+        nk = 2;
+        if (4 * s.num_ops > ci->num_wires) return "quotient_polys: ArithmeticGate ops exceed the wires";
+        break;
+      case MP2GPU_GATE_CONSTANT:
+        nc = nk = s.num_ops;
+        if (s.num_ops > ci->num_wires) return "quotient_polys: ConstantGate consts exceed the wires";
+        break;
+      case MP2GPU_GATE_PUBLIC_INPUT:
+        nc = 4;
+        if (!pi_hash) return "quotient_polys: PublicInputGate needs public_inputs_hash";
+        if (ci->num_wires < 4) return "quotient_polys: PublicInputGate needs 4 wires";
+        break;
+      default:
+        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input)";
+    }
+    ngc = std::max(ngc, nc);
+    max_gate_constants = std::max(max_gate_constants, nk);
+  }
+  if (ci->num_selectors + max_gate_constants > ci->num_constants) return "quotient_polys: gate constants exceed num_constants";
+  DeviceScope scope(bcs->device);
+  cudaStream_t st;
+  MP2_TRY(ctx_stream(&st));
+  const u32 nq_log = n_log + qb;
+  if (nq_log > 26) return "quotient_polys: quotient domain larger than 2^26";
+  const size_t Nq = (size_t)1 << nq_log, n = (size_t)1 << n_log;
+  P.n_log = n_log; P.qb = qb; P.nch = nch; P.num_wires = ci->num_wires; P.R = R; P.num_constants = ci->num_constants;
+  P.num_selectors = ci->num_selectors; P.npp = npp; P.num_gates = ci->num_gates;
+  P.gate_term_base = nch + nch * (npp + 1);
+  P.nterms = P.gate_term_base + ngc;
+  P.cs_cols = (u32)bcs->ncols; P.wi_cols = (u32)bwi->ncols; P.zp_cols = (u32)bzp->ncols;
+  P.cs = bcs->leaves; P.wi = bwi->leaves; P.zp = bzp->leaves;
+  for (u32 c = 0; c < nch; c++) { P.betas[c] = betas[c] % kP; P.gammas[c] = gammas[c] % kP; }
+  for (u32 k = 0; k < 4; k++) P.pi_hash[k] = pi_hash ? pi_hash[k] % kP : 0;
+  // ZeroPolyOnCoset: Z_H(g w^i) = g^n w_{2^qb}^(i mod 2^qb) - 1
+  const u64 g_pow_n = h_pow(kCosetShift, n), w_rate = h_root_of_unity(qb);
+  u64 wr = 1;
+  for (u32 j = 0; j < md; j++) {
+    const u64 gw = h_mul(g_pow_n, wr);
+    P.zh[j] = gw ? gw - 1 : kP - 1;  // (a sum with kP would wrap the u64)
+    P.zh_inv[j] = h_inv(P.zh[j]);
+    wr = h_mul(wr, w_rate);
+  }
+  P.w_nq = h_root_of_unity(nq_log);
+  P.n_field = (u64)n % kP;
+  std::vector<u64> tab((size_t)nch * P.nterms + R);
+  for (u32 c = 0; c < nch; c++) {
+    u64 a = 1;
+    for (u32 j = 0; j < P.nterms; j++) {
+      tab[(size_t)c * P.nterms + j] = a;
+      a = h_mul(a, alphas[c] % kP);
+    }
+  }
+  u64 k = 1;
+  for (u32 j = 0; j < R; j++) {  // get_unique_coset_shifts: powers of the multiplicative generator
+    tab[(size_t)nch * P.nterms + j] = k;
+    k = h_mul(k, kCosetShift);
+  }
+  DevBuf d_tab, d_q;
+  MP2_TRY(d_tab.alloc(tab.size(), st));
+  MP2_TRY(d_q.alloc((size_t)nch * Nq, st));
+  MP2_CUDA(cudaMemcpyAsync(d_tab.p, tab.data(), tab.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
+  P.apow = d_tab.p;
+  P.k_is = d_tab.p + (size_t)nch * P.nterms;
+  {
+    ProfScope _p("k_quotient_points", st);
+    k_quotient_points<<<(unsigned)((Nq + 127) / 128), 128, 0, st>>>(P, d_q.p);
+  }
+  MP2_LAUNCH_CHECK();
+  // the source vector `tab` must outlive the asynchronous upload
+  MP2_CUDA(cudaStreamSynchronize(st));
+  // coset_ifft: values on g<w> (natural order) -> coefficients; in place is not supported by the transform, so a
+  // second buffer takes the coefficients, which are then the chunk matrix (nch * 2^qb columns of n)
+  DevBuf d_coeffs;
+  MP2_TRY(d_coeffs.alloc((size_t)nch * Nq, st));
+  MP2_TRY(ntt_intt(d_q.p, Nq, d_coeffs.p, Nq, nch, nq_log, st));
+  {
+    const size_t total = (size_t)nch * Nq;
+    ProfScope _p("k_coset_unshift", st);
+    k_coset_unshift<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_coeffs.p, nq_log, total, h_inv(kCosetShift));
+  }
+  MP2_LAUNCH_CHECK();
+  return commit_device_columns(d_coeffs.p, (size_t)nch * md, n_log, rate_bits, cap_height, hash_kind, 1, chunks_out, leaves_out,
+                               digests_out, cap_out, handle_out, st);
+}
+
+}  // namespace mp2
+
+extern "C" const char *mp2gpu_quotient_polys(const mp2gpu_circuit *circuit, const mp2gpu_batch *constants_sigmas,
+                                             const mp2gpu_batch *wires, const mp2gpu_batch *zs_partial_products,
+                                             const uint64_t *betas, const uint64_t *gammas, const uint64_t *alphas,
+                                             const uint64_t *public_inputs_hash, uint32_t rate_bits, uint32_t cap_height,
+                                             uint32_t hash_kind, uint64_t *const *chunks_out, uint64_t *leaves_out,
+                                             uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **quotient_batch_out) {
+  mp2::Status s;
+  try {
+    s = mp2::quotient_polys(circuit, constants_sigmas, wires, zs_partial_products, betas, gammas, alphas, public_inputs_hash,
+                            rate_bits, cap_height, hash_kind, chunks_out, leaves_out, digests_out, cap_out, quotient_batch_out);
+  } catch (const std::exception &e) {
+    s = std::string("exception: ") + e.what();
+  }
+  if (s.empty()) return nullptr;
+  char *m = (char *)malloc(s.size() + 1);
+  if (m) memcpy(m, s.c_str(), s.size() + 1);
+  return m;
+}
