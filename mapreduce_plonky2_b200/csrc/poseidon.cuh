@@ -12,9 +12,11 @@
 #include "poseidon_constants.h"
 
 // Tuning knobs (see profiles/): MP2_ROUND_BARRIER keeps the warps of a CTA in the same round so the
-// instruction stream (far larger than the instruction caches) is fetched once per CTA, not per warp.
+// instruction stream (far larger than the instruction caches) is fetched once per CTA, not per warp.  It paid
+// 22 % on the round-1 kernel; with the partial rounds on the FP64 pipe (shorter code, 5 CTAs/SM) it costs 2 %
+// (profiles/r2_poseidon_f64.txt) and is off.
 #ifndef MP2_ROUND_BARRIER
-#define MP2_ROUND_BARRIER 1
+#define MP2_ROUND_BARRIER 0
 #endif
 // SYNC is a template flag of the permutations: only kernels in which every thread of the CTA runs the
 // same number of permutations may set it.
@@ -151,25 +153,31 @@ GL_DEV void pos_renorm3(u32 o0, u32 o1, u32 o2, u32 &l0, u32 &l1, u32 &l2) {
 // S-box on all 12 lanes.  Fully unrolled this is ~1000 instructions per round and the permutation
 // outgrows the instruction caches (ncu: `no_instruction` was the top stall); rolled up as 3 x 4 lanes
 // with a register rotation (24 moves per trip) it is a third of the code for 7 % more issue slots.
-#ifndef MP2_SBOX_ROLLED
-#define MP2_SBOX_ROLLED 1
+// Per permutation: Poseidon (whose partial rounds moved to the FP64 pipe and shrank) runs faster unrolled, Poseidon2
+// faster rolled (profiles/r2_poseidon_f64.txt).
+#ifndef MP2_POS_SBOX_ROLLED
+#define MP2_POS_SBOX_ROLLED 0
 #endif
+#ifndef MP2_P2_SBOX_ROLLED
+#define MP2_P2_SBOX_ROLLED 1
+#endif
+template <bool ROLLED>
 GL_DEV void sbox_layer(u64 (&s)[12]) {
-#if MP2_SBOX_ROLLED
+  if (ROLLED) {
 #pragma unroll 1
-  for (int it = 0; it < 3; it++) {
-    const u64 t0 = gl_pow7(s[0]), t1 = gl_pow7(s[1]), t2 = gl_pow7(s[2]), t3 = gl_pow7(s[3]);
+    for (int it = 0; it < 3; it++) {
+      const u64 t0 = gl_pow7(s[0]), t1 = gl_pow7(s[1]), t2 = gl_pow7(s[2]), t3 = gl_pow7(s[3]);
 #pragma unroll
-    for (int i = 0; i < 8; i++) s[i] = s[i + 4];
-    s[8] = t0;
-    s[9] = t1;
-    s[10] = t2;
-    s[11] = t3;
+      for (int i = 0; i < 8; i++) s[i] = s[i + 4];
+      s[8] = t0;
+      s[9] = t1;
+      s[10] = t2;
+      s[11] = t3;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
   }
-#else
-#pragma unroll
-  for (int i = 0; i < 12; i++) s[i] = gl_pow7(s[i]);
-#endif
 }
 
 // Naive schedule (A.6): 30 x { +RC ; S-box (all lanes | lane 0) ; MDS }, 4 full + 22 partial + 4 full.
@@ -189,7 +197,7 @@ GL_DEV void poseidon_permute_int(u64 (&s)[12]) {
     const int r0 = phase ? 26 : 0;
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
-      sbox_layer(s);
+      sbox_layer<MP2_POS_SBOX_ROLLED != 0>(s);
       pos_mds_rc(s, c_pos_rc3 + 36 * (r0 + k + 1));
       MP2_ROUND_SYNC();
     }
@@ -334,7 +342,7 @@ GL_DEV void poseidon_permute_f64(u64 (&s)[12]) {
     const int r0 = phase ? 26 : 0;
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
-      sbox_layer(s);
+      sbox_layer<MP2_POS_SBOX_ROLLED != 0>(s);
 #if MP2_POSEIDON_F64_FULL
       double YA[12], YB[12];
 #pragma unroll
@@ -478,7 +486,7 @@ GL_DEV void poseidon2_permute(u64 (&s)[12]) {
   for (int phase = 0; phase < 2; phase++) {  // one copy of the external-round code, see poseidon_permute
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
-      sbox_layer(s);
+      sbox_layer<MP2_P2_SBOX_ROLLED != 0>(s);
       p2_external_rc(s, 4 * phase + k + 1);  // slots 1..4, then 5..8 (tools/gen_poseidon_constants.py)
       MP2_ROUND_SYNC();
     }
