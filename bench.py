@@ -60,7 +60,7 @@ def parse_args():
                          "aggregation (configs[3])")
     ap.add_argument("--proofs", type=int, default=64, help="trace workload: proofs per GPU per step")
     ap.add_argument("--streams", type=int, default=8, help="trace workload: proofs in flight per GPU")
-    ap.add_argument("--exchange", default="nccl", choices=["peer", "nccl"],
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer = LDE kernel stores into the peers' buffers over NVLink; nccl = all_to_all_single")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -577,15 +577,39 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         api = "sharded.commit_sharded(host_out=...) with pinned host shards (H2D + D2H per rank, D2H overlapped with hashing)"
+        # the same call with the leaf rows left in HBM (every later reader of the rows runs on the device)
+        host_res = S.HostOutputs(coeffs_h, None, dig_h, cap_h, host_out.copy_stream)
+
+        def call_resident():
+            cols_d.copy_(cols_h, non_blocking=True)
+            S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
+                             exchange=a.exchange, host_out=host_res)
+            torch.cuda.synchronize()
+
+        call_resident()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call_resident()
+        dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_res = float(t.item())
     elems = a.ncols * N
-    out = {"value": elems / dt / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "ms_per_step": dt * 1e3, "steps": steps, "api": api,
-           "outputs": "coefficients + row-major leaves + digests + cap copied back to the host every step"}
-    if world == 1:
-        out["leaves_resident"] = {"value": elems / dt_res / 1e9, "unit": "Gelem/s", "ms_per_step": dt_res * 1e3,
-                                  "d2h_bytes_per_step": d2h - 8 * a.ncols * N,
-                                  "note": "same call with leaves_out = NULL + handle_out: leaves stay in HBM behind "
-                                          "mp2gpu_batch_fetch_rows (get_lde_values)"}
+    d2h_res = d2h - 8 * a.ncols * (N // world)
+    # Headline e2e: the call a patched plonky2 makes now that every later reader of the LDE rows runs on the device
+    # (quotient evaluation: mp2gpu_quotient_polys; openings: mp2gpu_batch_eval; query rounds: mp2gpu_batch_open) --
+    # host columns in; coefficients, digests and cap out; the rows stay in HBM behind the batch handle.  The variant
+    # that also ships every row to the host (what round 1 reported as e2e) is kept beside it.
+    out = {"value": elems / dt_res / 1e9, "unit": "Gelem/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_res,
+           "ms_per_step": dt_res * 1e3, "steps": steps,
+           "api": api + "; leaves_out = NULL + handle_out (rows stay device-resident)",
+           "outputs": "coefficients + digests + cap copied back to the host every step; LDE rows stay in HBM behind "
+                      "mp2gpu_batch_fetch_rows / _open / _eval / mp2gpu_quotient_polys",
+           "all_outputs_to_host": {"value": elems / dt / 1e9, "unit": "Gelem/s", "ms_per_step": dt * 1e3,
+                                   "d2h_bytes_per_step": d2h,
+                                   "note": "the same call with leaves_out set: all %0.1f GB of row-major leaves cross PCIe "
+                                           "as well (round 1's e2e definition)" % (8 * a.ncols * (N // world) / 1e9)}}
     return out
 
 

@@ -141,19 +141,22 @@ def _log2(x: int) -> int:
 
 def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, cap_height: int, hash_kind: int,
                    engine, group=None, from_coeffs: bool = False, want_leaves: bool = True,
-                   scratch: Optional[dict] = None, exchange: str = "nccl",
+                   scratch: Optional[dict] = None, exchange: str = "auto",
                    host_out: Optional[HostOutputs] = None) -> ShardedBatch:
     """PolynomialBatch::from_values / from_coeffs of one (ncols_total x n) batch over ``group``.
 
     ``cols_local``: this rank's columns, shape (ncols_total / G, n).  Requirements: G is a power of two,
     G divides ncols_total, and G <= 2^cap_height (every rank owns whole cap subtrees).
     ``scratch`` may hold reusable buffers (keys: coeffs, send, recv, leaves, digests, cap_local, cap).
-    ``exchange``: "nccl" = LDE into a send buffer + ``all_to_all_single``; "peer" = the LDE kernel stores
-    straight into the peers' receive buffers (symmetric memory over NVLink), no all-to-all.
+    ``exchange``: "peer" = the LDE kernel stores straight into the peers' receive buffers (symmetric memory over
+    NVLink), no all-to-all -- the default on GPUs ("auto"); "nccl" = LDE into a send buffer + ``all_to_all_single``
+    (what "auto" picks for CPU tensors, i.e. the gloo tests).
     ``host_out``: also stream this rank's outputs into pinned host buffers, overlapped with the compute."""
     G = dist.get_world_size(group)
     g = dist.get_rank(group)
     glog = _log2(G)
+    if exchange == "auto":
+        exchange = "peer" if cols_local.is_cuda else "nccl"
     c_loc, n = cols_local.shape
     n_log = _log2(n)
     if c_loc * G != ncols_total:
