@@ -269,6 +269,23 @@ const char *mp2gpu_commit_from_values_sharded(mp2gpu_comm *comm, const uint64_t 
                                               uint32_t hash_kind, int from_coeffs, uint64_t *const *coeffs_out,
                                               uint64_t *leaves_out, uint64_t *digests_out, uint64_t *cap_out);
 
+/* ---- Fiat-Shamir transcript (host) ----------------------------------------------------------------
+ * One Poseidon / Poseidon2 permutation of a 12-element state ON THE HOST, for `Challenger::duplexing` (plonky2
+ * iop/challenger.rs) only: the transcript is a few dozen strictly sequential permutations per proof over caps and
+ * challenges that already live on the host, and it is host code in the reference (part of plonky2's prover, reached
+ * from recursion-framework/src/circuit_builder.rs:308).  Not a fallback for anything on the data path: leaves,
+ * nodes, proof-of-work and all batched hashing run on the device only.  A Rust integration keeps plonky2's own
+ * challenger and never calls this; the Python / C++ host mirrors use it (tests check it against
+ * mp2gpu_permute_batch).  In place; inputs may be non-canonical, outputs are canonical. */
+const char *mp2gpu_transcript_permute(uint64_t *state12, uint32_t hash_kind);
+/* `Challenger::observe_elements` for n elements in one call (same host-only scope): state12 = sponge_state,
+ * buffer8 / *buffer_len = input_buffer (fewer than 8 pending elements), all updated in place; every element clears
+ * the output buffer, a full rate of 8 triggers a duplexing.  *duplexed_last_out = 1 iff the last element completed
+ * one (the output buffer is then state12[0..8), otherwise it is empty). */
+const char *mp2gpu_transcript_observe(uint64_t *state12, uint64_t *buffer8, uint32_t *buffer_len,
+                                      const uint64_t *elems, size_t n, uint32_t hash_kind,
+                                      uint32_t *duplexed_last_out);
+
 /* ---- quotient polynomials on the device ------------------------------------
  * plonky2 0.2.2 `compute_quotient_polys` (plonk/prover.rs, with plonk/vanishing_poly.rs
  * eval_vanishing_poly_base_batch) followed by the prover's `PolynomialBatch::from_coeffs(all_quotient_poly_chunks,

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmp2gpu.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "ntt.cu", "merkle.cu", "tables.cu", "prof.cu", "fri.cu", "selftest.cu", "sharded.cu", "quotient.cu"]
+SOURCES = ["api.cu", "ntt.cu", "merkle.cu", "tables.cu", "prof.cu", "fri.cu", "selftest.cu", "sharded.cu", "quotient.cu", "transcript.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 
@@ -45,7 +45,7 @@ def build_library(force: bool = False, verbose: bool = False, out: str = None) -
     env.pop("CXX", None)
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
         cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:

@@ -535,9 +535,12 @@ const char *mp2gpu_fri_proof_of_work(const uint64_t *duplex_state, uint32_t witn
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
     if (min_leading_zeros > 40) return "proof_of_work_bits too large";
-    // expected 2^min_lz candidates; batches of 2^20 (one wave of the hash kernel is ~10^5 threads)
-    const u64 batch = (u64)1 << 20;
-    for (u64 start = 0; start < kP; start += batch) {
+    // The smallest witness is geometric with mean 2^min_lz, and ranges are scanned in order (the atomicMin inside a
+    // range keeps the "smallest witness" rule), so the first range is sized at twice the mean -- 86 % of the grinds
+    // end there -- and later ranges double up to 2^22.  (A fixed 2^20 range hashed 16x more candidates than needed
+    // at the reference's 16 bits: 0.95 ms of a 2.5 ms fri_proof.)  Never below ~1.4 waves of the hash kernel.
+    u64 batch = (u64)1 << (min_leading_zeros + 1 < 17 ? 17 : min_leading_zeros + 1 > 22 ? 22 : min_leading_zeros + 1);
+    for (u64 start = 0; start < kP; start += batch, batch = batch < ((u64)1 << 22) ? batch << 1 : batch) {
       u64 found = ~(u64)0;
       u64 count = kP - start < batch ? kP - start : batch;
       MP2_TRY(pow_search((const u64 *)duplex_state, witness_pos, min_leading_zeros, hash_kind, start, count, &found, st));

@@ -24,6 +24,10 @@
 // n <= 2^14 : one pass over global memory, the whole line lives in shared memory (128 KB at 2^14).
 // n >  2^14 : two passes (n = n1*n2, four-step), each a shared-memory transform on a tile of adjacent
 //             lines (4 lines of 2^10 points at n = 2^20: the strided pass moves whole 32-byte sectors).
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "internal.h"
 #ifdef MP2_NTT_MUL_REDUCE_FMA
 #define MP2_MUL_REDUCE_FMA 1
@@ -389,9 +393,22 @@ static u32 threads_for(u32 tile_log) {
   if (t < 32) t = 32;
   return t;
 }
+// The dynamic shared-memory limit is an attribute of the FUNCTION (per device), shared by every host thread: it is
+// only ever raised, under a lock.  (Setting it to each launch's own size let one prover thread lower it between
+// another thread's set and launch: cudaErrorInvalidValue with several provers per process.)
 template <typename K>
 static Status allow_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) MP2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  if (bytes <= 48 * 1024) return "";
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> granted;
+  int device = 0;
+  MP2_CUDA(cudaGetDevice(&device));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &cur = granted[std::make_pair(device, (const void *)kernel)];
+  if (bytes > cur) {
+    MP2_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    cur = bytes;
+  }
   return "";
 }
 

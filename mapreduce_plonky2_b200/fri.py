@@ -3,8 +3,10 @@
 What runs where:
 
 * ``Challenger`` (plonky2 ``iop/challenger.rs``): the duplex sponge of the Fiat-Shamir transcript.  A few dozen
-  permutations per proof; each goes through ``mp2gpu_permute_batch`` (the library has no CPU hashing path; in
-  the Rust integration the challenger stays plonky2's own host code).
+  strictly sequential permutations per proof over host data; they run on the host (``mp2gpu_transcript_permute``,
+  as the reference's challenger does -- through the device each cost a ~60 us round trip, 6.7 ms per proof).
+  ``Challenger(on_device=True)`` keeps the round-1 behaviour (``mp2gpu_permute_batch``); in the Rust integration the
+  challenger stays plonky2's own host code, INTEGRATION.md section 4b.
 * ``open_batches``: ``OpeningSet::new``'s polynomial evaluations, on the coefficients resident in HBM.
 * ``prove_openings`` / ``fri_proof`` (``fri/oracle.rs``, ``fri/prover.rs``): alpha-batched quotient, commit phase,
   proof-of-work grind, query rounds -- leaves, digests and layer trees never leave the device; only caps, the
@@ -31,8 +33,9 @@ SPONGE_WIDTH, SPONGE_RATE = 12, 8
 class Challenger:
     """``Challenger<F, H>``: overwrite-mode duplex sponge; challenges are popped from the END of the squeezed rate."""
 
-    def __init__(self, hash_kind: int = P2.POSEIDON2):
+    def __init__(self, hash_kind: int = P2.POSEIDON2, on_device: bool = False):
         self.hash_kind = hash_kind
+        self.on_device = on_device
         self.sponge_state = np.zeros(SPONGE_WIDTH, dtype=np.uint64)
         self.input_buffer: List[int] = []
         self.output_buffer: List[int] = []
@@ -44,8 +47,24 @@ class Challenger:
             self.duplexing()
 
     def observe_elements(self, xs) -> None:
-        for x in np.asarray(xs, dtype=np.uint64).reshape(-1).tolist():
-            self.observe_element(x)
+        flat = np.ascontiguousarray(np.asarray(xs, dtype=np.uint64).reshape(-1))
+        if self.on_device or flat.size < 4:
+            for x in flat.tolist():
+                self.observe_element(x)
+            return
+        # the same element-by-element semantics in one host call (mp2gpu_transcript_observe)
+        import ctypes as C
+
+        from . import _lib
+        state = np.ascontiguousarray(self.sponge_state, dtype=np.uint64).copy()
+        buf = np.zeros(SPONGE_RATE, dtype=np.uint64)
+        buf[:len(self.input_buffer)] = self.input_buffer
+        blen, last = C.c_uint32(len(self.input_buffer)), C.c_uint32(0)
+        _lib.call("mp2gpu_transcript_observe", P2._ptr(state), P2._ptr(buf), C.byref(blen), P2._ptr(flat), flat.size,
+                  self.hash_kind, C.byref(last))
+        self.sponge_state = state
+        self.input_buffer = [int(v) for v in buf[:blen.value]]
+        self.output_buffer = [int(v) for v in state[:SPONGE_RATE]] if last.value else []
 
     def observe_extension_element(self, e) -> None:
         self.observe_elements(e)              # to_basefield_array()
@@ -57,8 +76,7 @@ class Challenger:
         self.observe_elements(h)
 
     def observe_cap(self, cap: MerkleCap) -> None:
-        for h in cap.hashes:
-            self.observe_hash(h)
+        self.observe_elements(np.asarray(cap.hashes, dtype=np.uint64))   # = observe_hash of every cap entry, in order
 
     def get_challenge(self) -> int:
         if self.input_buffer or not self.output_buffer:
@@ -76,7 +94,10 @@ class Challenger:
         for i, x in enumerate(self.input_buffer):
             self.sponge_state[i] = x
         self.input_buffer.clear()
-        self.sponge_state = P2.permute(self.sponge_state.reshape(1, SPONGE_WIDTH), self.hash_kind).reshape(SPONGE_WIDTH)
+        if self.on_device:
+            self.sponge_state = P2.permute(self.sponge_state.reshape(1, SPONGE_WIDTH), self.hash_kind).reshape(SPONGE_WIDTH)
+        else:
+            self.sponge_state = P2.transcript_permute(self.sponge_state, self.hash_kind)
         self.output_buffer = [int(v) for v in self.sponge_state[:SPONGE_RATE]]
 
 

@@ -52,6 +52,32 @@ def init(device: int = 0) -> None:
     _lib.call("mp2gpu_init", device)
 
 
+def pinned_empty(shape, dtype=np.uint64) -> np.ndarray:
+    """A numpy array over page-locked host memory (``mp2gpu_host_alloc``): what a caller should hand to the host-buffer
+    entry points so that copies run at PCIe speed and overlap with compute.  The memory lives as long as the array."""
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p(None)
+    _lib.call("mp2gpu_host_alloc", C.byref(ptr), max(nbytes, 1))
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):  # pragma: no cover
+            try:
+                _lib.load().mp2gpu_host_free(self.p)
+            except Exception:  # noqa: BLE001
+                pass
+
+    _PINNED_OWNERS[arr.__array_interface__["data"][0]] = _Owner(ptr)
+    return arr
+
+
+_PINNED_OWNERS = {}
+
+
 def device_count() -> int:
     n = C.c_int(0)
     _lib.call("mp2gpu_device_count", C.byref(n))
@@ -72,6 +98,13 @@ def permute(states, hash_kind: int = POSEIDON2) -> np.ndarray:
         raise ValueError("states must have 12 lanes")
     _lib.call("mp2gpu_permute_batch", _ptr(s), s.size // 12, hash_kind)
     return s
+
+
+def transcript_permute(state, hash_kind: int = POSEIDON2) -> np.ndarray:
+    """One permutation on the HOST (``mp2gpu_transcript_permute``): the challenger's duplexing only."""
+    st = np.ascontiguousarray(_arr(state).reshape(12).copy())
+    _lib.call("mp2gpu_transcript_permute", _ptr(st), hash_kind)
+    return st
 
 
 def hash_no_pad_batch(inputs, hash_kind: int = POSEIDON2) -> np.ndarray:
@@ -331,8 +364,9 @@ class PolynomialBatch:
     """``PolynomialBatch<F, C, D>{ polynomials, merkle_tree, degree_log, rate_bits, blinding }``."""
 
     def __init__(self, polynomials, merkle_tree: MerkleTree, degree_log: int, rate_bits: int, blinding: bool,
-                 handle=None):
-        self.polynomials = polynomials  # (ncols, n) coefficients
+                 handle=None, num_polys: Optional[int] = None):
+        self.polynomials = polynomials  # (ncols, n) coefficients (None when the caller left them on the device)
+        self.num_polys = len(polynomials) if polynomials is not None else num_polys
         self.merkle_tree = merkle_tree
         self.degree_log = degree_log
         self.rate_bits = rate_bits
@@ -341,7 +375,8 @@ class PolynomialBatch:
 
     # -- constructors ------------------------------------------------------------------------
     @classmethod
-    def _commit(cls, fn: str, cols, rate_bits, blinding, cap_height, hash_kind, keep_on_device, fetch_leaves):
+    def _commit(cls, fn: str, cols, rate_bits, blinding, cap_height, hash_kind, keep_on_device, fetch_leaves,
+                fetch_coeffs=True, fetch_digests=True):
         if blinding:
             raise Mp2GpuError("blinding (salted) batches are not supported: the reference never enables "
                               "zero_knowledge (mp2-common/src/lib.rs:45-47)")
@@ -352,32 +387,37 @@ class PolynomialBatch:
             raise Mp2GpuError("PolynomialValues length must be a power of two and the batch non-empty")
         N = n << rate_bits
         ncap = 1 << cap_height
-        coeffs = np.empty((ncols, n), dtype=np.uint64)
+        if not keep_on_device and not (fetch_coeffs and fetch_digests):
+            raise Mp2GpuError("outputs can only be left on the device with keep_on_device=True")
+        coeffs = np.empty((ncols, n), dtype=np.uint64) if fetch_coeffs else None
         leaves = np.empty((N, ncols), dtype=np.uint64) if fetch_leaves else None
-        digests = np.empty((max(2 * (N - ncap), 0), 4), dtype=np.uint64)
+        digests = np.empty((max(2 * (N - ncap), 0), 4), dtype=np.uint64) if fetch_digests else None
         cap = np.empty((ncap, 4), dtype=np.uint64)
         handle = C.c_void_p(None)
-        _lib.call(fn, _col_ptrs(cols), ncols, n_log, rate_bits, cap_height, hash_kind, _col_ptrs(coeffs),
-                  _ptr(leaves), _ptr(digests) if digests.size else None, _ptr(cap),
+        _lib.call(fn, _col_ptrs(cols), ncols, n_log, rate_bits, cap_height, hash_kind,
+                  _col_ptrs(coeffs) if coeffs is not None else None,
+                  _ptr(leaves), _ptr(digests) if digests is not None and digests.size else None, _ptr(cap),
                   C.byref(handle) if keep_on_device else None)
         tree = MerkleTree(leaves, digests, MerkleCap(cap), hash_kind)
-        return cls(coeffs, tree, n_log, rate_bits, False, handle if keep_on_device else None)
+        return cls(coeffs, tree, n_log, rate_bits, False, handle if keep_on_device else None, ncols)
 
     @classmethod
     def from_values(cls, values, rate_bits: int, blinding: bool, cap_height: int, timing=None,
                     fft_root_table=None, hash_kind: int = POSEIDON2, keep_on_device: bool = False,
-                    fetch_leaves: bool = True) -> "PolynomialBatch":
+                    fetch_leaves: bool = True, fetch_coeffs: bool = True, fetch_digests: bool = True) -> "PolynomialBatch":
         """``PolynomialBatch::from_values(values, rate_bits, blinding, cap_height, timing, fft_root_table)``.
-        ``timing`` / ``fft_root_table`` are accepted and ignored (twiddles are device resident)."""
+        ``timing`` / ``fft_root_table`` are accepted and ignored (twiddles are device resident).  With
+        ``keep_on_device`` the leaves / coefficients / digests may stay in HBM (``fetch_* = False``): every later
+        reader (quotient, openings, query rounds) has a device entry point; only the cap always comes back."""
         return cls._commit("mp2gpu_commit_from_values", values, rate_bits, blinding, cap_height, hash_kind,
-                           keep_on_device, fetch_leaves)
+                           keep_on_device, fetch_leaves, fetch_coeffs, fetch_digests)
 
     @classmethod
     def from_coeffs(cls, polynomials, rate_bits: int, blinding: bool, cap_height: int, timing=None,
                     fft_root_table=None, hash_kind: int = POSEIDON2, keep_on_device: bool = False,
-                    fetch_leaves: bool = True) -> "PolynomialBatch":
+                    fetch_leaves: bool = True, fetch_coeffs: bool = True, fetch_digests: bool = True) -> "PolynomialBatch":
         return cls._commit("mp2gpu_commit_from_coeffs", polynomials, rate_bits, blinding, cap_height, hash_kind,
-                           keep_on_device, fetch_leaves)
+                           keep_on_device, fetch_leaves, fetch_coeffs, fetch_digests)
 
     @classmethod
     def from_values_sharded(cls, comm: "Communicator", values, rate_bits: int, blinding: bool, cap_height: int,
@@ -436,7 +476,7 @@ class PolynomialBatch:
             raise Mp2GpuError("batch was not kept on the device")
         idx = _arr(leaf_indices, 1)
         h = self.degree_log + self.rate_bits - self.merkle_tree.cap.height()
-        rows = np.empty((idx.size, self.polynomials.shape[0]), dtype=np.uint64)
+        rows = np.empty((idx.size, self.num_polys), dtype=np.uint64)
         sib = np.empty((idx.size, h, 4), dtype=np.uint64)
         _lib.call("mp2gpu_batch_open", self._handle, _ptr(idx), idx.size, _ptr(rows), _ptr(sib) if h else None)
         return rows, sib
@@ -447,7 +487,7 @@ class PolynomialBatch:
         if self._handle is None:
             raise Mp2GpuError("batch was not kept on the device (keep_on_device=False)")
         pts = np.ascontiguousarray(_arr(points).reshape(-1, 2))
-        out = np.zeros((pts.shape[0], len(self.polynomials), 2), dtype=np.uint64)
+        out = np.zeros((pts.shape[0], self.num_polys, 2), dtype=np.uint64)
         _lib.call("mp2gpu_batch_eval", self._handle, _ptr(pts), pts.shape[0], _ptr(out))
         return out
 

@@ -83,7 +83,7 @@ def compute_quotient_polys(desc: CircuitDesc, constants_sigmas: PolynomialBatch,
                            zs_partial_products: PolynomialBatch, betas: Sequence[int], gammas: Sequence[int],
                            alphas: Sequence[int], public_inputs_hash: Sequence[int], rate_bits: int, cap_height: int,
                            hash_kind: int = POSEIDON2, keep_on_device: bool = True, fetch_leaves: bool = False,
-                           fetch_digests: bool = True) -> PolynomialBatch:
+                           fetch_digests: bool = True, fetch_chunks: bool = True) -> PolynomialBatch:
     """-> the quotient ``PolynomialBatch`` (``polynomials`` = the num_challenges * quotient_degree_factor chunks).
     The three inputs must be device-resident (``keep_on_device=True`` when they were committed)."""
     for b in (constants_sigmas, wires, zs_partial_products):
@@ -96,15 +96,15 @@ def compute_quotient_polys(desc: CircuitDesc, constants_sigmas: PolynomialBatch,
     vec = lambda v: np.ascontiguousarray(np.array([int(x) for x in v], dtype=np.uint64))
     b_, g_, a_, pi = vec(betas), vec(gammas), vec(alphas), vec(public_inputs_hash)
     N, ncap, ncols = n << rate_bits, 1 << cap_height, nch * md
-    chunks = np.empty((ncols, n), dtype=np.uint64)
+    chunks = np.empty((ncols, n), dtype=np.uint64) if fetch_chunks else None
     leaves = np.empty((N, ncols), dtype=np.uint64) if fetch_leaves else None
     digests = np.empty((max(2 * (N - ncap), 0), 4), dtype=np.uint64) if fetch_digests else None
     cap = np.empty((ncap, 4), dtype=np.uint64)
     handle = C.c_void_p(None)
     _lib.call("mp2gpu_quotient_polys", C.byref(cc), constants_sigmas._handle, wires._handle, zs_partial_products._handle,
               _ptr(b_), _ptr(g_), _ptr(a_), _ptr(pi) if pi.size else None, rate_bits, cap_height, hash_kind,
-              _col_ptrs(chunks), _ptr(leaves), _ptr(digests) if digests is not None and digests.size else None, _ptr(cap),
+              _col_ptrs(chunks) if chunks is not None else None, _ptr(leaves), _ptr(digests) if digests is not None and digests.size else None, _ptr(cap),
               C.byref(handle) if keep_on_device else None)
     del keep
     tree = MerkleTree(leaves, digests, MerkleCap(cap), hash_kind)
-    return PolynomialBatch(chunks, tree, desc.degree_bits, rate_bits, False, handle if keep_on_device else None)
+    return PolynomialBatch(chunks, tree, desc.degree_bits, rate_bits, False, handle if keep_on_device else None, ncols)

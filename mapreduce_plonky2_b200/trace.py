@@ -130,3 +130,173 @@ class TraceRunner:
     @property
     def lde_elems_per_proof(self) -> int:
         return sum(op.lde_elems for op in self.ops)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Whole device-side prover replay: every step of plonky2's prove() that this library implements, through the
+# host-buffer API (the calls a patched plonky2 makes), one prover per host thread (per-thread streams; ctypes drops
+# the GIL inside every call).  Still a replay on synthetic data: witness generation and the grand-product / partial
+# product computation that FEEDS the second commitment are host work in the reference and are not counted.
+# ------------------------------------------------------------------------------------------------------------------
+PROVER_INCLUDES = ("per prove(): from_values(135 wires) | challenger | from_values(20 Zs+partial products) | "
+                   "compute_quotient_polys on the device + from_coeffs(16 chunks) | OpeningSet evaluations at zeta, g*zeta | "
+                   "prove_openings: alpha-batched quotient, FRI commit phase, PoW grind (16 bits), 28 query rounds with "
+                   "Merkle paths; pinned host columns in; caps, openings and the FRI proof out (rows, coefficients and digests stay "
+                   "in HBM)")
+NUM_ROUTED_WIRES = 80
+
+
+def trace_circuit_desc(degree_bits: int):
+    """A circuit descriptor of the standard_recursion_config shape (135 wires, 80 routed, 2 challenges, quotient
+    degree factor 8) over the staged gate subset; gives 3 + 80 constants/sigma columns and 2 * (1 + 9) Z columns."""
+    from .quotient import CircuitDesc, GateDesc
+
+    return CircuitDesc(degree_bits, NUM_WIRES, NUM_ROUTED_WIRES, 3,
+                       [GateDesc("arithmetic", NUM_ROUTED_WIRES // 4), GateDesc("constant", 2), GateDesc("noop"),
+                        GateDesc("public_input")], [0, 0, 0, 0], [(0, 4)], 3, 2)
+
+
+class ProverTrace:
+    """``nthreads`` independent provers on the current device, each replaying whole proofs."""
+
+    def __init__(self, degrees=LEAF_PROOF_DEGREES, hash_kind: int = 1, nthreads: int = 8, seed: int = 0x7ACE):
+        import numpy as np
+
+        from . import fri as GF
+        from . import plonky2 as P2
+
+        self.np, self.GF, self.P2 = np, GF, P2
+        self.degrees, self.hash_kind, self.nthreads = tuple(degrees), hash_kind, nthreads
+        self.stage_log = None   # set to a list to collect (degree, [(stage, ms), ...]) per prove()
+        rng = np.random.default_rng(seed)
+        self.circuits = {}
+        for d in set(degrees):
+            n = 1 << d
+            desc = trace_circuit_desc(d)
+            cs = rng.integers(0, 1 << 62, (desc.num_constants + NUM_ROUTED_WIRES, n), dtype=np.uint64)
+            cs[0] = rng.integers(0, 4, n, dtype=np.uint64)  # selector column: a gate index per row
+            batch = P2.PolynomialBatch.from_values(cs, RATE_BITS, False, CAP_HEIGHT, hash_kind=hash_kind, keep_on_device=True,
+                                                   fetch_leaves=False)
+            self.circuits[d] = (desc, batch)
+        # per-thread synthetic witnesses (host memory; reused across proofs, the work does not depend on the values)
+        def pinned(shape):
+            a = P2.pinned_empty(shape)
+            a[...] = rng.integers(0, 1 << 62, shape, dtype=np.uint64)
+            return a
+
+        self.inputs = [{d: (pinned((NUM_WIRES, 1 << d)), pinned((ZS_PP_COLS, 1 << d))) for d in set(degrees)}
+                       for _ in range(nthreads)]
+
+    def prove(self, degree_bits: int, wires, zs_pp):
+        np, GF, P2 = self.np, self.GF, self.P2
+        from .quotient import compute_quotient_polys
+
+        import time
+
+        desc, cs = self.circuits[degree_bits]
+        kind = self.hash_kind
+        marks = [("start", time.perf_counter())]
+        mark = lambda name: marks.append((name, time.perf_counter()))
+        ch = GF.Challenger(kind)
+        ch.observe_cap(cs.merkle_tree.cap)
+        commit = lambda cols: P2.PolynomialBatch.from_values(cols, RATE_BITS, False, CAP_HEIGHT, hash_kind=kind,
+                                                             keep_on_device=True, fetch_leaves=False, fetch_coeffs=False,
+                                                             fetch_digests=False)
+        b_w = commit(wires)
+        mark("commit_wires")
+        ch.observe_cap(b_w.merkle_tree.cap)
+        betas, gammas = ch.get_n_challenges(2), ch.get_n_challenges(2)
+        b_z = commit(zs_pp)
+        mark("commit_zs")
+        ch.observe_cap(b_z.merkle_tree.cap)
+        alphas = ch.get_n_challenges(2)
+        b_q = compute_quotient_polys(desc, cs, b_w, b_z, betas, gammas, alphas, [1, 2, 3, 4], RATE_BITS, CAP_HEIGHT,
+                                     hash_kind=kind, fetch_digests=False, fetch_chunks=False)
+        mark("quotient")
+        ch.observe_cap(b_q.merkle_tree.cap)
+        zeta = ch.get_extension_challenge()
+        g = pow(7, (P2.ORDER - 1) >> degree_bits, P2.ORDER)  # any point: the replay only needs the work
+        gz = np.array([int(zeta[0]) * g % P2.ORDER, int(zeta[1]) * g % P2.ORDER], dtype=np.uint64)
+        oracles = [cs, b_w, b_z, b_q]
+        batches = [GF.FriBatchInfo(zeta, [(o, p) for o, b in enumerate(oracles) for p in range(b.num_polys)]),
+                   GF.FriBatchInfo(gz, [(2, 0), (2, 1)])]
+        openings = GF.open_batches(batches, oracles)
+        mark("openings")
+        for v in openings:
+            ch.observe_extension_elements(v)
+        proof = GF.prove_openings(batches, oracles, ch, GF.FriConfig().fri_params(degree_bits))
+        mark("fri")
+        for b in (b_w, b_z, b_q):
+            b.free()
+        mark("free")
+        if self.stage_log is not None:
+            self.stage_log.append((degree_bits, [(b[0], (b[1] - a[1]) * 1e3) for a, b in zip(marks, marks[1:])]))
+        return proof
+
+    def _start_workers(self) -> None:
+        """Persistent prover threads: the library keeps one stream set per calling thread and the stream-ordered pool
+        hands freed blocks back to the stream that freed them, so a prover must stay on its thread (fresh threads per
+        run made every run re-grow the pool: 10x swings in the measured rate)."""
+        import queue
+        import threading
+
+        from . import plonky2 as P2
+
+        self._jobs, self._done = queue.Queue(), queue.Queue()
+        device = self.torch_device()
+
+        def worker(t):
+            try:
+                P2.init(device)
+            except Exception as e:  # noqa: BLE001
+                self._done.put(e)
+                return
+            while True:
+                job = self._jobs.get()
+                if job is None:
+                    return
+                try:
+                    for d in self.degrees:
+                        w, z = self.inputs[t][d]
+                        self.prove(d, w, z)
+                    self._done.put(None)
+                except Exception as e:  # noqa: BLE001
+                    self._done.put(e)
+
+        self._threads = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(self.nthreads)]
+        for th in self._threads:
+            th.start()
+
+    def run(self, nproofs: int) -> None:
+        """``nproofs`` whole proofs, shared out over the prover threads; returns when all are done."""
+        import sys
+
+        if not getattr(self, "_threads", None):
+            self._start_workers()
+        # the provers spend their time inside ctypes calls (GIL released); a thread that returns from one must not
+        # wait the default 5 ms switch interval for the interpreter
+        old = sys.getswitchinterval()
+        sys.setswitchinterval(5e-5)
+        try:
+            for _ in range(nproofs):
+                self._jobs.put(1)
+            errors = [e for e in (self._done.get() for _ in range(nproofs)) if e is not None]
+        finally:
+            sys.setswitchinterval(old)
+        if errors:
+            raise errors[0]
+
+    @staticmethod
+    def torch_device() -> int:
+        import torch
+
+        return torch.cuda.current_device()
+
+    def free(self) -> None:
+        for _ in getattr(self, "_threads", []):
+            self._jobs.put(None)
+        for th in getattr(self, "_threads", []):
+            th.join(timeout=10)
+        self._threads = []
+        for _, b in self.circuits.values():
+            b.free()
