@@ -328,6 +328,11 @@ const char *mp2gpu_quotient_polys(const mp2gpu_circuit *circuit, const mp2gpu_ba
                                   uint32_t hash_kind, uint64_t *const *chunks_out, uint64_t *leaves_out,
                                   uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **quotient_batch_out);
 
+/* Returns the calling thread's cached device blocks and the unused part of the device's stream-ordered pool to the
+ * driver (the library keeps freed scratch for reuse: a prover repeats the same shapes).  Call it when another
+ * allocator in the process needs the memory. */
+const char *mp2gpu_trim(void);
+
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */
 /* While enabled, every kernel launch is bracketed by CUDA events on its own stream. */
 const char *mp2gpu_profile_enable(int on);

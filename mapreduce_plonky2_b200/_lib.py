@@ -81,6 +81,7 @@ SIGNATURES = {
                                      C.c_uint32, C.c_uint32, u64pp, u64p, u64p, u64p, C.POINTER(C.c_void_p)]),
     "mp2gpu_transcript_permute": (_ERR, [u64p, C.c_uint32]),
     "mp2gpu_transcript_observe": (_ERR, [u64p, u64p, u32p, u64p, C.c_size_t, C.c_uint32, u32p]),
+    "mp2gpu_trim": (_ERR, []),
     "mp2gpu_sync": (_ERR, [C.c_void_p]),
     "mp2gpu_profile_enable": (_ERR, [C.c_int]),
     "mp2gpu_profile_report": (_ERR, [C.c_char_p, C.c_size_t]),

@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <map>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mp2gpu.h"
@@ -18,10 +20,20 @@ struct DevStreams {
   cudaStream_t stream = nullptr;       // compute
   cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute
   cudaStream_t up_stream = nullptr;    // host->device uploads overlapped with compute
+  // block cache of this thread on this device (see pool_alloc in internal.h)
+  std::unordered_map<void *, size_t> live;   // blocks this thread allocated on `stream`: address -> bytes
+  std::multimap<size_t, void *> idle;        // freed on `stream`, ready for the next request of the same size
+  size_t idle_bytes = 0;
 };
 struct ThreadCtx {
   int device = 0;
   std::vector<DevStreams> per_device;
+  ~ThreadCtx() {  // thread exit: hand the idle blocks back (errors are ignored: the context may be gone already)
+    for (size_t d = 0; d < per_device.size(); d++)
+      for (auto &kv : per_device[d].idle) {
+        if (cudaSetDevice((int)d) == cudaSuccess) cudaFreeAsync(kv.second, per_device[d].stream);
+      }
+  }
 };
 static thread_local ThreadCtx t_ctx;
 
@@ -58,6 +70,58 @@ Status ctx_stream(cudaStream_t *out, cudaStream_t *copy_out, cudaStream_t *up_ou
   if (copy_out) *copy_out = d.copy_stream;
   if (up_out) *up_out = d.up_stream;
   return "";
+}
+
+namespace {
+DevStreams *own_streams(cudaStream_t st) {  // the calling thread's stream set if `st` is its compute stream on the current device
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || (size_t)dev >= t_ctx.per_device.size()) return nullptr;
+  DevStreams &d = t_ctx.per_device[dev];
+  return (d.stream && d.stream == st) ? &d : nullptr;
+}
+size_t cache_limit_bytes() {
+  static const size_t v = [] {
+    const char *e = getenv("MP2GPU_THREAD_CACHE_MB");
+    return (size_t)(e && *e ? atoll(e) : 3072) << 20;
+  }();
+  return v;
+}
+const size_t kMaxCachedBlock = (size_t)1 << 30;
+}  // namespace
+
+Status pool_alloc(u64 **p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) bytes = sizeof(u64);
+  DevStreams *d = own_streams(st);
+  if (d) {
+    auto it = d->idle.find(bytes);
+    if (it != d->idle.end()) {
+      *p = (u64 *)it->second;
+      d->idle.erase(it);
+      d->idle_bytes -= bytes;
+      d->live[*p] = bytes;
+      return "";
+    }
+  }
+  MP2_CUDA(cudaMallocAsync((void **)p, bytes, st));
+  if (d && bytes <= kMaxCachedBlock) d->live[*p] = bytes;
+  return "";
+}
+void pool_free(void *p, cudaStream_t st) {
+  if (!p) return;
+  DevStreams *d = own_streams(st);
+  if (d) {
+    auto it = d->live.find(p);
+    if (it != d->live.end()) {
+      const size_t bytes = it->second;
+      d->live.erase(it);
+      if (bytes <= kMaxCachedBlock && d->idle_bytes + bytes <= cache_limit_bytes()) {
+        d->idle.emplace(bytes, p);  // same thread, same stream: the next user is ordered after every pending use
+        d->idle_bytes += bytes;
+        return;
+      }
+    }
+  }
+  cudaFreeAsync(p, st);
 }
 
 // Runs the rest of the scope on the device a handle lives on, then gives the thread its own device back.
@@ -365,6 +429,22 @@ const char *mp2gpu_init(int device) {
   });
 }
 
+const char *mp2gpu_trim(void) {
+  return guarded([&]() -> Status {
+    cudaStream_t st;
+    MP2_TRY(ctx_stream(&st));
+    DevStreams &d = t_ctx.per_device[t_ctx.device];
+    for (auto &kv : d.idle) cudaFreeAsync(kv.second, st);
+    d.idle.clear();
+    d.idle_bytes = 0;
+    MP2_CUDA(cudaStreamSynchronize(st));
+    cudaMemPool_t pool;
+    MP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, t_ctx.device));
+    MP2_CUDA(cudaMemPoolTrimTo(pool, 0));
+    return "";
+  });
+}
+
 const char *mp2gpu_host_alloc(void **ptr_out, size_t bytes) {
   return guarded([&]() -> Status {
     if (!ptr_out) return "null ptr_out";
@@ -653,7 +733,7 @@ void mp2gpu_batch_free(mp2gpu_batch *b) {
   cudaGetDevice(&prev);
   cudaSetDevice(b->device);
   for (u64 *p : {b->coeffs, b->lde, b->leaves, b->digests, b->cap})
-    if (p) cudaFreeAsync(p, b->owner_stream);
+    if (p) pool_free(p, b->owner_stream);  // the owner thread gets them back into its cache, anyone else frees to the pool
   cudaSetDevice(prev);
   delete b;
 }

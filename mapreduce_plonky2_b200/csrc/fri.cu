@@ -352,8 +352,7 @@ const char *dup_c(const Status &s) {
   MP2_TRY(ctx_stream(&st))
 // stream-ordered allocation that the handle keeps (released by mp2gpu_fri_free / the next fold)
 Status fri_alloc(u64 **p, size_t elems, cudaStream_t st) {
-  MP2_CUDA(cudaMallocAsync(p, sizeof(u64) * (elems ? elems : 1), st));
-  return "";
+  return pool_alloc(p, sizeof(u64) * (elems ? elems : 1), st);
 }
 template <typename F>
 const char *guard(F f) {
@@ -537,7 +536,7 @@ const char *mp2gpu_fri_commit_layer(mp2gpu_fri *f, uint32_t arity_bits, uint64_t
     }();
     if (!built.empty()) {
       for (u64 *p : {L.leaves, L.digests, L.cap})
-        if (p) cudaFreeAsync(p, st);
+        if (p) pool_free(p, st);
       return built;
     }
     f->layers.push_back(L);
@@ -558,10 +557,10 @@ const char *mp2gpu_fri_fold(mp2gpu_fri *f, const uint64_t beta[2]) {
     MP2_TRY(fri_alloc(&next, 2 * n_out, st));
     Status folded = fri_fold(f->coeffs, n, next, n_out, n_out, ab, beta[0] % kP, beta[1] % kP, st);
     if (!folded.empty()) {
-      cudaFreeAsync(next, st);
+      pool_free(next, st);
       return folded;
     }
-    MP2_CUDA(cudaFreeAsync(f->coeffs, st));  // stream order: after the fold that read it
+    pool_free(f->coeffs, st);  // stream order: after the fold that read it
     MP2_CUDA(cudaStreamSynchronize(st));      // the handle may be used from another thread (another stream) next
     f->coeffs = next;
     f->n_log -= ab;
@@ -636,10 +635,10 @@ void mp2gpu_fri_free(mp2gpu_fri *f) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(f->device);
-  if (f->coeffs) cudaFreeAsync(f->coeffs, f->owner_stream);
+  if (f->coeffs) pool_free(f->coeffs, f->owner_stream);
   for (auto &L : f->layers)
     for (u64 *p : {L.leaves, L.digests, L.cap})
-      if (p) cudaFreeAsync(p, f->owner_stream);
+      if (p) pool_free(p, f->owner_stream);
   cudaSetDevice(prev);
   delete f;
 }

@@ -72,7 +72,16 @@ Status copy_columns_h2d(u64 *dev, const uint64_t *const *cols, size_t ncols, siz
 Status copy_columns_d2h(uint64_t *const *cols, const u64 *dev, size_t ncols, size_t n, cudaStream_t st);
 Status check_commit_args(size_t ncols, u32 n_log, u32 rate_bits, u32 cap_height, u32 hash_kind);
 
-// Stream-ordered scratch, returned to the pool on every exit path
+// Device blocks for scratch and handles.  Behind these two calls sits a small per-thread, per-device cache in front
+// of the stream-ordered pool (api.cu): a block freed on the calling thread's own compute stream is kept (exact size)
+// and handed to that thread's next request of the same size -- a prover thread repeats the same batch shapes, and
+// going through cudaMallocAsync / cudaFreeAsync every time let the pool re-grow under several concurrent provers
+// (100 ms-scale stalls, tools/prover_trace_var.py).  Blocks above 1 GiB, a cache above MP2GPU_THREAD_CACHE_MB
+// (default 3072), foreign streams and foreign threads go straight to the pool.  mp2gpu_trim() empties it.
+Status pool_alloc(u64 **p, size_t bytes, cudaStream_t st);
+void pool_free(void *p, cudaStream_t st);
+
+// Stream-ordered scratch, returned on every exit path
 struct DevBuf {
   u64 *p = nullptr;
   cudaStream_t st = nullptr;
@@ -82,8 +91,7 @@ struct DevBuf {
   Status alloc(size_t elems, cudaStream_t s) {
     st = s;
     if (elems == 0) elems = 1;
-    MP2_CUDA(cudaMallocAsync(&p, elems * sizeof(u64), s));
-    return "";
+    return pool_alloc(&p, elems * sizeof(u64), s);
   }
   u64 *release() {
     u64 *r = p;
@@ -91,7 +99,7 @@ struct DevBuf {
     return r;
   }
   ~DevBuf() {
-    if (p) cudaFreeAsync(p, st);
+    if (p) pool_free(p, st);
   }
 };
 
