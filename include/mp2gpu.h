@@ -300,6 +300,10 @@ const char *mp2gpu_transcript_observe(uint64_t *state12, uint64_t *buffer8, uint
 #define MP2GPU_GATE_ARITHMETIC 1u    /* ArithmeticGate{num_ops}: w[4i+3] - (c0 w[4i] w[4i+1] + c1 w[4i+2]) */
 #define MP2GPU_GATE_CONSTANT 2u      /* ConstantGate{num_consts = num_ops}: c_i - w_i */
 #define MP2GPU_GATE_PUBLIC_INPUT 3u  /* PublicInputGate: w_i - public_inputs_hash[i], i < 4 */
+#define MP2GPU_GATE_POSEIDON 4u      /* PoseidonGate (gates/poseidon.rs), 135 wires: input 0..11, output 12..23, swap 24,
+                                        delta 25..28, S-box inputs of full rounds 1..3 at 29 + 12 (round - 1) + i, of the
+                                        22 partial rounds at 65 + r, of the last full rounds at 87 + 12 round + i; 123
+                                        constraints: swap bit, 4 deltas, 36 + 22 + 48 S-box inputs, 12 outputs */
 typedef struct mp2gpu_gate {
   uint32_t kind;            /* MP2GPU_GATE_* */
   uint32_t num_ops;         /* see the kinds above */

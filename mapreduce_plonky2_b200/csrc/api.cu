@@ -680,9 +680,11 @@ const char *mp2gpu_batch_prove(const mp2gpu_batch *b, size_t leaf_index, uint64_
     DeviceScope on_batch_device(b->device);
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
-    for (size_t i = 0; i < idx.size(); i++)
-      MP2_CUDA(cudaMemcpyAsync(siblings_out + 4 * i, b->digests + 4 * idx[i], 32, cudaMemcpyDeviceToHost, st));
-    MP2_CUDA(cudaStreamSynchronize(st));
+    // one device gather + one copy for the whole path (round 1 issued one 32-byte copy per sibling)
+    const u64 leaf = (u64)leaf_index;
+    if (!idx.empty())
+      MP2_TRY(merkle_open(b->leaves, b->lde, N, b->ncols, b->digests, N, b->cap_height, &leaf, 1, nullptr,
+                          (u64 *)siblings_out, st));
     if (nsiblings_out) *nsiblings_out = idx.size();
     return "";
   });

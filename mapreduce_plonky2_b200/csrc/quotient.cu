@@ -15,7 +15,8 @@
 //     of challenge c ARE its 2^qb chunks of n, back to back -- the chunk matrix is committed in place with
 //     `from_coeffs` (the prover's quotient_polys_commitment).
 // Gate set: the staged subset of mp2-common/src/serialization/circuit_data_serialization.rs:234-266 that
-// oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate; anything else is an error.
+// oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate, PoseidonGate; anything else is
+// an error.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -23,6 +24,7 @@
 #include "../../include/mp2gpu.h"
 #include "internal.h"
 #include "gl.cuh"
+#include "poseidon.cuh"
 
 namespace mp2 {
 namespace {
@@ -115,6 +117,48 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
       for (u32 k = 0; k < gate.num_ops; k++) cons(k, gl_sub(gc[k], wi[k]));
     } else if (gate.kind == MP2GPU_GATE_PUBLIC_INPUT) {
       for (u32 k = 0; k < 4; k++) cons(k, gl_sub(wi[k], P.pi_hash[k]));
+    } else if (gate.kind == MP2GPU_GATE_POSEIDON) {
+      // PoseidonGate::eval_unfiltered (plonky2 gates/poseidon.rs), naive round structure: every S-box input except
+      // round 0's is a wire the state is overwritten with (the constraint polynomials equal those of plonky2's fast
+      // partial-round form: same functions of the wires).  Wire map: see MP2GPU_GATE_POSEIDON in mp2gpu.h.
+      u64 st[12];
+      const u64 sw = wi[24];
+      cons(0, gl_mul(sw, gl_sub(sw, 1)));
+#pragma unroll
+      for (u32 i = 0; i < 4; i++) {
+        const u64 lhs = wi[i], rhs = wi[i + 4], d = wi[25 + i];
+        cons(1 + i, gl_sub(gl_mul(sw, gl_sub(rhs, lhs)), d));
+        st[i] = gl_add(lhs, d);
+        st[i + 4] = gl_sub(rhs, d);
+      }
+#pragma unroll
+      for (u32 i = 8; i < 12; i++) st[i] = wi[i];
+#pragma unroll
+      for (u32 i = 0; i < 12; i++) st[i] = gl_add_c(st[i], c_pos_rc[i]);
+      u32 ci = 5;
+#pragma unroll 1
+      for (u32 r = 0; r < 30; r++) {
+        if (r < 4 || r >= 26) {
+          if (r != 0) {
+            const u64 *sb = wi + (r < 4 ? 29 + 12 * (r - 1) : 87 + 12 * (r - 26));
+#pragma unroll
+            for (u32 i = 0; i < 12; i++) {
+              cons(ci + i, gl_sub(st[i], sb[i]));
+              st[i] = sb[i];
+            }
+            ci += 12;
+          }
+#pragma unroll
+          for (u32 i = 0; i < 12; i++) st[i] = gl_pow7(st[i]);
+        } else {
+          const u64 sb = wi[65 + r - 4];
+          cons(ci++, gl_sub(st[0], sb));
+          st[0] = gl_pow7(sb);
+        }
+        pos_mds_rc(st, c_pos_rc3 + 36 * (r + 1));  // linear layer + the constants of round r + 1 (zeros after round 29)
+      }
+#pragma unroll
+      for (u32 i = 0; i < 12; i++) cons(ci + i, gl_sub(st[i], wi[12 + i]));
     }
 #pragma unroll
     for (u32 c = 0; c < kMaxChallenges; c++)
@@ -191,8 +235,12 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
         if (!pi_hash) return "quotient_polys: PublicInputGate needs public_inputs_hash";
         if (ci->num_wires < 4) return "quotient_polys: PublicInputGate needs 4 wires";
         break;
+      case MP2GPU_GATE_POSEIDON:
+        nc = 123;
+        if (ci->num_wires < 135) return "quotient_polys: PoseidonGate needs 135 wires";
+        break;
       default:
-        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input)";
+        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon)";
     }
     ngc = std::max(ngc, nc);
     max_gate_constants = std::max(max_gate_constants, nk);

@@ -6,7 +6,7 @@ caller asks for) comes back.  ctypes + numpy only.
 The descriptor mirrors the ``CommonCircuitData`` fields the vanishing polynomial depends on: ``gates`` in circuit
 order, ``SelectorsInfo { selector_indices, groups }``, ``num_constants`` (selectors + gate constants), the wire counts
 and ``quotient_degree_factor``.  Gate kinds outside the staged subset (ArithmeticGate, ConstantGate, PublicInputGate,
-NoopGate of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
+NoopGate, PoseidonGate of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
 """
 from __future__ import annotations
 
@@ -20,7 +20,7 @@ from . import _lib
 from ._lib import Mp2GpuError
 from .plonky2 import POSEIDON2, MerkleCap, MerkleTree, PolynomialBatch, _arr, _col_ptrs, _ptr
 
-GATE_KINDS = {"noop": 0, "arithmetic": 1, "constant": 2, "public_input": 3}
+GATE_KINDS = {"noop": 0, "arithmetic": 1, "constant": 2, "public_input": 3, "poseidon": 4}
 
 
 class _CGate(C.Structure):
@@ -36,7 +36,7 @@ class _CCircuit(C.Structure):
 
 @dataclass
 class GateDesc:
-    kind: str           # "arithmetic" | "constant" | "public_input" | "noop"
+    kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon"
     num_ops: int = 0    # ArithmeticGate::num_ops / ConstantGate::num_consts
 
 

@@ -148,12 +148,13 @@ NUM_ROUTED_WIRES = 80
 
 def trace_circuit_desc(degree_bits: int):
     """A circuit descriptor of the standard_recursion_config shape (135 wires, 80 routed, 2 challenges, quotient
-    degree factor 8) over the staged gate subset; gives 3 + 80 constants/sigma columns and 2 * (1 + 9) Z columns."""
+    degree factor 8) over the staged gate subset incl. PoseidonGate (the gate recursion circuits are made of); gives
+    4 + 80 constants/sigma columns and 2 * (1 + 9) Z columns."""
     from .quotient import CircuitDesc, GateDesc
 
-    return CircuitDesc(degree_bits, NUM_WIRES, NUM_ROUTED_WIRES, 3,
+    return CircuitDesc(degree_bits, NUM_WIRES, NUM_ROUTED_WIRES, 4,
                        [GateDesc("arithmetic", NUM_ROUTED_WIRES // 4), GateDesc("constant", 2), GateDesc("noop"),
-                        GateDesc("public_input")], [0, 0, 0, 0], [(0, 4)], 3, 2)
+                        GateDesc("public_input"), GateDesc("poseidon")], [0, 0, 0, 0, 1], [(0, 4), (4, 5)], 3, 2)
 
 
 class ProverTrace:

@@ -10,7 +10,7 @@ The prover evaluates, at every point x_i = g * w_{8n}^i of the coset LDE the thr
 then `coset_ifft` turns each q_c into coefficients and cuts it into `quotient_degree_factor` chunks of n, which are
 committed with `from_coeffs`.  Gate set restated here (the staged subset of
 mp2-common/src/serialization/circuit_data_serialization.rs:234-266): ArithmeticGate, ConstantGate, PublicInputGate,
-NoopGate behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
+NoopGate, PoseidonGate behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
 
 Pinned by definition, not by the Rust prover (absent): tests/plonk_ref.py restates the VERIFIER's
 `eval_vanishing_poly` + final identity, and the quotients computed here must pass it at random points
@@ -26,6 +26,41 @@ from . import oracle as O
 P = O.P
 UNUSED_SELECTOR = (1 << 32) - 1
 COSET_SHIFT = 7
+
+
+_POS_CIRC = (17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20)
+_POS_RC = None
+
+
+def _poseidon_gate(w):
+    """PoseidonGate::eval_unfiltered (plonky2 gates/poseidon.rs), naive round structure: wires input 0..11, output
+    12..23, swap 24, delta 25..28, S-box inputs of full rounds 1..3 at 29.., of the 22 partial rounds at 65.., of the
+    last four full rounds at 87..; 123 constraints (swap bit, 4 deltas, 36 + 22 + 48 S-box inputs, 12 outputs)."""
+    global _POS_RC
+    if _POS_RC is None:
+        _POS_RC = [int(v) for v in O.poseidon_round_constants()]
+    rc = _POS_RC
+    sw = w[24]
+    out = [sw * (sw - 1) % P]
+    st = list(w[:12])
+    for i in range(4):
+        out.append((sw * (w[i + 4] - w[i]) - w[25 + i]) % P)
+        st[i], st[i + 4] = (w[i] + w[25 + i]) % P, (w[i + 4] - w[25 + i]) % P
+    for r in range(30):
+        st = [(st[i] + rc[12 * r + i]) % P for i in range(12)]
+        if r < 4 or r >= 26:
+            if r:
+                base = 29 + 12 * (r - 1) if r < 4 else 87 + 12 * (r - 26)
+                out.extend((st[i] - w[base + i]) % P for i in range(12))
+                st = list(w[base:base + 12])
+            st = [pow(v, 7, P) for v in st]
+        else:
+            out.append((st[0] - w[65 + r - 4]) % P)
+            st[0] = pow(w[65 + r - 4], 7, P)
+        st = [(sum(st[(i + row) % 12] * _POS_CIRC[i] for i in range(12)) + (8 * st[0] if row == 0 else 0)) % P
+              for row in range(12)]
+    out.extend((st[i] - w[12 + i]) % P for i in range(12))
+    return out
 
 
 def _gate_constraints(desc, local_constants, local_wires, pi_hash):
@@ -51,6 +86,8 @@ def _gate_constraints(desc, local_constants, local_wires, pi_hash):
             cons = [(local_wires[i] - pi_hash[i]) % P for i in range(4)]
         elif gate.kind == "noop":
             cons = []
+        elif gate.kind == "poseidon":
+            cons = _poseidon_gate(local_wires)
         else:
             raise ValueError("gate kind %r is outside the staged subset" % gate.kind)
         for i, v in enumerate(cons):

@@ -32,18 +32,91 @@ UNUSED_SELECTOR = (1 << 32) - 1
 COSET_SHIFT = 7
 
 
+# ---- PoseidonGate (plonky2 gates/poseidon.rs): one permutation per row, 135 wires, 123 constraints ----------------
+# wires: input 0..11 | output 12..23 | swap 24 | delta 25..28 | full_sbox_0(round 1..3, i) 29 + 12 (round-1) + i |
+#        partial_sbox(r) 65 + r | full_sbox_1(round, i) 87 + 12 round + i | end 135
+# constraints, in order: swap (swap - 1); swap (rhs_i - lhs_i) - delta_i (i < 4); for the first full rounds 1..3 the
+# twelve `state_i - sbox_in_i`; the 22 partial `state_0 - sbox_in`; the 48 of the last full rounds; the 12 outputs.
+# Every S-box input except round 0's is a WIRE: the state is overwritten by it before the S-box, which is what keeps
+# the constraint degree at 7.  plonky2 evaluates the partial rounds in its fast (sparse-matrix) form; the constraint
+# polynomials are the same functions of the wires as the naive rounds used here (the two forms agree on every S-box
+# input for all values of the substituted wires, being identities of the affine maps between S-boxes).
+POSEIDON_GATE_WIRES, POSEIDON_GATE_CONSTRAINTS = 135, 123
+PG_OUT, PG_SWAP, PG_DELTA, PG_FULL0, PG_PARTIAL, PG_FULL1 = 12, 24, 25, 29, 65, 87
+
+
+def _pos_mds(s):
+    return [(sum(s[(i + r) % 12] * R.POS_CIRC[i] for i in range(12)) + s[r] * R.POS_DIAG[r]) % P for r in range(12)]
+
+
+def poseidon_gate_trace(inputs, swap):
+    """Witness of one PoseidonGate row: all 135 wires for the given 12 inputs and swap bit."""
+    rc = R.poseidon_round_constants()
+    w = [0] * POSEIDON_GATE_WIRES
+    w[0:12] = [v % P for v in inputs]
+    w[PG_SWAP] = swap
+    st = list(w[0:12])
+    for i in range(4):
+        d = swap * (w[i + 4] - w[i]) % P
+        w[PG_DELTA + i] = d
+        st[i], st[i + 4] = (w[i] + d) % P, (w[i + 4] - d) % P
+    for r in range(30):
+        st = [(v + rc[12 * r + i]) % P for i, v in enumerate(st)]
+        if r < 4 or r >= 26:
+            if 1 <= r < 4:
+                w[PG_FULL0 + 12 * (r - 1):PG_FULL0 + 12 * r] = st
+            elif r >= 26:
+                w[PG_FULL1 + 12 * (r - 26):PG_FULL1 + 12 * (r - 25)] = st
+            st = [pow(v, 7, P) for v in st]
+        else:
+            w[PG_PARTIAL + r - 4] = st[0]
+            st[0] = pow(st[0], 7, P)
+        st = _pos_mds(st)
+    w[PG_OUT:PG_OUT + 12] = st
+    return w
+
+
+def poseidon_gate_constraints(w):
+    """eval_unfiltered of PoseidonGate on arbitrary wire values (not necessarily a witness)."""
+    rc = R.poseidon_round_constants()
+    swap = w[PG_SWAP]
+    cons = [swap * (swap - 1) % P]
+    st = list(w[0:12])
+    for i in range(4):
+        lhs, rhs, d = w[i], w[i + 4], w[PG_DELTA + i]
+        cons.append((swap * (rhs - lhs) - d) % P)
+        st[i], st[i + 4] = (lhs + d) % P, (rhs - d) % P
+    for r in range(30):
+        st = [(v + rc[12 * r + i]) % P for i, v in enumerate(st)]
+        if r < 4 or r >= 26:
+            if r != 0:
+                base = PG_FULL0 + 12 * (r - 1) if r < 4 else PG_FULL1 + 12 * (r - 26)
+                for i in range(12):
+                    cons.append((st[i] - w[base + i]) % P)
+                    st[i] = w[base + i]
+            st = [pow(v, 7, P) for v in st]
+        else:
+            cons.append((st[0] - w[PG_PARTIAL + r - 4]) % P)
+            st[0] = pow(w[PG_PARTIAL + r - 4], 7, P)
+        st = _pos_mds(st)
+    cons += [(st[i] - w[PG_OUT + i]) % P for i in range(12)]
+    assert len(cons) == POSEIDON_GATE_CONSTRAINTS
+    return cons
+
+
 @dataclass
 class Gate:
-    kind: str           # "arithmetic" | "constant" | "public_input" | "noop"
+    kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon"
     num_ops: int = 0    # arithmetic: ops per row (4 wires each); constant: number of constants
 
     @property
     def num_constraints(self) -> int:
-        return {"arithmetic": self.num_ops, "constant": self.num_ops, "public_input": 4, "noop": 0}[self.kind]
+        return {"arithmetic": self.num_ops, "constant": self.num_ops, "public_input": 4, "noop": 0,
+                "poseidon": POSEIDON_GATE_CONSTRAINTS}[self.kind]
 
     @property
     def num_constants(self) -> int:
-        return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0}[self.kind]
+        return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0, "poseidon": 0}[self.kind]
 
 
 @dataclass
@@ -111,18 +184,24 @@ def subgroup(bits: int) -> List[int]:
 
 
 def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num_routed_wires: int = 8,
-                       two_groups: bool = False) -> Instance:
+                       two_groups: bool = False, with_poseidon: bool = False) -> Instance:
     rng = random.Random(seed)
     n = 1 << degree_bits
+    if with_poseidon:          # standard_recursion_config's shape: a PoseidonGate row needs all 135 wires
+        num_wires, num_routed_wires = max(num_wires, POSEIDON_GATE_WIRES), max(num_routed_wires, 24)
     num_ops = num_routed_wires // 4
     gates = [Gate("arithmetic", num_ops), Gate("constant", 2), Gate("noop"), Gate("public_input")]
     if two_groups:
         selector_indices, groups = [0, 0, 1, 1], [(0, 2), (2, 4)]
     else:
         selector_indices, groups = [0, 0, 0, 0], [(0, 4)]
+    if with_poseidon:          # the degree-7 gate gets a selector group of its own, as plonky2's grouping would do
+        gates.append(Gate("poseidon"))
+        selector_indices.append(len(groups))
+        groups.append((4, 5))
     c = Circuit(degree_bits, num_wires, num_routed_wires, gates, selector_indices, groups)
     pi_hash = [rng.randrange(P) for _ in range(4)]
-    row_gate = [3] + [rng.choice([0, 0, 0, 1, 2]) for _ in range(n - 1)]     # row 0: the public-input gate
+    row_gate = [3] + [rng.choice([0, 0, 0, 1, 2] + ([4, 4] if with_poseidon else [])) for _ in range(n - 1)]     # row 0: the public-input gate
     consts = [[0] * n for _ in range(c.num_constants)]
     for row, g in enumerate(row_gate):
         for s, (a, b) in enumerate(groups):
@@ -161,9 +240,19 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
                     src = rng.choice(outputs)
                     wires[j][row] = wires[src[0]][src[1]]
                     parent[find((j, row))] = find(src)
-        else:
+        elif g == 3:
             for k in range(4):
                 wires[k][row] = pi_hash[k]
+        else:
+            ins = [wires[j][row] for j in range(12)]
+            for j in range(12):   # some inputs are copies of earlier outputs (inputs and outputs are routed wires)
+                if outputs and rng.random() < 0.3:
+                    src = rng.choice(outputs)
+                    ins[j] = wires[src[0]][src[1]]
+                    parent[find((j, row))] = find(src)
+            for j, v in enumerate(poseidon_gate_trace(ins, rng.randrange(2))):
+                wires[j][row] = v
+            outputs.extend((PG_OUT + j, row) for j in range(12))
     classes: Dict[Tuple[int, int], List[Tuple[int, int]]] = {}
     for j in range(num_routed_wires):
         for row in range(n):
@@ -237,6 +326,8 @@ def gate_constraints(c: Circuit, local_constants: List[int], local_wires: List[i
             cons = [(gate_consts[i] - local_wires[i]) % P for i in range(gate.num_ops)]
         elif gate.kind == "public_input":
             cons = [(local_wires[i] - pi_hash[i]) % P for i in range(4)]
+        elif gate.kind == "poseidon":
+            cons = poseidon_gate_constraints(local_wires)
         else:
             cons = []
         for i, v in enumerate(cons):

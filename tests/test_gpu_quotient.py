@@ -25,17 +25,19 @@ def _commit3(G, inst, zs_pp, rate_bits, cap, kind):
     return mk(inst.constants + inst.sigmas), mk(inst.wires), mk(zs_pp)
 
 
-@pytest.mark.parametrize("seed,degree_bits,two_groups,kind,rate_bits,qbits", [
-    (1, 3, False, 0, 3, 3), (2, 4, False, 1, 3, 3), (3, 4, True, 0, 3, 3), (4, 5, True, 1, 3, 3), (5, 6, True, 0, 3, 2),
-    (6, 12, True, 1, 3, 3)])
-def test_quotient_matches_oracle_and_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups, kind, rate_bits, qbits):
+@pytest.mark.parametrize("seed,degree_bits,two_groups,kind,rate_bits,qbits,with_poseidon", [
+    (1, 3, False, 0, 3, 3, False), (2, 4, False, 1, 3, 3, False), (3, 4, True, 0, 3, 3, False), (4, 5, True, 1, 3, 3, False),
+    (5, 6, True, 0, 3, 2, False), (6, 12, True, 1, 3, 3, False),
+    (7, 3, False, 0, 3, 3, True), (8, 5, True, 1, 3, 3, True), (9, 10, True, 1, 3, 3, True)])
+def test_quotient_matches_oracle_and_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups, kind, rate_bits, qbits,
+                                                                  with_poseidon):
     import mapreduce_plonky2_b200 as G
     from mapreduce_plonky2_b200 import quotient as Q
     from oracle import quotient as OQ
 
     G.init(0)
     rng = random.Random(0x7171 + seed)
-    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups)
+    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups, with_poseidon=with_poseidon)
     c = inst.circuit
     c.quotient_degree_bits = qbits
     betas, gammas, alphas = ([rng.randrange(P) for _ in range(c.num_challenges)] for _ in range(3))
@@ -92,7 +94,7 @@ def test_unsupported_gate_and_shape_errors(oracle):
     zs_pp = PR.zs_partial_products(inst, betas, gammas)
     b_cs, b_w, b_z = _commit3(G, inst, zs_pp, 3, 2, 0)
     desc = Q.CircuitDesc.from_circuit(c)
-    desc.gates[2] = Q.GateDesc("poseidon")
+    desc.gates[2] = Q.GateDesc("base_sum")
     with pytest.raises(G.Mp2GpuError, match="outside the supported subset"):
         Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, 3, 2, hash_kind=0)
     desc = Q.CircuitDesc.from_circuit(c)

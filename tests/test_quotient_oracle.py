@@ -17,10 +17,27 @@ def _coeffs(cols):
     return np.array([R.ifft(list(c)) for c in cols], dtype=np.uint64)
 
 
-@pytest.mark.parametrize("seed,degree_bits,two_groups", [(1, 3, False), (2, 4, False), (3, 4, True), (4, 5, True)])
-def test_quotient_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups):
+def test_poseidon_gate_witness_satisfies_its_constraints_and_breaks_when_tampered():
+    import pyref as R
+    rng = random.Random(0x90)
+    for swap in (0, 1):
+        ins = [rng.randrange(P) for _ in range(12)]
+        w = PR.poseidon_gate_trace(ins, swap)
+        assert PR.poseidon_gate_constraints(w) == [0] * 123
+        perm_in = ins[4:8] + ins[0:4] + ins[8:] if swap else ins
+        assert w[12:24] == R.poseidon(perm_in)          # the gate computes plonky2's permutation (with the swap)
+        for j in (0, 24, 26, 40, 70, 100, 20):
+            bad = list(w)
+            bad[j] = (bad[j] + 1) % P
+            assert any(PR.poseidon_gate_constraints(bad))
+
+
+@pytest.mark.parametrize("seed,degree_bits,two_groups,with_poseidon", [(1, 3, False, False), (2, 4, False, False),
+                                                                        (3, 4, True, False), (4, 5, True, False),
+                                                                        (5, 3, False, True), (6, 4, True, True)])
+def test_quotient_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups, with_poseidon):
     rng = random.Random(0x5151 + seed)
-    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups)
+    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups, with_poseidon=with_poseidon)
     c = inst.circuit
     betas, gammas, alphas = ([rng.randrange(P) for _ in range(c.num_challenges)] for _ in range(3))
     zs_pp = PR.zs_partial_products(inst, betas, gammas)
