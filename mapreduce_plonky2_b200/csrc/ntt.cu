@@ -264,7 +264,14 @@ struct TwoPass {
 // element in pass 2 were this address arithmetic (profiles/r1f_lde_pass2_opcode_mix.txt).
 GL_DEV bool within_shard(const LdeMap &m, size_t L0, size_t len) { return ((L0 ^ (L0 + len - 1)) >> m.ls_log) == 0; }
 
-__global__ void __launch_bounds__(1024)
+// MAXT / MINB: launch bounds.  The four-step tiles run 256 threads per CTA.  Measured on the wide batch
+// (gpurun_out/r2n_ntt_variants.log): 4 CTAs/SM at 64 registers 45.6 ms per LDE, 3 CTAs at 80 registers 47.6 ms, 2 CTAs at
+// 102-114 registers 54.1 ms -- the passes want resident warps, not registers, so the bound stays at 4.
+#ifndef MP2_NTT_MINB
+#define MP2_NTT_MINB 4
+#endif
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
         TwoPass tp, const u64 *__restrict__ W1, const u64 *__restrict__ Wn, const u64 *__restrict__ scale) {
   extern __shared__ u64 sm[];
@@ -324,7 +331,8 @@ k_pass1(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, siz
 
 // pass 2: tile = LINES adjacent rows; size-n2 transform along each (contiguous) row: the tile is `total`
 // consecutive elements on both sides.  grid = (n1 / LINES, ncols, cosets)
-__global__ void __launch_bounds__(1024)
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 k_pass2(const u64 *__restrict__ in, size_t in_stride, u64 *__restrict__ out, size_t out_stride, LdeMap map,
         LdeMap out_map, TwoPass tp, const u64 *__restrict__ W2) {
   extern __shared__ u64 sm[];
@@ -412,6 +420,31 @@ static Status allow_smem(K kernel, size_t bytes) {
   return "";
 }
 
+template <typename... A>
+static Status launch_pass1(dim3 grid, u32 threads, size_t smem, cudaStream_t st, A... args) {
+  if (threads <= 256) {
+    MP2_TRY(allow_smem(k_pass1<256, MP2_NTT_MINB>, smem));
+    { ProfScope _p("k_pass1", st); k_pass1<256, MP2_NTT_MINB><<<grid, threads, smem, st>>>(args...); }
+  } else {
+    MP2_TRY(allow_smem(k_pass1<1024, 1>, smem));
+    { ProfScope _p("k_pass1", st); k_pass1<1024, 1><<<grid, threads, smem, st>>>(args...); }
+  }
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+template <typename... A>
+static Status launch_pass2(dim3 grid, u32 threads, size_t smem, cudaStream_t st, A... args) {
+  if (threads <= 256) {
+    MP2_TRY(allow_smem(k_pass2<256, MP2_NTT_MINB>, smem));
+    { ProfScope _p("k_pass2", st); k_pass2<256, MP2_NTT_MINB><<<grid, threads, smem, st>>>(args...); }
+  } else {
+    MP2_TRY(allow_smem(k_pass2<1024, 1>, smem));
+    { ProfScope _p("k_pass2", st); k_pass2<1024, 1><<<grid, threads, smem, st>>>(args...); }
+  }
+  MP2_LAUNCH_CHECK();
+  return "";
+}
+
 Status ntt_canonicalize(const u64 *in, size_t in_stride, u64 *out, size_t out_stride, size_t ncols, size_t n,
                         cudaStream_t st) {
   size_t total = ncols * n;
@@ -465,14 +498,12 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
   {
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);
-    MP2_TRY(allow_smem(k_pass1, smem));
     const size_t ctas = (((size_t)1 << tp.b) >> tp.lines_log) * ncols;
     if (ctas > 0x7fffffffull) return "batch too large for one iNTT launch (columns x tiles > 2^31)";
     tp.ncols = (u32)ncols;
     tp.tg_log = std::min(2u, tp.b - tp.lines_log);
     dim3 grid((unsigned)ctas, 1, 1);
-    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(values, in_stride, tmp, n, none, tp, W1, Wn, nullptr); }
-    MP2_LAUNCH_CHECK();
+    MP2_TRY(launch_pass1(grid, threads_for(tile_log), smem, st, values, in_stride, tmp, n, none, tp, W1, Wn, nullptr));
   }
   {
     u32 lines_log = std::min(tp.lines_log, tp.a);
@@ -480,10 +511,8 @@ Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_str
     tp2.lines_log = lines_log;
     u32 tile_log = tp.b + lines_log;
     size_t smem = smem_bytes_for(tile_log);
-    MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, 1);
-    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(tmp, n, coeffs, out_stride, none, none, tp2, W2); }
-    MP2_LAUNCH_CHECK();
+    MP2_TRY(launch_pass2(grid, threads_for(tile_log), smem, st, tmp, n, coeffs, out_stride, none, none, tp2, W2));
   }
   return "";
 }
@@ -560,14 +589,12 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
   if (phase != LDE_PASS2) {
     u32 tile_log = tp.a + tp.lines_log;
     size_t smem = smem_bytes_for(tile_log);
-    MP2_TRY(allow_smem(k_pass1, smem));
     const size_t ctas = ((((size_t)1 << tp.b) >> tp.lines_log) << rate_bits) * ncols;
     if (ctas > 0x7fffffffull) return "batch too large for one LDE launch (columns x cosets x tiles > 2^31)";
     tp.ncols = (u32)ncols;
     tp.tg_log = std::min(2u, tp.b - tp.lines_log);
     dim3 grid((unsigned)ctas, 1, 1);
-    { ProfScope _p("k_pass1", st); k_pass1<<<grid, threads_for(tile_log), smem, st>>>(coeffs, in_stride, mid, 0, mid_map, tp, W1, Wn, scale); }
-    MP2_LAUNCH_CHECK();
+    MP2_TRY(launch_pass1(grid, threads_for(tile_log), smem, st, coeffs, in_stride, mid, 0, mid_map, tp, W1, Wn, scale));
   }
   if (phase != LDE_PASS1) {
     u32 lines_log = std::min(tp.lines_log, tp.a);
@@ -576,10 +603,8 @@ Status ntt_coset_lde(const u64 *coeffs, size_t in_stride, u64 *lde, size_t lde_s
     tp2.coset0 = phase == LDE_PASS2 ? coset0 : 0;
     u32 tile_log = tp.b + lines_log;
     size_t smem = smem_bytes_for(tile_log);
-    MP2_TRY(allow_smem(k_pass2, smem));
     dim3 grid((unsigned)(((size_t)1 << tp.a) >> lines_log), (unsigned)ncols, phase == LDE_PASS2 ? ncosets : cosets);
-    { ProfScope _p("k_pass2", st); k_pass2<<<grid, threads_for(tile_log), smem, st>>>(mid, 0, lde, 0, mid_map, map, tp2, W2); }
-    MP2_LAUNCH_CHECK();
+    MP2_TRY(launch_pass2(grid, threads_for(tile_log), smem, st, mid, 0, lde, 0, mid_map, map, tp2, W2));
   }
   return "";
 }
