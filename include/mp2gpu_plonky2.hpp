@@ -239,10 +239,15 @@ struct FriCommitPhase {
 
 // Challenger<F, H> (plonky2 iop/challenger.rs): the overwrite-mode duplex sponge of the Fiat-Shamir transcript.
 // `Permute` is any callable void(uint64_t state[12]); DevicePermute sends the state through mp2gpu_permute_batch
-// (the library has no host hashing path), tests instantiate it with the CPU oracle's permutation.
+// (round 1's only option: a ~60 us round trip per duplexing); HostPermute below keeps the transcript on the host.
 template <Hasher H>
 struct DevicePermute {
   void operator()(uint64_t *state) const { check(mp2gpu_permute_batch(state, 1, (uint32_t)H)); }
+};
+// The transcript's usual permutation: on the host (mp2gpu_transcript_permute), as plonky2's own challenger does.
+template <Hasher H>
+struct HostPermute {
+  void operator()(uint64_t *state) const { check(mp2gpu_transcript_permute(state, (uint32_t)H)); }
 };
 template <typename Permute>
 struct Challenger {

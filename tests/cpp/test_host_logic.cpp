@@ -67,8 +67,29 @@ static int run(uint32_t kind) {
   return 0;
 }
 
+// HostPermute (mp2gpu_transcript_permute, the transcript's host-side permutation) == the oracle's, both hashers
+static int host_permute_matches_oracle() {
+  uint64_t seed = 4242;
+  for (int it = 0; it < 50; it++) {
+    uint64_t a[12], b[12], c[12];
+    for (int i = 0; i < 12; i++) a[i] = b[i] = c[i] = it < 2 ? (it ? ~0ULL : 0ULL) : splitmix(seed);
+    uint64_t a2[12];
+    for (int i = 0; i < 12; i++) a2[i] = a[i];
+    HostPermute<Hasher::Poseidon>()(a);
+    orc_permute(0, b);
+    HostPermute<Hasher::Poseidon2>()(a2);
+    orc_permute(1, c);
+    for (int i = 0; i < 12; i++) {
+      REQUIRE(a[i] == orc_gl_canon(b[i]));
+      REQUIRE(a2[i] == orc_gl_canon(c[i]));
+    }
+  }
+  return 0;
+}
+
 int main() {
   if (run(0) || run(1)) return 1;
+  if (host_permute_matches_oracle()) return 1;
   FriConfig cfg;
   REQUIRE((cfg.reduction_arity_bits(14) == std::vector<size_t>{4, 4, 4}));
   REQUIRE((cfg.reduction_arity_bits(13) == std::vector<size_t>{4, 4}));
