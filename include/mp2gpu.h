@@ -304,12 +304,18 @@ const char *mp2gpu_transcript_observe(uint64_t *state12, uint64_t *buffer8, uint
                                         delta 25..28, S-box inputs of full rounds 1..3 at 29 + 12 (round - 1) + i, of the
                                         22 partial rounds at 65 + r, of the last full rounds at 87 + 12 round + i; 123
                                         constraints: swap bit, 4 deltas, 36 + 22 + 48 S-box inputs, 12 outputs */
+#define MP2GPU_GATE_ARITHMETIC_EXT 5u /* ArithmeticExtensionGate{num_ops}, D = 2: per op the 2-wire groups m0 | m1 | addend |
+                                        output at 8i; output - (c0 m0 m1 + c1 addend), 2 constraints per op */
+#define MP2GPU_GATE_MUL_EXT 6u       /* MulExtensionGate{num_ops}: m0 | m1 | output at 6i; output - c0 m0 m1 */
+#define MP2GPU_GATE_BASE_SUM 7u      /* BaseSumGate<B = param>{num_limbs = num_ops}: wire 0 = sum, limbs from wire 1;
+                                        sum_i limb_i B^i - sum, then prod_{k < B} (limb_i - k) per limb */
 typedef struct mp2gpu_gate {
   uint32_t kind;            /* MP2GPU_GATE_* */
   uint32_t num_ops;         /* see the kinds above */
   uint32_t selector_index;  /* SelectorsInfo::selector_indices[gate] */
   uint32_t group_begin;     /* SelectorsInfo::groups[selector_index] = group_begin..group_end (gate indices) */
   uint32_t group_end;
+  uint32_t param;           /* BaseSumGate: the base B; 0 otherwise */
 } mp2gpu_gate;
 typedef struct mp2gpu_circuit {   /* the CommonCircuitData fields the vanishing polynomial depends on */
   uint32_t degree_bits;

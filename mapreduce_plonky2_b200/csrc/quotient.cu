@@ -15,8 +15,8 @@
 //     of challenge c ARE its 2^qb chunks of n, back to back -- the chunk matrix is committed in place with
 //     `from_coeffs` (the prover's quotient_polys_commitment).
 // Gate set: the staged subset of mp2-common/src/serialization/circuit_data_serialization.rs:234-266 that
-// oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate, PoseidonGate; anything else is
-// an error.
+// oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate, PoseidonGate,
+// ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>; anything else is an error.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -33,7 +33,7 @@ constexpr u32 kMaxGates = 32, kMaxChallenges = 4, kMaxQuotientBits = 4;
 constexpr u64 kUnusedSelector = 0xFFFFFFFFull;
 
 struct QGate {
-  u32 kind, num_ops, selector, group_begin, group_end;
+  u32 kind, num_ops, selector, group_begin, group_end, param;
 };
 struct QParams {
   u32 n_log, qb, nch, num_wires, R, num_constants, num_selectors, npp, num_gates, gate_term_base, nterms;
@@ -117,6 +117,34 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
       for (u32 k = 0; k < gate.num_ops; k++) cons(k, gl_sub(gc[k], wi[k]));
     } else if (gate.kind == MP2GPU_GATE_PUBLIC_INPUT) {
       for (u32 k = 0; k < 4; k++) cons(k, gl_sub(wi[k], P.pi_hash[k]));
+    } else if (gate.kind == MP2GPU_GATE_ARITHMETIC_EXT || gate.kind == MP2GPU_GATE_MUL_EXT) {
+      // D = 2, X^2 = 7: (a0 + a1 X)(b0 + b1 X) = (a0 b0 + 7 a1 b1) + (a0 b1 + a1 b0) X
+      const bool arith = gate.kind == MP2GPU_GATE_ARITHMETIC_EXT;
+      const u32 stride = arith ? 8 : 6, out_at = arith ? 6 : 4;
+      const u64 c0 = gc[0], c1 = arith ? gc[1] : 0;
+      for (u32 op = 0; op < gate.num_ops; op++) {
+        const u64 *w = wi + stride * op;
+        const u64 p0 = gl_mul_add(gl_mul(7, w[1]), w[3], gl_mul(w[0], w[2]));
+        const u64 p1 = gl_mul_add(w[0], w[3], gl_mul(w[1], w[2]));
+        u64 r0 = gl_mul(c0, p0), r1 = gl_mul(c0, p1);
+        if (arith) {
+          r0 = gl_mul_add(c1, w[4], r0);
+          r1 = gl_mul_add(c1, w[5], r1);
+        }
+        cons(2 * op, gl_sub(w[out_at], r0));
+        cons(2 * op + 1, gl_sub(w[out_at + 1], r1));
+      }
+    } else if (gate.kind == MP2GPU_GATE_BASE_SUM) {
+      const u64 base = gate.param;
+      u64 acc = 0;
+      for (u32 k = gate.num_ops; k-- > 0;) acc = gl_mul_add(acc, base, wi[1 + k]);  // reduce_with_powers(limbs, B)
+      cons(0, gl_sub(acc, wi[0]));
+      for (u32 k = 0; k < gate.num_ops; k++) {
+        const u64 l = wi[1 + k];
+        u64 pr = l;
+        for (u32 j = 1; j < gate.param; j++) pr = gl_mul(pr, gl_sub(l, (u64)j));
+        cons(1 + k, pr);
+      }
     } else if (gate.kind == MP2GPU_GATE_POSEIDON) {
       // PoseidonGate::eval_unfiltered (plonky2 gates/poseidon.rs), naive round structure: every S-box input except
       // round 0's is a wire the state is overwritten with (the constraint polynomials equal those of plonky2's fast
@@ -216,6 +244,7 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
     d.selector = s.selector_index;
     d.group_begin = s.group_begin;
     d.group_end = s.group_end;
+    d.param = s.param;
     if (s.selector_index >= ci->num_selectors) return "quotient_polys: gate selector_index out of range";
     if (s.group_begin > g || s.group_end <= g || s.group_end > ci->num_gates) return "quotient_polys: gate is outside its selector group";
     u32 nc = 0, nk = 0;
@@ -235,12 +264,27 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
         if (!pi_hash) return "quotient_polys: PublicInputGate needs public_inputs_hash";
         if (ci->num_wires < 4) return "quotient_polys: PublicInputGate needs 4 wires";
         break;
+      case MP2GPU_GATE_ARITHMETIC_EXT:
+        nc = 2 * s.num_ops;
+        nk = 2;
+        if (8 * s.num_ops > ci->num_wires) return "quotient_polys: ArithmeticExtensionGate ops exceed the wires";
+        break;
+      case MP2GPU_GATE_MUL_EXT:
+        nc = 2 * s.num_ops;
+        nk = 1;
+        if (6 * s.num_ops > ci->num_wires) return "quotient_polys: MulExtensionGate ops exceed the wires";
+        break;
+      case MP2GPU_GATE_BASE_SUM:
+        nc = 1 + s.num_ops;
+        if (s.param < 2 || s.param > 16) return "quotient_polys: BaseSumGate base must be 2..16";
+        if (1 + s.num_ops > ci->num_wires) return "quotient_polys: BaseSumGate limbs exceed the wires";
+        break;
       case MP2GPU_GATE_POSEIDON:
         nc = 123;
         if (ci->num_wires < 135) return "quotient_polys: PoseidonGate needs 135 wires";
         break;
       default:
-        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon)";
+        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum)";
     }
     ngc = std::max(ngc, nc);
     max_gate_constants = std::max(max_gate_constants, nk);

@@ -6,7 +6,7 @@ caller asks for) comes back.  ctypes + numpy only.
 The descriptor mirrors the ``CommonCircuitData`` fields the vanishing polynomial depends on: ``gates`` in circuit
 order, ``SelectorsInfo { selector_indices, groups }``, ``num_constants`` (selectors + gate constants), the wire counts
 and ``quotient_degree_factor``.  Gate kinds outside the staged subset (ArithmeticGate, ConstantGate, PublicInputGate,
-NoopGate, PoseidonGate of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
+NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B> of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
 """
 from __future__ import annotations
 
@@ -20,12 +20,13 @@ from . import _lib
 from ._lib import Mp2GpuError
 from .plonky2 import POSEIDON2, MerkleCap, MerkleTree, PolynomialBatch, _arr, _col_ptrs, _ptr
 
-GATE_KINDS = {"noop": 0, "arithmetic": 1, "constant": 2, "public_input": 3, "poseidon": 4}
+GATE_KINDS = {"noop": 0, "arithmetic": 1, "constant": 2, "public_input": 3, "poseidon": 4, "arithmetic_extension": 5,
+              "mul_extension": 6, "base_sum": 7}
 
 
 class _CGate(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("num_ops", C.c_uint32), ("selector_index", C.c_uint32),
-                ("group_begin", C.c_uint32), ("group_end", C.c_uint32)]
+                ("group_begin", C.c_uint32), ("group_end", C.c_uint32), ("param", C.c_uint32)]
 
 
 class _CCircuit(C.Structure):
@@ -36,8 +37,9 @@ class _CCircuit(C.Structure):
 
 @dataclass
 class GateDesc:
-    kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon"
-    num_ops: int = 0    # ArithmeticGate::num_ops / ConstantGate::num_consts
+    kind: str           # one of GATE_KINDS
+    num_ops: int = 0    # Arithmetic(Extension)Gate / MulExtensionGate::num_ops, ConstantGate::num_consts, BaseSumGate::num_limbs
+    param: int = 0      # BaseSumGate<B>: B
 
 
 @dataclass
@@ -56,7 +58,7 @@ class CircuitDesc:
     def from_circuit(cls, c) -> "CircuitDesc":
         """From any object with the same attribute names (e.g. tests/plonk_ref.Circuit)."""
         return cls(c.degree_bits, c.num_wires, c.num_routed_wires, c.num_constants,
-                   [GateDesc(g.kind, g.num_ops) for g in c.gates], list(c.selector_indices), list(c.groups),
+                   [GateDesc(g.kind, g.num_ops, getattr(g, "param", 0)) for g in c.gates], list(c.selector_indices), list(c.groups),
                    c.quotient_degree_bits, c.num_challenges)
 
     @property
@@ -73,7 +75,7 @@ class CircuitDesc:
             if g.kind not in GATE_KINDS:
                 raise Mp2GpuError("gate kind %r is outside the supported subset %s" % (g.kind, sorted(GATE_KINDS)))
             a, b = self.groups[self.selector_indices[i]]
-            arr[i] = _CGate(GATE_KINDS[g.kind], g.num_ops, self.selector_indices[i], a, b)
+            arr[i] = _CGate(GATE_KINDS[g.kind], g.num_ops, self.selector_indices[i], a, b, g.param)
         cc = _CCircuit(self.degree_bits, self.quotient_degree_bits, self.num_challenges, self.num_wires,
                        self.num_routed_wires, self.num_constants, self.num_selectors, len(self.gates), arr)
         return cc, arr  # keep `arr` alive with the struct

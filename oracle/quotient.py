@@ -10,7 +10,7 @@ The prover evaluates, at every point x_i = g * w_{8n}^i of the coset LDE the thr
 then `coset_ifft` turns each q_c into coefficients and cuts it into `quotient_degree_factor` chunks of n, which are
 committed with `from_coeffs`.  Gate set restated here (the staged subset of
 mp2-common/src/serialization/circuit_data_serialization.rs:234-266): ArithmeticGate, ConstantGate, PublicInputGate,
-NoopGate, PoseidonGate behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
+NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B> behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
 
 Pinned by definition, not by the Rust prover (absent): tests/plonk_ref.py restates the VERIFIER's
 `eval_vanishing_poly` + final identity, and the quotients computed here must pass it at random points
@@ -88,6 +88,27 @@ def _gate_constraints(desc, local_constants, local_wires, pi_hash):
             cons = []
         elif gate.kind == "poseidon":
             cons = _poseidon_gate(local_wires)
+        elif gate.kind == "arithmetic_extension":   # gates/arithmetic_extension.rs, D = 2: out - (c0 m0 m1 + c1 addend)
+            cons = []
+            for i in range(gate.num_ops):
+                w = local_wires[8 * i:8 * i + 8]
+                cons.append((w[6] - (gc[0] * (w[0] * w[2] + 7 * w[1] * w[3]) + gc[1] * w[4])) % P)
+                cons.append((w[7] - (gc[0] * (w[0] * w[3] + w[1] * w[2]) + gc[1] * w[5])) % P)
+        elif gate.kind == "mul_extension":          # gates/multiplication_extension.rs: out - c0 m0 m1
+            cons = []
+            for i in range(gate.num_ops):
+                w = local_wires[6 * i:6 * i + 6]
+                cons.append((w[4] - gc[0] * (w[0] * w[2] + 7 * w[1] * w[3])) % P)
+                cons.append((w[5] - gc[0] * (w[0] * w[3] + w[1] * w[2])) % P)
+        elif gate.kind == "base_sum":               # gates/base_sum.rs BaseSumGate<B>{num_limbs}: B = gate.param
+            limbs = local_wires[1:1 + gate.num_ops]
+            total = sum(l * pow(gate.param, i, P) for i, l in enumerate(limbs)) % P
+            cons = [(total - local_wires[0]) % P]
+            for l in limbs:
+                pr = 1
+                for k in range(gate.param):
+                    pr = pr * (l - k) % P
+                cons.append(pr)
         else:
             raise ValueError("gate kind %r is outside the staged subset" % gate.kind)
         for i, v in enumerate(cons):

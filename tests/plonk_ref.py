@@ -104,19 +104,69 @@ def poseidon_gate_constraints(w):
     return cons
 
 
+# ---- extension-field and base-sum gates (plonky2 gates/arithmetic_extension.rs, multiplication_extension.rs,
+# base_sum.rs), D = 2, X^2 = W = 7 ----------------------------------------------------------------------------------
+#   ArithmeticExtensionGate{num_ops}: per op i the D-wire groups multiplicand_0 at 4Di, multiplicand_1 at 4Di + D, addend
+#     at 4Di + 2D, output at 4Di + 3D;  constraint (D components): output - (c0 * m0 * m1 + c1 * addend)
+#   MulExtensionGate{num_ops}: m0 at 3Di, m1 at 3Di + D, output at 3Di + 2D;  output - c0 * m0 * m1
+#   BaseSumGate<B>{num_limbs}: wire 0 = sum, limbs at 1..;  [sum_i limb_i B^i - sum] ++ [prod_{k<B} (limb_i - k)]_i
+EXT_W = 7
+
+
+def ext_mul(a, b):
+    return ((a[0] * b[0] + EXT_W * a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def arithmetic_extension_constraints(w, num_ops, c0, c1):
+    out = []
+    for i in range(num_ops):
+        m0, m1, ad, o = (w[8 * i + 2 * k:8 * i + 2 * k + 2] for k in range(4))
+        pr = ext_mul(m0, m1)
+        out += [(o[k] - (c0 * pr[k] + c1 * ad[k])) % P for k in range(2)]
+    return out
+
+
+def mul_extension_constraints(w, num_ops, c0):
+    out = []
+    for i in range(num_ops):
+        m0, m1, o = (w[6 * i + 2 * k:6 * i + 2 * k + 2] for k in range(3))
+        pr = ext_mul(m0, m1)
+        out += [(o[k] - c0 * pr[k]) % P for k in range(2)]
+    return out
+
+
+def base_sum_constraints(w, num_limbs, base):
+    limbs = w[1:1 + num_limbs]
+    acc = 0
+    for l in reversed(limbs):
+        acc = (acc * base + l) % P
+    out = [(acc - w[0]) % P]
+    for l in limbs:
+        pr = 1
+        for k in range(base):
+            pr = pr * (l - k) % P
+        out.append(pr)
+    return out
+
+
 @dataclass
 class Gate:
-    kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon"
-    num_ops: int = 0    # arithmetic: ops per row (4 wires each); constant: number of constants
+    kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon" | "arithmetic_extension" |
+                        # "mul_extension" | "base_sum"
+    num_ops: int = 0    # arithmetic(_extension) / mul_extension: ops per row; constant: number of constants;
+                        # base_sum: num_limbs
+    param: int = 0      # base_sum: the base B
 
     @property
     def num_constraints(self) -> int:
         return {"arithmetic": self.num_ops, "constant": self.num_ops, "public_input": 4, "noop": 0,
-                "poseidon": POSEIDON_GATE_CONSTRAINTS}[self.kind]
+                "poseidon": POSEIDON_GATE_CONSTRAINTS, "arithmetic_extension": 2 * self.num_ops,
+                "mul_extension": 2 * self.num_ops, "base_sum": 1 + self.num_ops}[self.kind]
 
     @property
     def num_constants(self) -> int:
-        return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0, "poseidon": 0}[self.kind]
+        return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0, "poseidon": 0,
+                "arithmetic_extension": 2, "mul_extension": 1, "base_sum": 0}[self.kind]
 
 
 @dataclass
@@ -184,7 +234,7 @@ def subgroup(bits: int) -> List[int]:
 
 
 def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num_routed_wires: int = 8,
-                       two_groups: bool = False, with_poseidon: bool = False) -> Instance:
+                       two_groups: bool = False, with_poseidon: bool = False, extra_gates: bool = False) -> Instance:
     rng = random.Random(seed)
     n = 1 << degree_bits
     if with_poseidon:          # standard_recursion_config's shape: a PoseidonGate row needs all 135 wires
@@ -199,9 +249,19 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
         gates.append(Gate("poseidon"))
         selector_indices.append(len(groups))
         groups.append((4, 5))
+    extra = []
+    if extra_gates:            # a third selector group: filtered degree (3 + 1) + 4 = 8 <= 9
+        if num_routed_wires < 8:
+            raise ValueError("the extension gates need at least 8 routed wires")
+        base = len(gates)
+        gates += [Gate("arithmetic_extension", num_routed_wires // 8), Gate("mul_extension", num_routed_wires // 6),
+                  Gate("base_sum", min(6, num_routed_wires - 1), 2), Gate("base_sum", min(5, num_routed_wires - 1), 4)]
+        selector_indices += [len(groups)] * 4
+        groups.append((base, base + 4))
+        extra = list(range(base, base + 4))
     c = Circuit(degree_bits, num_wires, num_routed_wires, gates, selector_indices, groups)
     pi_hash = [rng.randrange(P) for _ in range(4)]
-    row_gate = [3] + [rng.choice([0, 0, 0, 1, 2] + ([4, 4] if with_poseidon else [])) for _ in range(n - 1)]     # row 0: the public-input gate
+    row_gate = [3] + [rng.choice([0, 0, 0, 1, 2] + ([4, 4] if with_poseidon else []) + extra) for _ in range(n - 1)]     # row 0: the public-input gate
     consts = [[0] * n for _ in range(c.num_constants)]
     for row, g in enumerate(row_gate):
         for s, (a, b) in enumerate(groups):
@@ -243,6 +303,29 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
         elif g == 3:
             for k in range(4):
                 wires[k][row] = pi_hash[k]
+        elif gates[g].kind == "arithmetic_extension":
+            c0, c1 = consts[c.num_selectors][row], consts[c.num_selectors + 1][row]
+            for i in range(gates[g].num_ops):
+                m0, m1, ad = ([wires[8 * i + 2 * k + t][row] for t in range(2)] for k in range(3))
+                pr = ext_mul(m0, m1)
+                for t in range(2):
+                    wires[8 * i + 6 + t][row] = (c0 * pr[t] + c1 * ad[t]) % P
+                    outputs.append((8 * i + 6 + t, row))
+        elif gates[g].kind == "mul_extension":
+            c0 = consts[c.num_selectors][row]
+            for i in range(gates[g].num_ops):
+                m0, m1 = ([wires[6 * i + 2 * k + t][row] for t in range(2)] for k in range(2))
+                pr = ext_mul(m0, m1)
+                for t in range(2):
+                    wires[6 * i + 4 + t][row] = c0 * pr[t] % P
+                    outputs.append((6 * i + 4 + t, row))
+        elif gates[g].kind == "base_sum":
+            base, nl = gates[g].param, gates[g].num_ops
+            limbs = [rng.randrange(base) for _ in range(nl)]
+            for i, l in enumerate(limbs):
+                wires[1 + i][row] = l
+            wires[0][row] = sum(l * base ** i for i, l in enumerate(limbs)) % P
+            outputs.append((0, row))
         else:
             ins = [wires[j][row] for j in range(12)]
             for j in range(12):   # some inputs are copies of earlier outputs (inputs and outputs are routed wires)
@@ -328,6 +411,12 @@ def gate_constraints(c: Circuit, local_constants: List[int], local_wires: List[i
             cons = [(local_wires[i] - pi_hash[i]) % P for i in range(4)]
         elif gate.kind == "poseidon":
             cons = poseidon_gate_constraints(local_wires)
+        elif gate.kind == "arithmetic_extension":
+            cons = arithmetic_extension_constraints(local_wires, gate.num_ops, gate_consts[0], gate_consts[1])
+        elif gate.kind == "mul_extension":
+            cons = mul_extension_constraints(local_wires, gate.num_ops, gate_consts[0])
+        elif gate.kind == "base_sum":
+            cons = base_sum_constraints(local_wires, gate.num_ops, gate.param)
         else:
             cons = []
         for i, v in enumerate(cons):

@@ -28,7 +28,8 @@ def _commit3(G, inst, zs_pp, rate_bits, cap, kind):
 @pytest.mark.parametrize("seed,degree_bits,two_groups,kind,rate_bits,qbits,with_poseidon", [
     (1, 3, False, 0, 3, 3, False), (2, 4, False, 1, 3, 3, False), (3, 4, True, 0, 3, 3, False), (4, 5, True, 1, 3, 3, False),
     (5, 6, True, 0, 3, 2, False), (6, 12, True, 1, 3, 3, False),
-    (7, 3, False, 0, 3, 3, True), (8, 5, True, 1, 3, 3, True), (9, 10, True, 1, 3, 3, True)])
+    (7, 3, False, 0, 3, 3, True), (8, 5, True, 1, 3, 3, True), (9, 10, True, 1, 3, 3, True),
+    (10, 4, False, 0, 3, 3, "extra"), (11, 5, True, 1, 3, 3, "both"), (12, 9, True, 0, 3, 3, "both")])
 def test_quotient_matches_oracle_and_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups, kind, rate_bits, qbits,
                                                                   with_poseidon):
     import mapreduce_plonky2_b200 as G
@@ -37,7 +38,8 @@ def test_quotient_matches_oracle_and_passes_the_verifier_identity(oracle, seed, 
 
     G.init(0)
     rng = random.Random(0x7171 + seed)
-    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups, with_poseidon=with_poseidon)
+    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups,
+                                 with_poseidon=with_poseidon in (True, "both"), extra_gates=with_poseidon in ("extra", "both"))
     c = inst.circuit
     c.quotient_degree_bits = qbits
     betas, gammas, alphas = ([rng.randrange(P) for _ in range(c.num_challenges)] for _ in range(3))
@@ -94,7 +96,7 @@ def test_unsupported_gate_and_shape_errors(oracle):
     zs_pp = PR.zs_partial_products(inst, betas, gammas)
     b_cs, b_w, b_z = _commit3(G, inst, zs_pp, 3, 2, 0)
     desc = Q.CircuitDesc.from_circuit(c)
-    desc.gates[2] = Q.GateDesc("base_sum")
+    desc.gates[2] = Q.GateDesc("random_access")
     with pytest.raises(G.Mp2GpuError, match="outside the supported subset"):
         Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, 3, 2, hash_kind=0)
     desc = Q.CircuitDesc.from_circuit(c)

@@ -32,12 +32,13 @@ def test_poseidon_gate_witness_satisfies_its_constraints_and_breaks_when_tampere
             assert any(PR.poseidon_gate_constraints(bad))
 
 
-@pytest.mark.parametrize("seed,degree_bits,two_groups,with_poseidon", [(1, 3, False, False), (2, 4, False, False),
-                                                                        (3, 4, True, False), (4, 5, True, False),
-                                                                        (5, 3, False, True), (6, 4, True, True)])
-def test_quotient_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups, with_poseidon):
+@pytest.mark.parametrize("seed,degree_bits,two_groups,with_poseidon,extra", [
+    (1, 3, False, False, False), (2, 4, False, False, False), (3, 4, True, False, False), (4, 5, True, False, False),
+    (5, 3, False, True, False), (6, 4, True, True, False), (7, 4, False, False, True), (8, 4, True, True, True)])
+def test_quotient_passes_the_verifier_identity(oracle, seed, degree_bits, two_groups, with_poseidon, extra):
     rng = random.Random(0x5151 + seed)
-    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups, with_poseidon=with_poseidon)
+    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups, with_poseidon=with_poseidon,
+                                 extra_gates=extra)
     c = inst.circuit
     betas, gammas, alphas = ([rng.randrange(P) for _ in range(c.num_challenges)] for _ in range(3))
     zs_pp = PR.zs_partial_products(inst, betas, gammas)
