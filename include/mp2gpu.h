@@ -338,9 +338,10 @@ const char *mp2gpu_quotient_polys(const mp2gpu_circuit *circuit, const mp2gpu_ba
                                   uint32_t hash_kind, uint64_t *const *chunks_out, uint64_t *leaves_out,
                                   uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **quotient_batch_out);
 
-/* Returns the calling thread's cached device blocks and the unused part of the device's stream-ordered pool to the
- * driver (the library keeps freed scratch for reuse: a prover repeats the same shapes).  Call it when another
- * allocator in the process needs the memory. */
+/* Returns the calling thread's cached device blocks, the device's cached twiddle tables and the unused part of its
+ * stream-ordered pool to the driver (the library keeps freed scratch for reuse: a prover repeats the same shapes;
+ * tables are rebuilt on demand).  Call it when another allocator in the process needs the memory and no other
+ * thread has library work in flight on this device. */
 const char *mp2gpu_trim(void);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------- */

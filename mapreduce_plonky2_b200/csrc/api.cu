@@ -438,6 +438,7 @@ const char *mp2gpu_trim(void) {
     d.idle.clear();
     d.idle_bytes = 0;
     MP2_CUDA(cudaStreamSynchronize(st));
+    table_cache_clear();
     cudaMemPool_t pool;
     MP2_CUDA(cudaDeviceGetDefaultMemPool(&pool, t_ctx.device));
     MP2_CUDA(cudaMemPoolTrimTo(pool, 0));

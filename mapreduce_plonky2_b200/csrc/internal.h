@@ -132,6 +132,7 @@ Status table_roots(u32 log_t, cudaStream_t st, const u64 **out);
 // polynomial batches; 7^(arity^i) for FRI layer i)
 static const u64 kCosetShift = 7;
 Status table_coset_scale(u32 log_n, u32 rate_bits, u64 shift, cudaStream_t st, const u64 **out);
+void table_cache_clear();  // frees the current device's cached tables (mp2gpu_trim)
 
 // ---- transforms (ntt.cu) ----
 Status ntt_intt(const u64 *values, size_t in_stride, u64 *coeffs, size_t out_stride, size_t ncols,

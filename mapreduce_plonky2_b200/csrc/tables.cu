@@ -50,10 +50,17 @@ Status get_table(int kind, u32 log, u64 base, cudaStream_t st, const u64 **out) 
   size_t count = (size_t)1 << log;
   u64 *d = nullptr;
   MP2_CUDA(cudaMalloc(&d, sizeof(u64) * count));
-  k_fill_powers<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d, base, count);
-  MP2_LAUNCH_CHECK();
-  // other threads (other streams) may pick the table up from the cache right away
-  MP2_CUDA(cudaStreamSynchronize(st));
+  Status built = [&]() -> Status {
+    k_fill_powers<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d, base, count);
+    MP2_LAUNCH_CHECK();
+    // other threads (other streams) may pick the table up from the cache right away
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  }();
+  if (!built.empty()) {
+    cudaFree(d);
+    return built;
+  }
   g_tables[key] = d;
   *out = d;
   return "";
@@ -83,15 +90,38 @@ Status table_coset_scale(u32 log_n, u32 rate_bits, u64 shift, cudaStream_t st, c
   }
   u64 *d = nullptr, *d_bases = nullptr;
   MP2_CUDA(cudaMalloc(&d, sizeof(u64) * count));
-  MP2_CUDA(cudaMalloc(&d_bases, sizeof(u64) * cosets));
-  MP2_CUDA(cudaMemcpyAsync(d_bases, bases.data(), sizeof(u64) * cosets, cudaMemcpyHostToDevice, st));
-  k_fill_coset_scale<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d, d_bases, log_n, count);
-  MP2_LAUNCH_CHECK();
-  MP2_CUDA(cudaStreamSynchronize(st));
-  MP2_CUDA(cudaFree(d_bases));
+  Status built = [&]() -> Status {
+    MP2_CUDA(cudaMalloc(&d_bases, sizeof(u64) * cosets));
+    MP2_CUDA(cudaMemcpyAsync(d_bases, bases.data(), sizeof(u64) * cosets, cudaMemcpyHostToDevice, st));
+    k_fill_coset_scale<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(d, d_bases, log_n, count);
+    MP2_LAUNCH_CHECK();
+    MP2_CUDA(cudaStreamSynchronize(st));
+    return "";
+  }();
+  if (d_bases) cudaFree(d_bases);
+  if (!built.empty()) {
+    cudaFree(d);
+    return built;
+  }
   g_tables[key] = d;
   *out = d;
   return "";
+}
+
+// mp2gpu_trim: drop the cached tables of the current device (rebuilt on demand).  Callers must not have transforms in
+// flight on other threads.
+void table_cache_clear() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lock(g_mu);
+  for (auto it = g_tables.begin(); it != g_tables.end();) {
+    if (it->first.device == dev) {
+      cudaFree(it->second);
+      it = g_tables.erase(it);
+    } else {
+      ++it;
+    }
+  }
 }
 
 }  // namespace mp2

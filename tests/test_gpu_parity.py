@@ -338,3 +338,19 @@ def test_circuit_digest_on_device(G, oracle):
         parts = np.concatenate([cap.reshape(-1), oracle.hash_pad(np.zeros(0, dtype=np.uint64), kind),
                                 np.array([12], dtype=np.uint64)])
         assert np.array_equal(G.circuit_digest(cap, 12, kind), oracle.hash_no_pad(parts, kind))
+
+
+def test_trim_releases_and_everything_still_works(oracle):
+    """mp2gpu_trim drops the thread's block cache, the device's tables and the idle pool memory; the next commitment
+    rebuilds what it needs and is still bit-exact."""
+    import mapreduce_plonky2_b200 as G
+    from mapreduce_plonky2_b200 import _lib
+
+    G.init(0)
+    cols = field_elems(0x7717, (9, 1 << 9))
+    a = G.PolynomialBatch.from_values(cols, 3, False, 4, hash_kind=G.POSEIDON)
+    _lib.call("mp2gpu_trim")
+    b = G.PolynomialBatch.from_values(cols, 3, False, 4, hash_kind=G.POSEIDON)
+    ref = oracle.commit(cols, 3, 4, 0)
+    for pb in (a, b):
+        assert np.array_equal(pb.merkle_tree.cap.hashes, ref["cap"]) and np.array_equal(pb.merkle_tree.leaves, ref["leaves"])
