@@ -1,0 +1,100 @@
+"""Host mirror of plonky2's ``prove`` from the point where the witness is known (plonk/prover.rs
+``prove_with_partition_witness``; reached in the reference from ``circuit_data.prove(pw)`` at
+recursion-framework/src/circuit_builder.rs:308 and .../universal_verifier_gadget/wrap_circuit.rs:143), every data-path
+step on the device:
+
+    wires commitment -> challenger(circuit digest, public-inputs hash, wires cap) -> betas, gammas
+    -> Z / partial-products commitment (the VALUES are host work: the caller's callback) -> alphas
+    -> quotient polynomials + their commitment (mp2gpu_quotient_polys) -> zeta
+    -> OpeningSet at zeta and g*zeta (mp2gpu_batch_eval) -> prove_openings (FRI: mp2gpu_fri_*)
+
+The rows of the four batches never leave HBM.  Gate coverage is the quotient kernel's (quotient.py); lookups and
+zero-knowledge blinding are not supported (the reference enables neither).  ctypes + numpy only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Sequence
+
+import numpy as np
+
+from . import fri as GF
+from . import plonky2 as P2
+from .quotient import CircuitDesc, compute_quotient_polys
+
+P = P2.ORDER
+
+
+@dataclass
+class OpeningSet:
+    """``OpeningSet``: every polynomial at zeta (extension values, (count, 2) arrays) and the Zs at g*zeta."""
+    constants: np.ndarray
+    plonk_sigmas: np.ndarray
+    wires: np.ndarray
+    plonk_zs: np.ndarray
+    partial_products: np.ndarray
+    quotient_polys: np.ndarray
+    plonk_zs_next: np.ndarray
+
+
+@dataclass
+class Proof:
+    """``Proof<F, C, D>`` (plonk/proof.rs)."""
+    wires_cap: P2.MerkleCap
+    plonk_zs_partial_products_cap: P2.MerkleCap
+    quotient_polys_cap: P2.MerkleCap
+    openings: OpeningSet
+    opening_proof: GF.FriProof
+
+
+def primitive_root_of_unity(bits: int) -> int:
+    return pow(pow(7, (P - 1) >> 32, P), 1 << (32 - bits), P)
+
+
+def prove(circuit: CircuitDesc, constants_sigmas: P2.PolynomialBatch, circuit_digest: Sequence[int],
+          wires_values, public_inputs_hash: Sequence[int],
+          zs_partial_products: Callable[[List[int], List[int]], np.ndarray],
+          config: GF.FriConfig = None, hash_kind: int = P2.POSEIDON2) -> Proof:
+    """``constants_sigmas``: the device-resident batch committed at build time.  ``wires_values``: (num_wires, n).
+    ``zs_partial_products(betas, gammas)`` -> (num_challenges * (1 + num_partial_products), n) values, laid out
+    [Z_0.., partial products of challenge 0, of challenge 1, ...] (``wires_permutation_partial_products_and_zs``)."""
+    config = config or GF.FriConfig()
+    nch, db = circuit.num_challenges, circuit.degree_bits
+    commit = lambda cols: P2.PolynomialBatch.from_values(np.asarray(cols, dtype=np.uint64), config.rate_bits, False,
+                                                         config.cap_height, hash_kind=hash_kind, keep_on_device=True,
+                                                         fetch_leaves=False, fetch_coeffs=False, fetch_digests=False)
+    wires = commit(wires_values)
+    ch = GF.Challenger(hash_kind)
+    ch.observe_hash(np.asarray(circuit_digest, dtype=np.uint64))
+    ch.observe_hash(np.asarray(public_inputs_hash, dtype=np.uint64))
+    ch.observe_cap(wires.merkle_tree.cap)
+    betas, gammas = ch.get_n_challenges(nch), ch.get_n_challenges(nch)
+    zs_pp = commit(zs_partial_products(betas, gammas))
+    ch.observe_cap(zs_pp.merkle_tree.cap)
+    alphas = ch.get_n_challenges(nch)
+    quotient = compute_quotient_polys(circuit, constants_sigmas, wires, zs_pp, betas, gammas, alphas, public_inputs_hash,
+                                      config.rate_bits, config.cap_height, hash_kind=hash_kind, fetch_digests=False,
+                                      fetch_chunks=False)
+    ch.observe_cap(quotient.merkle_tree.cap)
+    zeta = ch.get_extension_challenge()
+    g = primitive_root_of_unity(db)
+    g_zeta = np.array([int(zeta[0]) * g % P, int(zeta[1]) * g % P], dtype=np.uint64)
+    oracles = [constants_sigmas, wires, zs_pp, quotient]
+    batches = [GF.FriBatchInfo(zeta, [(o, p) for o, b in enumerate(oracles) for p in range(b.num_polys)]),
+               GF.FriBatchInfo(g_zeta, [(2, p) for p in range(nch)])]
+    fri_openings = GF.open_batches(batches, oracles)
+    for vals in fri_openings:          # challenger.observe_openings(&openings.to_fri_openings())
+        ch.observe_extension_elements(vals)
+    at_zeta, nc = fri_openings[0], circuit.num_constants
+    w0 = constants_sigmas.num_polys
+    z0 = w0 + wires.num_polys
+    q0 = z0 + zs_pp.num_polys
+    openings = OpeningSet(at_zeta[:nc], at_zeta[nc:w0], at_zeta[w0:z0], at_zeta[z0:z0 + nch], at_zeta[z0 + nch:q0],
+                          at_zeta[q0:], fri_openings[1])
+    try:
+        opening_proof = GF.prove_openings(batches, oracles, ch, config.fri_params(db))
+    finally:
+        caps = wires.merkle_tree.cap, zs_pp.merkle_tree.cap, quotient.merkle_tree.cap
+        for b in (wires, zs_pp, quotient):
+            b.free()
+    return Proof(caps[0], caps[1], caps[2], openings, opening_proof)

@@ -429,7 +429,7 @@ def eval_vanishing_poly(c: Circuit, x: int, local_constants, local_wires, pi_has
     """plonky2 `eval_vanishing_poly` at one point x (any field element outside the subgroup)."""
     n, md, np_ = c.n, c.max_degree, c.num_partial_products
     z_h = (pow(x, n, P) - 1) % P
-    l_0 = z_h * pow(n * (x - 1) % P, P - 2, P) % P
+    l_0 = z_h * (n * (x - 1)).inv() if isinstance(x, Ext) else z_h * pow(n * (x - 1) % P, P - 2, P) % P
     z1_terms, pp_terms = [], []
     for i in range(c.num_challenges):
         z_x, z_gx = local_zs[i], next_zs[i]
@@ -481,3 +481,111 @@ def check_quotient_identity(inst: Instance, zs_pp_cols, quotient_chunks, betas, 
         if van[i] != z_h * t % P:
             return False
     return True
+
+
+# ---- the whole verifier, by definition (plonky2 plonk/verifier.rs `verify_with_challenges` + fri/verifier.rs) -------
+class Ext:
+    """GF(p^2) = F[X]/(X^2 - 7) with the operators the constraint code above uses on plain integers (`%` is the
+    identity), so that the same functions evaluate at an extension point."""
+    __slots__ = ("a", "b")
+
+    def __init__(self, a, b=0):
+        self.a, self.b = a % P, b % P
+
+    @staticmethod
+    def of(x):
+        return x if isinstance(x, Ext) else Ext(int(x), 0)
+
+    def __add__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a + o.a, self.b + o.b)
+
+    __radd__ = __add__
+
+    def __sub__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a - o.a, self.b - o.b)
+
+    def __rsub__(self, o):
+        return Ext.of(o) - self
+
+    def __neg__(self):
+        return Ext(-self.a, -self.b)
+
+    def __mul__(self, o):
+        o = Ext.of(o)
+        return Ext(self.a * o.a + EXT_W * self.b * o.b, self.a * o.b + self.b * o.a)
+
+    __rmul__ = __mul__
+
+    def __mod__(self, _m):
+        return self
+
+    def __pow__(self, e, _m=None):
+        r, base = Ext(1), self
+        while e:
+            if e & 1:
+                r = r * base
+            base = base * base
+            e >>= 1
+        return r
+
+    def inv(self):
+        norm = (self.a * self.a - EXT_W * self.b * self.b) % P
+        ni = pow(norm, P - 2, P)
+        return Ext(self.a * ni, -self.b * ni)
+
+    def __eq__(self, o):
+        o = Ext.of(o)
+        return self.a == o.a and self.b == o.b
+
+    def __hash__(self):
+        return hash((self.a, self.b))
+
+    def pair(self):
+        return (self.a, self.b)
+
+
+def verify_proof(c: Circuit, circuit_digest, constants_sigmas_cap, public_inputs_hash, proof, kind, pow_bits=16):
+    """Accepts or raises.  `proof`: dict(wires_cap, zs_pp_cap, quotient_cap, openings = dict(constants, sigmas, wires,
+    zs, partial_products, quotient, zs_next: lists of (a, b) pairs), fri = the dict pyref.verify_fri_proof consumes).
+    Challenges are re-derived from the transcript; the vanishing identity is evaluated in GF(p^2) by the same constraint
+    code the quotient tests use; the FRI proof is checked by pyref.verify_fri_proof."""
+    n, nch = c.n, c.num_challenges
+    ch = R.Challenger(kind)
+    flat = lambda cap: [int(x) for h in cap for x in h]
+    ch.observe([int(x) for x in circuit_digest])
+    ch.observe([int(x) for x in public_inputs_hash])
+    ch.observe(flat(proof["wires_cap"]))
+    betas = [ch.challenge() for _ in range(nch)]
+    gammas = [ch.challenge() for _ in range(nch)]
+    ch.observe(flat(proof["zs_pp_cap"]))
+    alphas = [ch.challenge() for _ in range(nch)]
+    ch.observe(flat(proof["quotient_cap"]))
+    zeta = ch.ext_challenge()
+    o = proof["openings"]
+    E = lambda vals: [Ext(int(v[0]), int(v[1])) for v in vals]
+    z = Ext(*zeta)
+    van = eval_vanishing_poly(c, z, E(o["constants"]), E(o["wires"]), [int(v) for v in public_inputs_hash], E(o["zs"]),
+                              E(o["zs_next"]), E(o["partial_products"]), E(o["sigmas"]), betas, gammas, alphas)
+    zeta_n = z ** n
+    z_h = zeta_n - 1
+    q = E(o["quotient"])
+    for i in range(nch):
+        t = Ext(0)
+        for k in reversed(range(c.max_degree)):
+            t = t * zeta_n + q[i * c.max_degree + k]
+        assert van[i] == z_h * t, "vanishing polynomial identity (challenge %d)" % i
+    # FRI: every polynomial at zeta, the Zs again at g * zeta
+    widths = [c.num_constants + c.num_routed_wires, c.num_wires, nch * (1 + c.num_partial_products), nch * c.max_degree]
+    g = R.root_of_unity(c.degree_bits)
+    gz = (zeta[0] * g % P, zeta[1] * g % P)
+    batches = [(zeta, [(oi, p) for oi, w in enumerate(widths) for p in range(w)]), (gz, [(2, p) for p in range(nch)])]
+    at_zeta = [tuple(int(x) for x in v) for key in ("constants", "sigmas", "wires", "zs", "partial_products", "quotient")
+               for v in o[key]]
+    openings = [at_zeta, [tuple(int(x) for x in v) for v in o["zs_next"]]]
+    for vals in openings:
+        ch.observe([x for v in vals for x in v])
+    import fri_ref
+    R.verify_fri_proof(batches, openings, [constants_sigmas_cap, proof["wires_cap"], proof["zs_pp_cap"], proof["quotient_cap"]],
+                       proof["fri"], ch, c.degree_bits, fri_ref.arity_schedule(c.degree_bits), pow_bits=pow_bits, kind=kind)
