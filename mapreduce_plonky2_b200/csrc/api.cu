@@ -451,7 +451,7 @@ const char *mp2gpu_host_alloc(void **ptr_out, size_t bytes) {
     if (!ptr_out) return "null ptr_out";
     cudaStream_t st;
     MP2_TRY(ctx_stream(&st));
-    MP2_CUDA(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocDefault));
+    MP2_CUDA(cudaHostAlloc(ptr_out, bytes ? bytes : 1, cudaHostAllocPortable));  // pinned for every device of the process (sharded entry point)
     return "";
   });
 }
