@@ -546,6 +546,13 @@ def measure_map_stage(a, torch, dist, G, world, rank):
                  "includes": T.PROVER_INCLUDES, "gpu_launches": int(launches),
                  "excluded": "witness generation, the grand-product / partial-product values (host inputs of the second "
                              "commitment), proof assembly; gates limited to the staged subset; degrees ASSUMED"}
+    if rank == 0 and out is not None and world == 1 and not a.no_cpu_baseline:
+        # the commitments-only trace on the CPU port, one proof on all host threads (oracle/: the checker, timed as a baseline)
+        threads = host_threads()
+        dt_cpu = cpu_trace_time(1, threads, T.LEAF_PROOF_DEGREES)
+        out["cpu_baseline"] = {"value": 1.0 / dt_cpu, "unit": "proofs/s", "cores": threads, "kind": "port",
+                               "sample": "one leaf-proof commitment trace (%.1f s): the same commitments and FRI-layer trees as "
+                                         "`value`, no quotient / openings / FRI arithmetic" % dt_cpu}
     if rank == 0 and out is not None and whole is not None:
         out["whole_prover"] = whole
         out["note"] = ("value = commitments + FRI-layer trees only (device-resident inputs, upper bound); whole_prover = "
