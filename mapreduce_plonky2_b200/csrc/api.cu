@@ -285,10 +285,24 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
                                cudaMemcpyDeviceToHost, cp));
     }
   }
-  MP2_TRY(merkle_levels(N, cap_height, hash_kind, d_dig.p, d_cap.p, st));
+  // Levels and the digest copy: on big trees the cap subtrees are finished in 4 groups, and a group's digest chunk
+  // (contiguous in plonky2's layout) travels to the host while the next group's levels are built -- otherwise the
+  // 0.5 GB of digests of the wide batch is 10 ms of exposed PCIe time at the end of the call.
+  const size_t groups = (digests_out && ndig && ncap >= 4 && N >= ((size_t)1 << 20)) ? 4 : 1;
+  if (groups == 1) {
+    MP2_TRY(merkle_levels(N, cap_height, hash_kind, d_dig.p, d_cap.p, st));
+    if (digests_out && ndig)
+      MP2_CUDA(cudaMemcpyAsync(digests_out, d_dig.p, ndig * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
+  } else {
+    const size_t nsub = ncap / groups, chunk = ndig / groups * 4;  // u64 per group
+    for (size_t gq = 0; gq < groups; gq++) {
+      MP2_TRY(merkle_levels_subtrees(N, cap_height, hash_kind, d_dig.p, d_cap.p, gq * nsub, nsub, st));
+      MP2_CUDA(cudaEventRecord(ev, st));
+      MP2_CUDA(cudaStreamWaitEvent(cp, ev, 0));
+      MP2_CUDA(cudaMemcpyAsync(digests_out + gq * chunk, d_dig.p + gq * chunk, chunk * sizeof(u64), cudaMemcpyDeviceToHost, cp));
+    }
+  }
   MP2_CUDA(cudaMemcpyAsync(cap_out, d_cap.p, ncap * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
-  if (digests_out && ndig)
-    MP2_CUDA(cudaMemcpyAsync(digests_out, d_dig.p, ndig * 4 * sizeof(u64), cudaMemcpyDeviceToHost, st));
   MP2_CUDA(cudaStreamSynchronize(st));
   MP2_CUDA(cudaStreamSynchronize(cp));
   if (handle_out) {

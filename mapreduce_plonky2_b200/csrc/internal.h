@@ -171,6 +171,8 @@ Status merkle_colmajor_leaves(const u64 *lde, size_t lde_stride, size_t ncols, s
                               u32 hash_kind, size_t leaf_begin, size_t leaf_end, u64 *leaves_out, u64 *digests,
                               u64 *cap, cudaStream_t st);
 Status merkle_levels(size_t nleaves, u32 cap_height, u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st);
+Status merkle_levels_subtrees(size_t nleaves, u32 cap_height, u32 hash_kind, u64 *digests, u64 *cap, size_t sub0,
+                              size_t nsub, cudaStream_t st);
 Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 cap_height,
                        u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st);
 // flat: concatenated leaves, offsets: nleaves+1 prefix sums (device)

@@ -411,11 +411,12 @@ static Status launch_leaf_hash(const u64 *in, size_t stride, u32 ncols, size_t l
 #define MP2_COOP_LEVEL_NODES 2048
 #endif
 
+// Levels of `nsub` consecutive cap subtrees whose digest chunks start at `digests` (and cap entries at `cap`).
 template <u32 KIND>
-static Status build_levels(u64 *digests, u64 *cap, u32 h, u32 cap_height, cudaStream_t st) {
+static Status build_levels(u64 *digests, u64 *cap, u32 h, size_t nsub, cudaStream_t st) {
   const size_t coop_below = (size_t)env_int("MP2_COOP_LEVEL_NODES", MP2_COOP_LEVEL_NODES);
   for (u32 layer = 1; layer <= h; layer++) {
-    size_t nnodes = ((size_t)1 << (h - layer)) << cap_height;
+    size_t nnodes = ((size_t)1 << (h - layer)) * nsub;
     if (nnodes <= coop_below) {
       ProfScope _p("k_merkle_layer_coop", st);
       k_merkle_layer_coop<KIND><<<grid_for(nnodes * 16, 128), 128, 0, st>>>(digests, cap, h, layer, nnodes);
@@ -453,8 +454,21 @@ Status merkle_colmajor_leaves(const u64 *lde, size_t lde_stride, size_t ncols, s
 Status merkle_levels(size_t nleaves, u32 cap_height, u32 hash_kind, u64 *digests, u64 *cap, cudaStream_t st) {
   u32 h;
   MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
-  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
-                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
+  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, (size_t)1 << cap_height, st)
+                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, (size_t)1 << cap_height, st);
+}
+
+// the levels of cap subtrees [sub0, sub0 + nsub) only (their digest chunks are contiguous): lets a caller copy one
+// group's digests out while the next group is still being built
+Status merkle_levels_subtrees(size_t nleaves, u32 cap_height, u32 hash_kind, u64 *digests, u64 *cap, size_t sub0,
+                              size_t nsub, cudaStream_t st) {
+  u32 h;
+  MP2_TRY(check_tree_args(nleaves, cap_height, hash_kind, &h));
+  if (sub0 + nsub > ((size_t)1 << cap_height)) return "subtree range out of bounds";
+  const size_t per = 2 * (((size_t)1 << h) - 1);
+  u64 *d = digests + 4 * sub0 * per, *c = cap + 4 * sub0;
+  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(d, c, h, nsub, st)
+                                         : build_levels<MP2_HASH_POSEIDON>(d, c, h, nsub, st);
 }
 
 Status merkle_colmajor(const u64 *lde, size_t lde_stride, size_t ncols, size_t nleaves, u32 cap_height,
@@ -473,8 +487,8 @@ Status merkle_rowmajor(const u64 *leaves, size_t nleaves, size_t leaf_len, u32 c
     MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON2, false>(leaves, leaf_len, (u32)leaf_len, 0, nleaves, h, nullptr, digests, cap, st)));
   else
     MP2_TRY((launch_leaf_hash<MP2_HASH_POSEIDON, false>(leaves, leaf_len, (u32)leaf_len, 0, nleaves, h, nullptr, digests, cap, st)));
-  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
-                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
+  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, (size_t)1 << cap_height, st)
+                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, (size_t)1 << cap_height, st);
 }
 
 Status merkle_ragged(const u64 *flat, const u64 *offsets, size_t nleaves, u32 cap_height, u32 hash_kind,
@@ -487,8 +501,8 @@ Status merkle_ragged(const u64 *flat, const u64 *offsets, size_t nleaves, u32 ca
   else
     { ProfScope _p("k_leaf_hash_ragged", st); k_leaf_hash_ragged<MP2_HASH_POSEIDON><<<g, MP2_HASH_BLOCK, 0, st>>>(flat, offsets, nleaves, h, digests, cap); }
   MP2_LAUNCH_CHECK();
-  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, cap_height, st)
-                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, cap_height, st);
+  return hash_kind == MP2_HASH_POSEIDON2 ? build_levels<MP2_HASH_POSEIDON2>(digests, cap, h, (size_t)1 << cap_height, st)
+                                         : build_levels<MP2_HASH_POSEIDON>(digests, cap, h, (size_t)1 << cap_height, st);
 }
 
 Status hash_no_pad_batch(const u64 *inputs, size_t count, size_t input_len, u32 hash_kind, u64 *out,

@@ -354,3 +354,18 @@ def test_trim_releases_and_everything_still_works(oracle):
     ref = oracle.commit(cols, 3, 4, 0)
     for pb in (a, b):
         assert np.array_equal(pb.merkle_tree.cap.hashes, ref["cap"]) and np.array_equal(pb.merkle_tree.leaves, ref["leaves"])
+
+
+def test_grouped_levels_with_pipelined_digest_copy(oracle):
+    """N = 2^20 leaves: the host entry point builds the cap subtrees in 4 groups and copies each group's digest chunk out
+    while the next is built (api.cu commit_host); the result must be the plain tree."""
+    import mapreduce_plonky2_b200 as G
+
+    G.init(0)
+    cols = field_elems(0x6E0, (5, 1 << 17))
+    for kind in (G.POSEIDON, G.POSEIDON2):
+        pb = G.PolynomialBatch.from_values(cols, 3, False, 4, hash_kind=kind, fetch_leaves=False)
+        ref = oracle.commit(cols, 3, 4, kind, want_leaves=False)
+        assert np.array_equal(pb.merkle_tree.digests, ref["digests"])
+        assert np.array_equal(pb.merkle_tree.cap.hashes, ref["cap"])
+        assert np.array_equal(pb.polynomials, ref["coeffs"])
