@@ -240,7 +240,11 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
   } ev_guard{ev};
   // The transforms are per column, so big batches go through in column blocks: the upload of block k+1 overlaps
   // the iNTT + LDE of block k, and block k's coefficients travel back while block k+1 is transformed.
-  const size_t nblocks = (ncols >= 16 && ncols * n >= ((size_t)1 << 24)) ? 8 : 1;
+  static const size_t kBlocks = [] {
+    const char *e = getenv("MP2_COMMIT_BLOCKS");
+    return (size_t)(e && *e ? atoi(e) : 16);
+  }();
+  const size_t nblocks = (ncols >= 2 * kBlocks && ncols * n >= ((size_t)1 << 24)) ? kBlocks : 1;
   // Leaf rows go back to the host in blocks while the next block is hashed.  When the LDE is the two-pass kind and
   // a block is one coset (leaf block j = coset bitrev_r(j)), the contiguous pass of that coset is run just before
   // its block is hashed, so the first rows start travelling one pass earlier.
