@@ -105,3 +105,33 @@ def test_unsupported_gate_and_shape_errors(oracle):
     desc.quotient_degree_bits = 4
     with pytest.raises(G.Mp2GpuError, match="exceeds a batch's rate_bits"):
         Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, 3, 2, hash_kind=0)
+
+
+@pytest.mark.parametrize("nch,routed,qbits,degree_bits", [(1, 8, 3, 4), (3, 12, 2, 5), (4, 20, 3, 4), (2, 9, 1, 6)])
+def test_quotient_other_shapes(oracle, nch, routed, qbits, degree_bits):
+    """1 / 3 / 4 challenges, routed-wire counts that are not multiples of the chunk size, quotient degree factors 2 / 4 / 8."""
+    import mapreduce_plonky2_b200 as G
+    from mapreduce_plonky2_b200 import quotient as Q
+    from oracle import quotient as OQ
+
+    G.init(0)
+    rng = random.Random(0xA5 + nch * 7 + routed)
+    inst = PR.synthetic_instance(100 + nch, degree_bits=degree_bits, num_wires=routed + 3, num_routed_wires=routed,
+                                 two_groups=(nch % 2 == 0))
+    c = inst.circuit
+    c.num_challenges, c.quotient_degree_bits = nch, qbits
+    betas, gammas, alphas = ([rng.randrange(P) for _ in range(nch)] for _ in range(3))
+    zs_pp = PR.zs_partial_products(inst, betas, gammas)
+    b_cs, b_w, b_z = _commit3(G, inst, zs_pp, 3, 4, 0)
+    qb = Q.compute_quotient_polys(Q.CircuitDesc.from_circuit(c), b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash,
+                                  3, 4, hash_kind=0)
+    ref = OQ.compute_quotient_polys(c, _coeffs(inst.constants + inst.sigmas), _coeffs(inst.wires), _coeffs(zs_pp), betas, gammas,
+                                    alphas, inst.public_inputs_hash)
+    # bit-exact against the oracle whatever the degrees (for qbits < 3 the pointwise "quotient" is not low-degree -- the
+    # circuit's constraints have degree up to 7 -- but both sides compute the same function on the same coset)
+    assert np.array_equal(qb.polynomials, ref)
+    if qbits == 3:
+        zeta = rng.randrange(2, P)
+        assert PR.check_quotient_identity(inst, zs_pp, [list(map(int, ch)) for ch in qb.polynomials], betas, gammas, alphas, zeta)
+    for b in (b_cs, b_w, b_z, qb):
+        b.free()
