@@ -309,13 +309,21 @@ const char *mp2gpu_transcript_observe(uint64_t *state12, uint64_t *buffer8, uint
 #define MP2GPU_GATE_MUL_EXT 6u       /* MulExtensionGate{num_ops}: m0 | m1 | output at 6i; output - c0 m0 m1 */
 #define MP2GPU_GATE_BASE_SUM 7u      /* BaseSumGate<B = param>{num_limbs = num_ops}: wire 0 = sum, limbs from wire 1;
                                         sum_i limb_i B^i - sum, then prod_{k < B} (limb_i - k) per limb */
+#define MP2GPU_GATE_REDUCING 8u      /* ReducingGate{num_coeffs = num_ops}, D = 2: output 0..2 | alpha 2..4 | old_acc 4..6 | base
+                                        coefficients from 6 | accumulators after them (the last one is the output wires);
+                                        acc_{i-1} alpha + coeff_i - acc_i, 2 constraints each */
+#define MP2GPU_GATE_REDUCING_EXT 9u  /* ReducingExtensionGate{num_coeffs = num_ops}: the same with extension coefficients */
+#define MP2GPU_GATE_RANDOM_ACCESS 10u /* RandomAccessGate{bits = param & 0xFF, num_copies = num_ops, num_extra_constants =
+                                        param >> 8}: per copy access_index | claimed_element | 2^bits list items, then the
+                                        extra constants, then (unrouted) the index bits; per copy b(b-1) per bit, index
+                                        reconstruction, folded list - claimed_element; then constant_i - wire_i */
 typedef struct mp2gpu_gate {
   uint32_t kind;            /* MP2GPU_GATE_* */
   uint32_t num_ops;         /* see the kinds above */
   uint32_t selector_index;  /* SelectorsInfo::selector_indices[gate] */
   uint32_t group_begin;     /* SelectorsInfo::groups[selector_index] = group_begin..group_end (gate indices) */
   uint32_t group_end;
-  uint32_t param;           /* BaseSumGate: the base B; 0 otherwise */
+  uint32_t param;           /* BaseSumGate: the base B; RandomAccessGate: bits | num_extra_constants << 8; 0 otherwise */
 } mp2gpu_gate;
 typedef struct mp2gpu_circuit {   /* the CommonCircuitData fields the vanishing polynomial depends on */
   uint32_t degree_bits;

@@ -16,7 +16,8 @@
 //     `from_coeffs` (the prover's quotient_polys_commitment).
 // Gate set: the staged subset of mp2-common/src/serialization/circuit_data_serialization.rs:234-266 that
 // oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate, PoseidonGate,
-// ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>; anything else is an error.
+// ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate;
+// anything else is an error.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -134,6 +135,44 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
         cons(2 * op, gl_sub(w[out_at], r0));
         cons(2 * op + 1, gl_sub(w[out_at + 1], r1));
       }
+    } else if (gate.kind == MP2GPU_GATE_REDUCING || gate.kind == MP2GPU_GATE_REDUCING_EXT) {
+      const bool ext = gate.kind == MP2GPU_GATE_REDUCING_EXT;
+      const u32 nco = gate.num_ops, start_accs = 6 + (ext ? 2 * nco : nco);
+      const u64 al0 = wi[2], al1 = wi[3];
+      u64 a0 = wi[4], a1 = wi[5];
+      for (u32 k = 0; k < nco; k++) {
+        const u64 c0 = ext ? wi[6 + 2 * k] : wi[6 + k], c1 = ext ? wi[7 + 2 * k] : 0;
+        const u32 at = k == nco - 1 ? 0 : start_accs + 2 * k;
+        const u64 n0 = wi[at], n1 = wi[at + 1];
+        // acc * alpha + coeff - next, in GF(p^2)
+        const u64 t0 = gl_add(gl_mul_add(gl_mul(7, a1), al1, gl_mul(a0, al0)), c0);
+        const u64 t1 = gl_add(gl_mul_add(a0, al1, gl_mul(a1, al0)), c1);
+        cons(2 * k, gl_sub(t0, n0));
+        cons(2 * k + 1, gl_sub(t1, n1));
+        a0 = n0;
+        a1 = n1;
+      }
+    } else if (gate.kind == MP2GPU_GATE_RANDOM_ACCESS) {
+      const u32 bits = gate.param & 0xFF, copies = gate.num_ops, nx = gate.param >> 8, vec = 1u << bits;
+      const u32 routed = (2 + vec) * copies + nx;
+      u32 ci = 0;
+      for (u32 cp = 0; cp < copies; cp++) {
+        const u64 *w = wi + (2 + vec) * cp, *bs = wi + routed + cp * bits;
+        u64 rec = 0;
+        for (u32 k = 0; k < bits; k++) cons(ci++, gl_mul(bs[k], gl_sub(bs[k], 1)));
+        for (u32 k = bits; k-- > 0;) rec = gl_add(gl_add(rec, rec), bs[k]);
+        cons(ci++, gl_sub(rec, w[0]));
+        // fold the list pairwise by the bits; vec <= 64 elements live in registers / local memory
+        u64 items[64];
+        for (u32 k = 0; k < vec; k++) items[k] = w[2 + k];
+        u32 len = vec;
+        for (u32 b = 0; b < bits; b++) {
+          len >>= 1;
+          for (u32 k = 0; k < len; k++) items[k] = gl_mul_add(bs[b], gl_sub(items[2 * k + 1], items[2 * k]), items[2 * k]);
+        }
+        cons(ci++, gl_sub(items[0], w[1]));
+      }
+      for (u32 k = 0; k < nx; k++) cons(ci++, gl_sub(gc[k], wi[(2 + vec) * copies + k]));
     } else if (gate.kind == MP2GPU_GATE_BASE_SUM) {
       const u64 base = gate.param;
       u64 acc = 0;
@@ -279,12 +318,28 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
         if (s.param < 2 || s.param > 16) return "quotient_polys: BaseSumGate base must be 2..16";
         if (1 + s.num_ops > ci->num_wires) return "quotient_polys: BaseSumGate limbs exceed the wires";
         break;
+      case MP2GPU_GATE_REDUCING:
+      case MP2GPU_GATE_REDUCING_EXT: {
+        const bool ext = s.kind == MP2GPU_GATE_REDUCING_EXT;
+        nc = 2 * s.num_ops;
+        if (s.num_ops == 0) return "quotient_polys: ReducingGate without coefficients";
+        if (6 + (ext ? 2 : 1) * s.num_ops + 2 * (s.num_ops - 1) > ci->num_wires) return "quotient_polys: ReducingGate exceeds the wires";
+        break;
+      }
+      case MP2GPU_GATE_RANDOM_ACCESS: {
+        const u32 bits = s.param & 0xFF, nx = s.param >> 8;
+        if (bits == 0 || bits > 6) return "quotient_polys: RandomAccessGate bits must be 1..6";
+        nc = s.num_ops * (bits + 2) + nx;
+        nk = nx;
+        if ((2 + (1u << bits)) * s.num_ops + nx + s.num_ops * bits > ci->num_wires) return "quotient_polys: RandomAccessGate exceeds the wires";
+        break;
+      }
       case MP2GPU_GATE_POSEIDON:
         nc = 123;
         if (ci->num_wires < 135) return "quotient_polys: PoseidonGate needs 135 wires";
         break;
       default:
-        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum)";
+        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum, reducing, reducing_extension, random_access)";
     }
     ngc = std::max(ngc, nc);
     max_gate_constants = std::max(max_gate_constants, nk);

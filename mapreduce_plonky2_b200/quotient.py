@@ -6,7 +6,8 @@ caller asks for) comes back.  ctypes + numpy only.
 The descriptor mirrors the ``CommonCircuitData`` fields the vanishing polynomial depends on: ``gates`` in circuit
 order, ``SelectorsInfo { selector_indices, groups }``, ``num_constants`` (selectors + gate constants), the wire counts
 and ``quotient_degree_factor``.  Gate kinds outside the staged subset (ArithmeticGate, ConstantGate, PublicInputGate,
-NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B> of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
+NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate,
+ReducingExtensionGate, RandomAccessGate of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
 """
 from __future__ import annotations
 
@@ -21,7 +22,7 @@ from ._lib import Mp2GpuError
 from .plonky2 import POSEIDON2, MerkleCap, MerkleTree, PolynomialBatch, _arr, _col_ptrs, _ptr
 
 GATE_KINDS = {"noop": 0, "arithmetic": 1, "constant": 2, "public_input": 3, "poseidon": 4, "arithmetic_extension": 5,
-              "mul_extension": 6, "base_sum": 7}
+              "mul_extension": 6, "base_sum": 7, "reducing": 8, "reducing_extension": 9, "random_access": 10}
 
 
 class _CGate(C.Structure):
@@ -39,7 +40,7 @@ class _CCircuit(C.Structure):
 class GateDesc:
     kind: str           # one of GATE_KINDS
     num_ops: int = 0    # Arithmetic(Extension)Gate / MulExtensionGate::num_ops, ConstantGate::num_consts, BaseSumGate::num_limbs
-    param: int = 0      # BaseSumGate<B>: B
+    param: int = 0      # BaseSumGate<B>: B; RandomAccessGate: bits | num_extra_constants << 8
 
 
 @dataclass

@@ -10,7 +10,8 @@ The prover evaluates, at every point x_i = g * w_{8n}^i of the coset LDE the thr
 then `coset_ifft` turns each q_c into coefficients and cuts it into `quotient_degree_factor` chunks of n, which are
 committed with `from_coeffs`.  Gate set restated here (the staged subset of
 mp2-common/src/serialization/circuit_data_serialization.rs:234-266): ArithmeticGate, ConstantGate, PublicInputGate,
-NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B> behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
+NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate behind
+plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
 
 Pinned by definition, not by the Rust prover (absent): tests/plonk_ref.py restates the VERIFIER's
 `eval_vanishing_poly` + final identity, and the quotients computed here must pass it at random points
@@ -100,6 +101,33 @@ def _gate_constraints(desc, local_constants, local_wires, pi_hash):
                 w = local_wires[6 * i:6 * i + 6]
                 cons.append((w[4] - gc[0] * (w[0] * w[2] + 7 * w[1] * w[3])) % P)
                 cons.append((w[5] - gc[0] * (w[0] * w[3] + w[1] * w[2])) % P)
+        elif gate.kind in ("reducing", "reducing_extension"):   # gates/reducing{,_extension}.rs: acc*alpha + coeff - next acc
+            ext = gate.kind == "reducing_extension"
+            w, nco = local_wires, gate.num_ops
+            start_accs = 6 + (2 * nco if ext else nco)
+            a0, a1 = w[4], w[5]
+            cons = []
+            for i in range(nco):
+                c0, c1 = (w[6 + 2 * i], w[7 + 2 * i]) if ext else (w[6 + i], 0)
+                n0, n1 = (w[0], w[1]) if i == nco - 1 else (w[start_accs + 2 * i], w[start_accs + 2 * i + 1])
+                cons.append((a0 * w[2] + 7 * a1 * w[3] + c0 - n0) % P)
+                cons.append((a0 * w[3] + a1 * w[2] + c1 - n1) % P)
+                a0, a1 = n0, n1
+        elif gate.kind == "random_access":          # gates/random_access.rs: bits = param & 0xFF, extra constants = param >> 8
+            bits, copies, nx = gate.param & 0xFF, gate.num_ops, gate.param >> 8
+            vec = 1 << bits
+            routed = (2 + vec) * copies + nx
+            w, cons = local_wires, []
+            for cp in range(copies):
+                b0 = (2 + vec) * cp
+                bs = [w[routed + cp * bits + i] for i in range(bits)]
+                cons += [b * (b - 1) % P for b in bs]
+                cons.append((sum(b << i for i, b in enumerate(bs)) - w[b0]) % P)
+                items = list(w[b0 + 2:b0 + 2 + vec])
+                for b in bs:
+                    items = [(items[2 * k] + b * (items[2 * k + 1] - items[2 * k])) % P for k in range(len(items) // 2)]
+                cons.append((items[0] - w[b0 + 1]) % P)
+            cons += [(gc[i] - w[(2 + vec) * copies + i]) % P for i in range(nx)]
         elif gate.kind == "base_sum":               # gates/base_sum.rs BaseSumGate<B>{num_limbs}: B = gate.param
             limbs = local_wires[1:1 + gate.num_ops]
             total = sum(l * pow(gate.param, i, P) for i, l in enumerate(limbs)) % P

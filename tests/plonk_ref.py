@@ -149,6 +149,58 @@ def base_sum_constraints(w, num_limbs, base):
     return out
 
 
+# ---- ReducingGate / ReducingExtensionGate / RandomAccessGate (plonky2 gates/reducing.rs, reducing_extension.rs,
+# random_access.rs), D = 2 -----------------------------------------------------------------------------------------------
+#   ReducingGate{num_coeffs}: output 0..2 | alpha 2..4 | old_acc 4..6 | base-field coeffs 6..6+n | accs from 6+n (2 wires each;
+#     the LAST acc is the output wires);  constraints (2 each): acc_{i-1} * alpha + coeff_i - acc_i,  acc_{-1} = old_acc
+#   ReducingExtensionGate{num_coeffs}: the same with extension coefficients at 6 + 2i, accs from 6 + 2n
+#   RandomAccessGate{bits, num_copies, num_extra_constants}, vec_size = 2^bits: per copy c at (2 + vec_size) c: access_index,
+#     claimed_element, list items; extra constants after the copies (all routed); then the index bits, `bits` per copy.
+#     Constraints per copy: b (b - 1) per bit; sum_i b_i 2^i - access_index; the list folded pairwise by the bits
+#     (x + b (y - x)) down to one element - claimed_element.  Then constant_i - extra_constant_wire_i.
+def _ext_add(a, b):
+    return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+
+
+def reducing_constraints(w, n, extension):
+    alpha, acc = w[2:4], w[4:6]
+    start_accs = 6 + (2 * n if extension else n)
+    out = []
+    for i in range(n):
+        coeff = w[6 + 2 * i:8 + 2 * i] if extension else (w[6 + i], 0)
+        nxt = w[0:2] if i == n - 1 else w[start_accs + 2 * i:start_accs + 2 * i + 2]
+        t = _ext_add(ext_mul(acc, alpha), coeff)
+        out += [(t[0] - nxt[0]) % P, (t[1] - nxt[1]) % P]
+        acc = nxt
+    return out
+
+
+def random_access_layout(bits, copies, extra):
+    vec = 1 << bits
+    routed = (2 + vec) * copies + extra
+    return vec, routed
+
+
+def random_access_constraints(w, bits, copies, extra, gate_consts):
+    vec, routed = random_access_layout(bits, copies, extra)
+    out = []
+    for c in range(copies):
+        base = (2 + vec) * c
+        idx, claimed = w[base], w[base + 1]
+        items = list(w[base + 2:base + 2 + vec])
+        bs = [w[routed + c * bits + i] for i in range(bits)]
+        out += [b * (b - 1) % P for b in bs]
+        rec = 0
+        for b in reversed(bs):
+            rec = (rec * 2 + b) % P
+        out.append((rec - idx) % P)
+        for b in bs:
+            items = [(items[2 * k] + b * (items[2 * k + 1] - items[2 * k])) % P for k in range(len(items) // 2)]
+        out.append((items[0] - claimed) % P)
+    out += [(gate_consts[i] - w[(2 + vec) * copies + i]) % P for i in range(extra)]
+    return out
+
+
 @dataclass
 class Gate:
     kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon" | "arithmetic_extension" |
@@ -161,12 +213,15 @@ class Gate:
     def num_constraints(self) -> int:
         return {"arithmetic": self.num_ops, "constant": self.num_ops, "public_input": 4, "noop": 0,
                 "poseidon": POSEIDON_GATE_CONSTRAINTS, "arithmetic_extension": 2 * self.num_ops,
-                "mul_extension": 2 * self.num_ops, "base_sum": 1 + self.num_ops}[self.kind]
+                "mul_extension": 2 * self.num_ops, "base_sum": 1 + self.num_ops, "reducing": 2 * self.num_ops,
+                "reducing_extension": 2 * self.num_ops,
+                "random_access": self.num_ops * ((self.param & 0xFF) + 2) + (self.param >> 8)}[self.kind]
 
     @property
     def num_constants(self) -> int:
         return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0, "poseidon": 0,
-                "arithmetic_extension": 2, "mul_extension": 1, "base_sum": 0}[self.kind]
+                "arithmetic_extension": 2, "mul_extension": 1, "base_sum": 0, "reducing": 0, "reducing_extension": 0,
+                "random_access": self.param >> 8}[self.kind]
 
 
 @dataclass
@@ -259,6 +314,15 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
         selector_indices += [len(groups)] * 4
         groups.append((base, base + 4))
         extra = list(range(base, base + 4))
+        if num_wires >= 24 and num_routed_wires >= 14:
+            # a fourth group (filtered degree (2 + 1) + 3 = 6): the reducing gates and a 2-bit, 2-copy random access
+            b2 = len(gates)
+            nred = min((num_routed_wires - 6), (num_wires - 4) // 3, 5)
+            nrede = min((num_routed_wires - 6) // 2, (num_wires - 4) // 4, 3)
+            gates += [Gate("reducing", nred), Gate("reducing_extension", nrede), Gate("random_access", 2, 2 | (2 << 8))]
+            selector_indices += [len(groups)] * 3
+            groups.append((b2, b2 + 3))
+            extra += list(range(b2, b2 + 3))
     c = Circuit(degree_bits, num_wires, num_routed_wires, gates, selector_indices, groups)
     pi_hash = [rng.randrange(P) for _ in range(4)]
     row_gate = [3] + [rng.choice([0, 0, 0, 1, 2] + ([4, 4] if with_poseidon else []) + extra) for _ in range(n - 1)]     # row 0: the public-input gate
@@ -319,6 +383,30 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
                 for t in range(2):
                     wires[6 * i + 4 + t][row] = c0 * pr[t] % P
                     outputs.append((6 * i + 4 + t, row))
+        elif gates[g].kind in ("reducing", "reducing_extension"):
+            nco, ext = gates[g].num_ops, gates[g].kind == "reducing_extension"
+            start_accs = 6 + (2 * nco if ext else nco)
+            acc = [wires[4][row], wires[5][row]]
+            alpha = [wires[2][row], wires[3][row]]
+            for i in range(nco):
+                coeff = [wires[6 + 2 * i][row], wires[7 + 2 * i][row]] if ext else [wires[6 + i][row], 0]
+                acc = list(_ext_add(ext_mul(acc, alpha), coeff))
+                at = 0 if i == nco - 1 else start_accs + 2 * i
+                wires[at][row], wires[at + 1][row] = acc
+            outputs += [(0, row), (1, row)]
+        elif gates[g].kind == "random_access":
+            bits, copies, nx = gates[g].param & 0xFF, gates[g].num_ops, gates[g].param >> 8
+            vec, routed = random_access_layout(bits, copies, nx)
+            for cpy in range(copies):
+                idx = rng.randrange(vec)
+                b0 = (2 + vec) * cpy
+                wires[b0][row] = idx
+                wires[b0 + 1][row] = wires[b0 + 2 + idx][row]
+                for i in range(bits):
+                    wires[routed + cpy * bits + i][row] = (idx >> i) & 1
+                outputs.append((b0 + 1, row))
+            for i in range(nx):
+                wires[(2 + vec) * copies + i][row] = consts[c.num_selectors + i][row]
         elif gates[g].kind == "base_sum":
             base, nl = gates[g].param, gates[g].num_ops
             limbs = [rng.randrange(base) for _ in range(nl)]
@@ -417,6 +505,10 @@ def gate_constraints(c: Circuit, local_constants: List[int], local_wires: List[i
             cons = mul_extension_constraints(local_wires, gate.num_ops, gate_consts[0])
         elif gate.kind == "base_sum":
             cons = base_sum_constraints(local_wires, gate.num_ops, gate.param)
+        elif gate.kind in ("reducing", "reducing_extension"):
+            cons = reducing_constraints(local_wires, gate.num_ops, gate.kind == "reducing_extension")
+        elif gate.kind == "random_access":
+            cons = random_access_constraints(local_wires, gate.param & 0xFF, gate.num_ops, gate.param >> 8, gate_consts)
         else:
             cons = []
         for i, v in enumerate(cons):
