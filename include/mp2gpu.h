@@ -317,6 +317,10 @@ const char *mp2gpu_transcript_observe(uint64_t *state12, uint64_t *buffer8, uint
                                         param >> 8}: per copy access_index | claimed_element | 2^bits list items, then the
                                         extra constants, then (unrouted) the index bits; per copy b(b-1) per bit, index
                                         reconstruction, folded list - claimed_element; then constant_i - wire_i */
+#define MP2GPU_GATE_EXPONENTIATION 11u /* ExponentiationGate{num_power_bits = num_ops}: base 0 | bits (LE) from 1 | output 1+n |
+                                         intermediate values from 2+n; (i ? iv_{i-1}^2 : 1)(b base + 1 - b) - iv_i with
+                                         b = bit_{n-1-i}; then output - iv_{n-1} */
+#define MP2GPU_GATE_POSEIDON_MDS 12u   /* PoseidonMdsGate: 12 extension inputs at 2i, outputs at 24 + 2i; output - MDS(input) */
 typedef struct mp2gpu_gate {
   uint32_t kind;            /* MP2GPU_GATE_* */
   uint32_t num_ops;         /* see the kinds above */

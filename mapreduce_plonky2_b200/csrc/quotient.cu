@@ -16,8 +16,8 @@
 //     `from_coeffs` (the prover's quotient_polys_commitment).
 // Gate set: the staged subset of mp2-common/src/serialization/circuit_data_serialization.rs:234-266 that
 // oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate, PoseidonGate,
-// ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate;
-// anything else is an error.
+// ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate,
+// ExponentiationGate, PoseidonMdsGate; anything else is an error.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -152,6 +152,30 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
         a0 = n0;
         a1 = n1;
       }
+    } else if (gate.kind == MP2GPU_GATE_EXPONENTIATION) {
+      const u32 nb = gate.num_ops;
+      const u64 base = wi[0];
+      const u64 *bits = wi + 1, *iv = wi + 2 + nb;
+      for (u32 k = 0; k < nb; k++) {
+        const u64 prev = k == 0 ? 1 : gl_sqr(iv[k - 1]);
+        const u64 b = bits[nb - 1 - k];
+        // b * base + (1 - b)
+        const u64 sel = gl_add(gl_mul(b, base), gl_sub(1, b));
+        cons(k, gl_sub(gl_mul(prev, sel), iv[k]));
+      }
+      cons(nb, gl_sub(wi[1 + nb], iv[nb - 1]));
+    } else if (gate.kind == MP2GPU_GATE_POSEIDON_MDS) {
+      constexpr u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+      for (u32 r = 0; r < 12; r++)
+        for (u32 comp = 0; comp < 2; comp++) {
+          u64 acc = r == 0 ? gl_mul(8, wi[comp]) : 0;
+          for (u32 k = 0; k < 12; k++) {
+            u32 src = k + r;
+            src = src >= 12 ? src - 12 : src;
+            acc = gl_mul_add(wi[2 * src + comp], (u64)CIRC[k], acc);
+          }
+          cons(2 * r + comp, gl_sub(wi[24 + 2 * r + comp], acc));
+        }
     } else if (gate.kind == MP2GPU_GATE_RANDOM_ACCESS) {
       const u32 bits = gate.param & 0xFF, copies = gate.num_ops, nx = gate.param >> 8, vec = 1u << bits;
       const u32 routed = (2 + vec) * copies + nx;
@@ -334,12 +358,21 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
         if ((2 + (1u << bits)) * s.num_ops + nx + s.num_ops * bits > ci->num_wires) return "quotient_polys: RandomAccessGate exceeds the wires";
         break;
       }
+      case MP2GPU_GATE_EXPONENTIATION:
+        nc = s.num_ops + 1;
+        if (s.num_ops == 0) return "quotient_polys: ExponentiationGate without power bits";
+        if (2 + 2 * s.num_ops > ci->num_wires) return "quotient_polys: ExponentiationGate exceeds the wires";
+        break;
+      case MP2GPU_GATE_POSEIDON_MDS:
+        nc = 24;
+        if (ci->num_wires < 48) return "quotient_polys: PoseidonMdsGate needs 48 wires";
+        break;
       case MP2GPU_GATE_POSEIDON:
         nc = 123;
         if (ci->num_wires < 135) return "quotient_polys: PoseidonGate needs 135 wires";
         break;
       default:
-        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum, reducing, reducing_extension, random_access)";
+        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum, reducing, reducing_extension, random_access, exponentiation, poseidon_mds)";
     }
     ngc = std::max(ngc, nc);
     max_gate_constants = std::max(max_gate_constants, nk);

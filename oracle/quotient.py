@@ -10,8 +10,8 @@ The prover evaluates, at every point x_i = g * w_{8n}^i of the coset LDE the thr
 then `coset_ifft` turns each q_c into coefficients and cuts it into `quotient_degree_factor` chunks of n, which are
 committed with `from_coeffs`.  Gate set restated here (the staged subset of
 mp2-common/src/serialization/circuit_data_serialization.rs:234-266): ArithmeticGate, ConstantGate, PublicInputGate,
-NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate behind
-plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
+NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate,
+ExponentiationGate, PoseidonMdsGate behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
 
 Pinned by definition, not by the Rust prover (absent): tests/plonk_ref.py restates the VERIFIER's
 `eval_vanishing_poly` + final identity, and the quotients computed here must pass it at random points
@@ -113,6 +113,20 @@ def _gate_constraints(desc, local_constants, local_wires, pi_hash):
                 cons.append((a0 * w[2] + 7 * a1 * w[3] + c0 - n0) % P)
                 cons.append((a0 * w[3] + a1 * w[2] + c1 - n1) % P)
                 a0, a1 = n0, n1
+        elif gate.kind == "exponentiation":         # gates/exponentiation.rs ExponentiationGate{num_power_bits = num_ops}
+            w, nb = local_wires, gate.num_ops
+            cons = []
+            for i in range(nb):
+                prev = 1 if i == 0 else w[2 + nb + i - 1] ** 2 % P
+                b = w[1 + (nb - 1 - i)]
+                cons.append((prev * (b * w[0] + 1 - b) - w[2 + nb + i]) % P)
+            cons.append((w[1 + nb] - w[2 + 2 * nb - 1]) % P)
+        elif gate.kind == "poseidon_mds":           # gates/poseidon_mds.rs: output - MDS(input), 12 extension elements
+            w, cons = local_wires, []
+            for r in range(12):
+                for comp in range(2):
+                    acc = sum(w[2 * ((i + r) % 12) + comp] * _POS_CIRC[i] for i in range(12)) + (8 * w[comp] if r == 0 else 0)
+                    cons.append((w[24 + 2 * r + comp] - acc) % P)
         elif gate.kind == "random_access":          # gates/random_access.rs: bits = param & 0xFF, extra constants = param >> 8
             bits, copies, nx = gate.param & 0xFF, gate.num_ops, gate.param >> 8
             vec = 1 << bits

@@ -201,6 +201,32 @@ def random_access_constraints(w, bits, copies, extra, gate_consts):
     return out
 
 
+# ---- ExponentiationGate{num_power_bits} and PoseidonMdsGate (plonky2 gates/exponentiation.rs, poseidon_mds.rs) ----------
+#   Exponentiation: base 0 | power bits 1..1+n (little endian) | output 1+n | intermediate values from 2+n;
+#     for i < n: (i == 0 ? 1 : iv_{i-1}^2) * (bit_{n-1-i} * base + 1 - bit_{n-1-i}) - iv_i;  then output - iv_{n-1}
+#   PoseidonMds: 12 extension inputs at 2i, 12 extension outputs at 24 + 2i; output - MDS(input) component-wise
+def exponentiation_constraints(w, n):
+    base, out_w = w[0], w[1 + n]
+    bits, iv = w[1:1 + n], w[2 + n:2 + 2 * n]
+    cons = []
+    for i in range(n):
+        prev = 1 if i == 0 else iv[i - 1] * iv[i - 1] % P
+        b = bits[n - 1 - i]
+        cons.append((prev * ((b * base + 1 - b) % P) - iv[i]) % P)
+    cons.append((out_w - iv[n - 1]) % P)
+    return cons
+
+
+def poseidon_mds_constraints(w):
+    cons = []
+    for comp in range(2):
+        col = [w[2 * i + comp] for i in range(12)]
+        res = _pos_mds(col)
+        cons_comp = [(w[24 + 2 * r + comp] - res[r]) % P for r in range(12)]
+        cons.append(cons_comp)
+    return [cons[comp][r] for r in range(12) for comp in range(2)]
+
+
 @dataclass
 class Gate:
     kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon" | "arithmetic_extension" |
@@ -215,13 +241,14 @@ class Gate:
                 "poseidon": POSEIDON_GATE_CONSTRAINTS, "arithmetic_extension": 2 * self.num_ops,
                 "mul_extension": 2 * self.num_ops, "base_sum": 1 + self.num_ops, "reducing": 2 * self.num_ops,
                 "reducing_extension": 2 * self.num_ops,
-                "random_access": self.num_ops * ((self.param & 0xFF) + 2) + (self.param >> 8)}[self.kind]
+                "random_access": self.num_ops * ((self.param & 0xFF) + 2) + (self.param >> 8),
+                "exponentiation": self.num_ops + 1, "poseidon_mds": 24}[self.kind]
 
     @property
     def num_constants(self) -> int:
         return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0, "poseidon": 0,
                 "arithmetic_extension": 2, "mul_extension": 1, "base_sum": 0, "reducing": 0, "reducing_extension": 0,
-                "random_access": self.param >> 8}[self.kind]
+                "random_access": self.param >> 8, "exponentiation": 0, "poseidon_mds": 0}[self.kind]
 
 
 @dataclass
@@ -323,6 +350,13 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
             selector_indices += [len(groups)] * 3
             groups.append((b2, b2 + 3))
             extra += list(range(b2, b2 + 3))
+            if num_wires >= 48 and num_routed_wires >= 24:
+                # a fifth group: ExponentiationGate (degree 4) and PoseidonMdsGate (degree 1): (1 + 1) + 4 = 6
+                b3 = len(gates)
+                gates += [Gate("exponentiation", min(num_routed_wires - 2, (num_wires - 2) // 2, 7)), Gate("poseidon_mds")]
+                selector_indices += [len(groups)] * 2
+                groups.append((b3, b3 + 2))
+                extra += [b3, b3 + 1]
     c = Circuit(degree_bits, num_wires, num_routed_wires, gates, selector_indices, groups)
     pi_hash = [rng.randrange(P) for _ in range(4)]
     row_gate = [3] + [rng.choice([0, 0, 0, 1, 2] + ([4, 4] if with_poseidon else []) + extra) for _ in range(n - 1)]     # row 0: the public-input gate
@@ -394,6 +428,23 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
                 at = 0 if i == nco - 1 else start_accs + 2 * i
                 wires[at][row], wires[at + 1][row] = acc
             outputs += [(0, row), (1, row)]
+        elif gates[g].kind == "exponentiation":
+            nb = gates[g].num_ops
+            base_v = wires[0][row]
+            bits = [rng.randrange(2) for _ in range(nb)]
+            acc = 1
+            for i in range(nb):
+                wires[1 + i][row] = bits[i]
+            for i in range(nb):
+                acc = (1 if i == 0 else acc * acc % P) * (base_v if bits[nb - 1 - i] else 1) % P
+                wires[2 + nb + i][row] = acc
+            wires[1 + nb][row] = acc
+            outputs.append((1 + nb, row))
+        elif gates[g].kind == "poseidon_mds":
+            for comp in range(2):
+                res = _pos_mds([wires[2 * i + comp][row] for i in range(12)])
+                for r in range(12):
+                    wires[24 + 2 * r + comp][row] = res[r]
         elif gates[g].kind == "random_access":
             bits, copies, nx = gates[g].param & 0xFF, gates[g].num_ops, gates[g].param >> 8
             vec, routed = random_access_layout(bits, copies, nx)
@@ -509,6 +560,10 @@ def gate_constraints(c: Circuit, local_constants: List[int], local_wires: List[i
             cons = reducing_constraints(local_wires, gate.num_ops, gate.kind == "reducing_extension")
         elif gate.kind == "random_access":
             cons = random_access_constraints(local_wires, gate.param & 0xFF, gate.num_ops, gate.param >> 8, gate_consts)
+        elif gate.kind == "exponentiation":
+            cons = exponentiation_constraints(local_wires, gate.num_ops)
+        elif gate.kind == "poseidon_mds":
+            cons = poseidon_mds_constraints(local_wires)
         else:
             cons = []
         for i, v in enumerate(cons):

@@ -96,7 +96,7 @@ def test_unsupported_gate_and_shape_errors(oracle):
     zs_pp = PR.zs_partial_products(inst, betas, gammas)
     b_cs, b_w, b_z = _commit3(G, inst, zs_pp, 3, 2, 0)
     desc = Q.CircuitDesc.from_circuit(c)
-    desc.gates[2] = Q.GateDesc("exponentiation")
+    desc.gates[2] = Q.GateDesc("coset_interpolation")
     with pytest.raises(G.Mp2GpuError, match="outside the supported subset"):
         Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, 3, 2, hash_kind=0)
     desc = Q.CircuitDesc.from_circuit(c)
