@@ -620,12 +620,12 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         cap_h = torch.empty((ncap, 4), dtype=torch.int64, pin_memory=True)
         cols_d = torch.empty((c_loc, n), dtype=torch.int64, device="cuda")
 
-        up_stream = torch.cuda.Stream()
-        host_out = S.HostOutputs(coeffs_h, leaves_h, dig_h, cap_h, torch.cuda.Stream(), cols_host=cols_h, up_stream=up_stream)
+        host_out = S.HostOutputs(coeffs_h, leaves_h, dig_h, cap_h, torch.cuda.Stream())
 
         def call():
-            # the sharded commitment with its input uploaded block by block under the iNTT and its outputs streamed back
-            # to the pinned buffers under the compute (coefficients under the LDE, leaf blocks under the hashing)
+            # upload on the compute stream, then the sharded commitment with its outputs streamed back to the
+            # pinned buffers under the compute (coefficients under the LDE, leaf blocks under the hashing)
+            cols_d.copy_(cols_h, non_blocking=True)
             S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
                              exchange=a.exchange, host_out=host_out)
             torch.cuda.synchronize()
@@ -640,11 +640,12 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-        api = "sharded.commit_sharded(host_out=...) with pinned host shards (per rank: H2D in blocks under the iNTT, D2H under the LDE / hashing)"
+        api = "sharded.commit_sharded(host_out=...) with pinned host shards (H2D + D2H per rank, D2H overlapped with hashing)"
         # the same call with the leaf rows left in HBM (every later reader of the rows runs on the device)
-        host_res = S.HostOutputs(coeffs_h, None, dig_h, cap_h, host_out.copy_stream, cols_host=cols_h, up_stream=up_stream)
+        host_res = S.HostOutputs(coeffs_h, None, dig_h, cap_h, host_out.copy_stream)
 
         def call_resident():
+            cols_d.copy_(cols_h, non_blocking=True)
             S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
                              exchange=a.exchange, host_out=host_res)
             torch.cuda.synchronize()

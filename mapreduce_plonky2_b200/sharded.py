@@ -97,11 +97,6 @@ class HostOutputs:
     cap: Optional[torch.Tensor]
     copy_stream: "torch.cuda.Stream"
     chunks: int = 8
-    # optional pipelined input: pinned host columns (c/G, n) uploaded block by block on ``up_stream`` into the
-    # ``cols_local`` staging tensor, each block's iNTT starting as soon as it has landed
-    cols_host: Optional[torch.Tensor] = None
-    up_stream: Optional["torch.cuda.Stream"] = None
-    up_blocks: int = 4
 
 
 class PeerExchange:
@@ -185,13 +180,10 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
     tm.mark("start")
     # 1. per-column work on the local column shard
     coeffs = buf("coeffs", (c_loc, n))
-
-    def first_stage(src, dst):
-        if from_coeffs:
-            engine.canonical_copy(src, dst)
-        else:
-            engine.intt(src, dst)
-
+    if from_coeffs:
+        engine.canonical_copy(cols_local, coeffs)
+    else:
+        engine.intt(cols_local, coeffs)
     def to_host(dst, src):
         # dst <- src on the copy stream, ordered after everything queued on the compute stream so far
         if host_out is None or dst is None:
@@ -202,23 +194,7 @@ def commit_sharded(cols_local: torch.Tensor, ncols_total: int, rate_bits: int, c
         with torch.cuda.stream(host_out.copy_stream):
             dst.copy_(src, non_blocking=True)
 
-    if host_out is not None and host_out.cols_host is not None and host_out.up_stream is not None:
-        # upload of block k+1 under the iNTT of block k; coefficients of block k go back under block k+1
-        up = host_out.up_stream
-        up.wait_stream(torch.cuda.current_stream())   # the staging tensor is free again (previous call's readers are done)
-        nblk = host_out.up_blocks if c_loc >= 2 * host_out.up_blocks else 1
-        for k in range(nblk):
-            c0, c1 = k * c_loc // nblk, (k + 1) * c_loc // nblk
-            with torch.cuda.stream(up):
-                cols_local[c0:c1].copy_(host_out.cols_host[c0:c1], non_blocking=True)
-                landed = torch.cuda.Event()
-                landed.record()
-            torch.cuda.current_stream().wait_event(landed)
-            first_stage(cols_local[c0:c1], coeffs[c0:c1])
-            to_host(host_out.coeffs[c0:c1] if host_out.coeffs is not None else None, coeffs[c0:c1])
-    else:
-        first_stage(cols_local, coeffs)
-        to_host(host_out.coeffs if host_out else None, coeffs)
+    to_host(host_out.coeffs if host_out else None, coeffs)
     if exchange == "peer" and G > 1:
         # 2+3 fused: every rank's LDE kernel writes block s of its output into rank s's receive buffer
         ex = sc.get("peer_exchange")

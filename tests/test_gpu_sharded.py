@@ -77,59 +77,6 @@ def test_sharded_from_coeffs_nccl(tmp_path, oracle):
     assert np.array_equal(parts[0]["cap"], ref["cap"])
 
 
-def _worker_host(rank, world, port, ncols, n_log, kind, out_dir):
-    """Pinned host columns in (uploaded block by block under the iNTT), every output streamed to pinned host buffers."""
-    sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import torch
-    import torch.distributed as dist
-
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
-    from util import field_elems
-
-    from mapreduce_plonky2_b200 import sharded as S
-
-    cols = field_elems(0xBEEF, (ncols, 1 << n_log))
-    c_loc, n, N = ncols // world, 1 << n_log, (1 << n_log) << 3
-    pin = lambda shape: torch.empty(shape, dtype=torch.int64, pin_memory=True)
-    cols_h = pin((c_loc, n))
-    cols_h.copy_(torch.from_numpy(cols[rank * c_loc:(rank + 1) * c_loc].view(np.int64).copy()))
-    ho = S.HostOutputs(pin((c_loc, n)), pin((N // world, ncols)), pin((2 * (N - 16) // world, 4)), pin((16, 4)),
-                       torch.cuda.Stream(), cols_host=cols_h, up_stream=torch.cuda.Stream())
-    staging = torch.empty((c_loc, n), dtype=torch.int64, device="cuda")
-    scratch = {}
-    for _ in range(2):   # twice: the second call reuses the staging tensor while the first call's copies drain
-        S.commit_sharded(staging, ncols, 3, 4, kind, S.CudaEngine(), scratch=scratch, host_out=ho)
-    torch.cuda.synchronize()
-    np.savez(os.path.join(out_dir, "rank%d.npz" % rank), coeffs=ho.coeffs.numpy().view(np.uint64),
-             leaves=ho.leaves.numpy().view(np.uint64), digests=ho.digests.numpy().view(np.uint64), cap=ho.cap.numpy().view(np.uint64))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-def test_sharded_pipelined_host_buffers(tmp_path, oracle):
-    import torch
-    import torch.multiprocessing as mp
-
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    from util import field_elems
-
-    ncols, n_log, kind = 32, 17, 0     # 2^20 leaves: 8 leaf chunks and 4 upload blocks per rank
-    port = 29800 + (os.getpid() % 2000)
-    mp.spawn(_worker_host, args=(2, port, ncols, n_log, kind, str(tmp_path)), nprocs=2, join=True)
-    ref = oracle.commit(field_elems(0xBEEF, (ncols, 1 << n_log)), 3, 4, kind)
-    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(2)]
-    assert np.array_equal(np.concatenate([p["coeffs"] for p in parts]), ref["coeffs"])
-    assert np.array_equal(np.concatenate([p["leaves"] for p in parts]), ref["leaves"])
-    assert np.array_equal(np.concatenate([p["digests"] for p in parts]), ref["digests"])
-    for p in parts:
-        assert np.array_equal(p["cap"], ref["cap"])
-
-
 # ---- the same path behind the C ABI: one process, one host thread per device, peer stores, no NCCL -------------
 def _build_cpp(tmp_path, name):
     import subprocess
