@@ -322,16 +322,18 @@ GL_DEV void pos_renorm_d(double &A, double &B) {
 //     round `round` - 1 (full rounds; round 30 = zeros);
 //   c_pos_t0bias[2*(r-4) + plane] = 2^52 + offset + word of t_{r+1}[0] (partial rounds, lane 0);
 //   c_pos_exbias[2*lane + plane]  = 2^52 + offset + word of d_26[lane] (leaving the partial rounds).
-static __constant__ double c_pos_dbias[MP2_POSEIDON_DBIAS_LEN] = {MP2_POSEIDON_DBIAS_LIST};
-static __constant__ double c_pos_t0bias[MP2_POSEIDON_T0BIAS_LEN] = {MP2_POSEIDON_T0BIAS_LIST};
-static __constant__ double c_pos_exbias[MP2_POSEIDON_EXBIAS_LEN] = {MP2_POSEIDON_EXBIAS_LIST};
-static __constant__ double c_pos_r4[MP2_POSEIDON_R4D_LEN] = {MP2_POSEIDON_R4D_LIST};  // round-4 constants as plane doubles
-
-// MP2_POSEIDON_F64_FULL = 1: the eight full rounds use the FP64 planes too; 0: they keep the 22|21|21-bit integer
-// planes and only the 22 partial rounds (where FP64 removes the per-round renormalisation) run on the FP64 pipe.
 #ifndef MP2_POSEIDON_F64_FULL
 #define MP2_POSEIDON_F64_FULL 0
 #endif
+static __constant__ double c_pos_t0bias[MP2_POSEIDON_T0BIAS_LEN] = {MP2_POSEIDON_T0BIAS_LIST};
+static __constant__ double c_pos_exbias[MP2_POSEIDON_EXBIAS_LEN] = {MP2_POSEIDON_EXBIAS_LIST};
+#if MP2_POSEIDON_F64_FULL  // only the all-FP64 variant needs the per-round biases (6 KB of constant memory)
+static __constant__ double c_pos_dbias[MP2_POSEIDON_DBIAS_LEN] = {MP2_POSEIDON_DBIAS_LIST};
+static __constant__ double c_pos_r4[MP2_POSEIDON_R4D_LEN] = {MP2_POSEIDON_R4D_LIST};  // round-4 constants as plane doubles
+#endif
+
+// MP2_POSEIDON_F64_FULL = 1: the eight full rounds use the FP64 planes too; 0 (default): they keep the 22|21|21-bit integer
+// planes and only the 22 partial rounds (where FP64 removes the per-round renormalisation) run on the FP64 pipe.
 template <bool SYNC>
 GL_DEV void poseidon_permute_f64(u64 (&s)[12]) {
 #pragma unroll
