@@ -13,7 +13,6 @@ zero-knowledge blinding are not supported (the reference enables neither).  ctyp
 """
 from __future__ import annotations
 
-from dataclasses import dataclass
 from typing import Callable, List, Sequence
 
 import numpy as np
@@ -25,26 +24,9 @@ from .quotient import CircuitDesc, compute_quotient_polys
 P = P2.ORDER
 
 
-@dataclass
-class OpeningSet:
-    """``OpeningSet``: every polynomial at zeta (extension values, (count, 2) arrays) and the Zs at g*zeta."""
-    constants: np.ndarray
-    plonk_sigmas: np.ndarray
-    wires: np.ndarray
-    plonk_zs: np.ndarray
-    partial_products: np.ndarray
-    quotient_polys: np.ndarray
-    plonk_zs_next: np.ndarray
-
-
-@dataclass
-class Proof:
-    """``Proof<F, C, D>`` (plonk/proof.rs)."""
-    wires_cap: P2.MerkleCap
-    plonk_zs_partial_products_cap: P2.MerkleCap
-    quotient_polys_cap: P2.MerkleCap
-    openings: OpeningSet
-    opening_proof: GF.FriProof
+# Proof / OpeningSet are the wire-format classes (wire.py): a proof produced here serialises as
+# bincode(ProofWithVK) / bincode(ProofWithPublicInputs) without conversion (mp2-common/src/proof.rs:41-57).
+from .wire import OpeningSet, Proof, ProofWithPublicInputs, ProofWithVK, VerifierOnlyCircuitData  # noqa: E402,F401
 
 
 def primitive_root_of_unity(bits: int) -> int:
@@ -89,8 +71,9 @@ def prove(circuit: CircuitDesc, constants_sigmas: P2.PolynomialBatch, circuit_di
     w0 = constants_sigmas.num_polys
     z0 = w0 + wires.num_polys
     q0 = z0 + zs_pp.num_polys
-    openings = OpeningSet(at_zeta[:nc], at_zeta[nc:w0], at_zeta[w0:z0], at_zeta[z0:z0 + nch], at_zeta[z0 + nch:q0],
-                          at_zeta[q0:], fri_openings[1])
+    openings = OpeningSet(constants=at_zeta[:nc], plonk_sigmas=at_zeta[nc:w0], wires=at_zeta[w0:z0],
+                          plonk_zs=at_zeta[z0:z0 + nch], plonk_zs_next=fri_openings[1],
+                          partial_products=at_zeta[z0 + nch:q0], quotient_polys=at_zeta[q0:])
     try:
         opening_proof = GF.prove_openings(batches, oracles, ch, config.fri_params(db))
     finally:

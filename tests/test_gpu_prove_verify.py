@@ -51,6 +51,16 @@ def test_gpu_proof_is_accepted_by_the_by_definition_verifier(seed, degree_bits, 
     d = _as_dict(proof)
     cs_cap = cs.merkle_tree.cap.hashes.tolist()
     PR.verify_proof(c, digest.tolist(), cs_cap, inst.public_inputs_hash, d, kind, pow_bits=10)
+    # ... and as the bytes the reference moves between tasks: bincode(ProofWithVK) -> parse -> the same proof verifies
+    from mapreduce_plonky2_b200 import wire as W
+
+    pvk = W.ProofWithVK(W.ProofWithPublicInputs(proof, np.array(inst.public_inputs_hash, dtype=np.uint64)),
+                        W.VerifierOnlyCircuitData(cs.merkle_tree.cap, digest))
+    data = pvk.serialize()
+    back = W.ProofWithVK.deserialize(data)
+    assert back.serialize() == data
+    PR.verify_proof(c, back.vk.circuit_digest.tolist(), back.vk.constants_sigmas_cap.hashes.tolist(), inst.public_inputs_hash,
+                    _as_dict(back.proof.proof), kind, pow_bits=10)
     # tampering: an opening, a cap, the final polynomial, a public input
     rng = random.Random(seed)
     for what in ("opening", "quotient_opening", "cap", "final_poly", "public_input"):
