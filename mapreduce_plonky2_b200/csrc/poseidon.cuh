@@ -467,6 +467,48 @@ GL_DEV void p2_external_rc(u64 (&s)[12], int slot) {
   for (int i = 0; i < 12; i++) s[i] = pos_merge3(o0[i], o1[i], o2[i]);
 }
 
+// The same layer on the FP64 pipe (MP2_POSEIDON2_F64, default): two exact 32-bit planes as doubles (row sums <= 64:
+// 38-bit outputs), the slot constant folded into the 2^52 conversion bias, planes merged by pos_merge_d.  The integer
+// Poseidon2 kernel is alu-bound (ncu: alu 78 %, fma-heavy 70 %, fp64 idle, profiles/r2z_poseidon2_leafhash.summary.txt);
+// this moves ~200 of the ~350 instructions of each of the nine external layers off the integer pipes.
+#ifndef MP2_POSEIDON2_F64
+#define MP2_POSEIDON2_F64 1
+#endif
+static __constant__ double c_p2_dbias[MP2_POSEIDON2_DBIAS_LEN] = {MP2_POSEIDON2_DBIAS_LIST};
+GL_DEV void p2_ext_plane_d(const double (&x)[12], double (&y)[12]) {
+  double t[12];
+#pragma unroll
+  for (int c = 0; c < 12; c += 4) {
+    const double x0 = x[c], x1 = x[c + 1], x2 = x[c + 2], x3 = x[c + 3];
+    const double t0 = x0 + x1, t1 = x2 + x3;
+    const double t2 = x1 * 2.0 + t1, t3 = x3 * 2.0 + t0;
+    const double t4 = t1 * 4.0 + t3, t5 = t0 * 4.0 + t2;
+    t[c] = t3 + t5;
+    t[c + 1] = t5;
+    t[c + 2] = t2 + t4;
+    t[c + 3] = t4;
+  }
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    const double col = t[l] + t[4 + l] + t[8 + l];
+#pragma unroll
+    for (int k = 0; k < 3; k++) y[4 * k + l] = t[4 * k + l] + col;
+  }
+}
+GL_DEV void p2_external_rc_d(u64 (&s)[12], int slot) {
+  double A[12], B[12], YA[12], YB[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    A[i] = pos_u32_to_d(lo32(s[i]));
+    B[i] = pos_u32_to_d(hi32(s[i]));
+  }
+  p2_ext_plane_d(A, YA);
+  p2_ext_plane_d(B, YB);
+  const double *bias = c_p2_dbias + 24 * slot;
+#pragma unroll
+  for (int i = 0; i < 12; i++) s[i] = pos_merge_d(YA[i] + bias[2 * i], YB[i] + bias[2 * i + 1]);
+}
+
 // M_I: out[i] = s[i]*mu_i + sum(s).  The sum is accumulated in 96 bits and reduced once.
 GL_DEV void p2_internal(u64 (&s)[12]) {
   u32 a0 = lo32(s[0]), a1 = hi32(s[0]), a2 = 0;
@@ -482,14 +524,19 @@ GL_DEV void p2_internal(u64 (&s)[12]) {
 
 template <bool SYNC>
 GL_DEV void poseidon2_permute(u64 (&s)[12]) {
-  p2_external_rc(s, 0);
+#if MP2_POSEIDON2_F64
+#define P2_EXTERNAL p2_external_rc_d
+#else
+#define P2_EXTERNAL p2_external_rc
+#endif
+  P2_EXTERNAL(s, 0);
   const u64 *rc = c_p2_rc + 48;
 #pragma unroll 1
   for (int phase = 0; phase < 2; phase++) {  // one copy of the external-round code, see poseidon_permute
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
       sbox_layer<MP2_P2_SBOX_ROLLED != 0>(s);
-      p2_external_rc(s, 4 * phase + k + 1);  // slots 1..4, then 5..8 (tools/gen_poseidon_constants.py)
+      P2_EXTERNAL(s, 4 * phase + k + 1);  // slots 1..4, then 5..8 (tools/gen_poseidon_constants.py)
       MP2_ROUND_SYNC();
     }
     if (phase == 0) {

@@ -140,6 +140,8 @@ def main():
         tabled("MP2_POSEIDON_R4D", poseidon_f64_tables()[3]),
         "// Poseidon2 external-round constants as 22|21|21-bit limbs, index ((12*slot + lane)*3 + limb); see generator",
         table32("MP2_POSEIDON2_RC3", p2_rc3),
+        "// the same slot constants as FP64 conversion biases: (12*slot + lane)*2 + word -> 2^52 + 32-bit word (p2_external_rc_d)",
+        tabled("MP2_POSEIDON2_DBIAS", [(1 << 52) + w for slot in slots for v in slot for w in (v & 0xFFFFFFFF, v >> 32)]),
         table("MP2_POSEIDON2_DIAG", R.P2_DIAG),
         "",
     ]
