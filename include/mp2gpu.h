@@ -16,7 +16,8 @@
  *     canonical (< p), so ==, serde and to_bytes agree with the CPU path;
  *   - entry points are re-entrant: each calling thread gets its own CUDA stream, the device is the
  *     one last chosen by that thread with mp2gpu_init() (default 0);
- *   - there is NO CPU fallback: without a usable CUDA device every call returns an error string.
+ *   - there is NO CPU fallback: without a usable CUDA device every data-path call returns an error string (the two
+ *     mp2gpu_transcript_* entry points and mp2gpu_merkle_prove are host-only by nature and say so).
  *
  * Layouts:
  *   coeffs   ncols x n            column-major, natural order
