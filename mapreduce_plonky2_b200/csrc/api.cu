@@ -320,7 +320,9 @@ Status commit_host(const uint64_t *const *cols, size_t ncols, u32 n_log, u32 rat
     b->cap_height = cap_height;
     b->hash_kind = hash_kind;
     b->coeffs = d_coeffs.release();
-    b->lde = nullptr;  // the row-major leaves serve every reader of the handle; the column-major copy is dropped
+    // the row-major leaves serve every reader of the handle; the column-major copy is kept as well when it is small
+    // (proof-sized batches: the quotient kernel reads it coalesced), dropped for big ones
+    b->lde = ncols * N * sizeof(u64) <= ((size_t)1 << 29) ? d_lde.release() : nullptr;
     b->leaves = d_leaves.release();
     b->digests = d_dig.release();
     b->cap = d_cap.release();
@@ -366,7 +368,7 @@ Status commit_device_columns(const u64 *d_cols, size_t ncols, u32 n_log, u32 rat
     b->cap_height = cap_height;
     b->hash_kind = hash_kind;
     b->coeffs = d_coeffs.release();
-    b->lde = nullptr;
+    b->lde = ncols * N * sizeof(u64) <= ((size_t)1 << 29) ? d_lde.release() : nullptr;
     b->leaves = d_leaves.release();
     b->digests = d_dig.release();
     b->cap = d_cap.release();

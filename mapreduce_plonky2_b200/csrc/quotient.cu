@@ -39,7 +39,9 @@ struct QGate {
 struct QParams {
   u32 n_log, qb, nch, num_wires, R, num_constants, num_selectors, npp, num_gates, gate_term_base, nterms;
   u32 cs_cols, wi_cols, zp_cols;
-  const u64 *cs, *wi, *zp;          // row-major leaves of the three batches (N_lde rows each, first N_q used)
+  const u64 *cs, *wi, *zp;          // the three batches: row-major leaves (N_lde rows each, first N_q used), or -- COLMAJOR --
+                                    // their leaf-ordered column-major LDE (column c at + c * stride), read coalesced
+  size_t cs_stride, wi_stride, zp_stride;
   const u64 *apow;                  // nch x nterms: alpha_c^j
   const u64 *k_is;                  // R coset shifts 7^j
   u64 betas[kMaxChallenges], gammas[kMaxChallenges], pi_hash[4];
@@ -51,6 +53,16 @@ struct QParams {
 GL_DEV u64 gl_neg(u64 a) { return gl_sub(0, a); }
 GL_DEV u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
 
+// one batch row seen from one thread: element c of leaf L
+template <bool COLMAJOR>
+struct Row {
+  const u64 *p;
+  size_t stride;
+  GL_DEV u64 operator[](u32 c) const { return COLMAJOR ? p[(size_t)c * stride] : p[c]; }
+  GL_DEV Row operator+(u32 c) const { return Row{COLMAJOR ? p + (size_t)c * stride : p + c, stride}; }
+};
+
+template <bool COLMAJOR>
 __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__ QParams P, u64 *__restrict__ out) {
   const u32 nq_log = P.n_log + P.qb;
   const u32 L = blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,8 +70,11 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
   const u32 i = brev_bits(L, nq_log);
   const u32 md = 1u << P.qb;
   const u32 L_next = brev_bits((i + md) & ((1u << nq_log) - 1), nq_log);  // next_step = 2^quotient_degree_bits
-  const u64 *cs = P.cs + (size_t)L * P.cs_cols, *wi = P.wi + (size_t)L * P.wi_cols;
-  const u64 *zp = P.zp + (size_t)L * P.zp_cols, *zp_next = P.zp + (size_t)L_next * P.zp_cols;
+  typedef Row<COLMAJOR> R;
+  const R cs{COLMAJOR ? P.cs + L : P.cs + (size_t)L * P.cs_cols, P.cs_stride};
+  const R wi{COLMAJOR ? P.wi + L : P.wi + (size_t)L * P.wi_cols, P.wi_stride};
+  const R zp{COLMAJOR ? P.zp + L : P.zp + (size_t)L * P.zp_cols, P.zp_stride};
+  const R zp_next{COLMAJOR ? P.zp + L_next : P.zp + (size_t)L_next * P.zp_cols, P.zp_stride};
   const u64 sx = gl_mul(kCosetShift, gl_pow(P.w_nq, i));  // shifted_x
   const u64 zh = P.zh[i & (md - 1)];
   const u64 l_0 = gl_mul(zh, gl_inv(gl_mul(P.n_field, gl_sub(sx, 1))));
@@ -74,7 +89,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
   // vanishing_z_1_terms, then the partial-product checks challenge by challenge
   for (u32 c = 0; c < P.nch; c++) add_term(c, gl_mul(l_0, gl_sub(zp[c], 1)));
   const u32 nchunks = P.npp + 1;
-  const u64 *sig = cs + P.num_constants;
+  const R sig = cs + P.num_constants;
   for (u32 c = 0; c < P.nch; c++) {
     const u64 beta = P.betas[c], gamma = P.gammas[c];
     u64 prev = zp[c];  // accs[q]: Z(x), partial products..., Z(g x)
@@ -92,7 +107,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
     }
   }
   // evaluate_gate_constraints_base_batch: sum_g filter_g * sum_i alpha^(base + i) * constraint_{g,i}
-  const u64 *gc = cs + P.num_selectors;
+  const R gc = cs + P.num_selectors;
   for (u32 g = 0; g < P.num_gates; g++) {
     const QGate gate = P.gates[g];
     const u64 s = cs[gate.selector];
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
     if (gate.kind == MP2GPU_GATE_ARITHMETIC) {
       const u64 c0 = gc[0], c1 = gc[1];
       for (u32 op = 0; op < gate.num_ops; op++) {
-        const u64 *w = wi + 4 * op;
+        const R w = wi + 4 * op;
         cons(op, gl_sub(w[3], gl_mul_add(gl_mul(c0, w[0]), w[1], gl_mul(c1, w[2]))));
       }
     } else if (gate.kind == MP2GPU_GATE_CONSTANT) {
@@ -124,7 +139,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
       const u32 stride = arith ? 8 : 6, out_at = arith ? 6 : 4;
       const u64 c0 = gc[0], c1 = arith ? gc[1] : 0;
       for (u32 op = 0; op < gate.num_ops; op++) {
-        const u64 *w = wi + stride * op;
+        const R w = wi + stride * op;
         const u64 p0 = gl_mul_add(gl_mul(7, w[1]), w[3], gl_mul(w[0], w[2]));
         const u64 p1 = gl_mul_add(w[0], w[3], gl_mul(w[1], w[2]));
         u64 r0 = gl_mul(c0, p0), r1 = gl_mul(c0, p1);
@@ -155,7 +170,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
     } else if (gate.kind == MP2GPU_GATE_EXPONENTIATION) {
       const u32 nb = gate.num_ops;
       const u64 base = wi[0];
-      const u64 *bits = wi + 1, *iv = wi + 2 + nb;
+      const R bits = wi + 1, iv = wi + (2 + nb);
       for (u32 k = 0; k < nb; k++) {
         const u64 prev = k == 0 ? 1 : gl_sqr(iv[k - 1]);
         const u64 b = bits[nb - 1 - k];
@@ -181,7 +196,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
       const u32 routed = (2 + vec) * copies + nx;
       u32 ci = 0;
       for (u32 cp = 0; cp < copies; cp++) {
-        const u64 *w = wi + (2 + vec) * cp, *bs = wi + routed + cp * bits;
+        const R w = wi + (2 + vec) * cp, bs = wi + (routed + cp * bits);
         u64 rec = 0;
         for (u32 k = 0; k < bits; k++) cons(ci++, gl_mul(bs[k], gl_sub(bs[k], 1)));
         for (u32 k = bits; k-- > 0;) rec = gl_add(gl_add(rec, rec), bs[k]);
@@ -231,7 +246,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
       for (u32 r = 0; r < 30; r++) {
         if (r < 4 || r >= 26) {
           if (r != 0) {
-            const u64 *sb = wi + (r < 4 ? 29 + 12 * (r - 1) : 87 + 12 * (r - 26));
+            const R sb = wi + (r < 4 ? 29 + 12 * (r - 1) : 87 + 12 * (r - 26));
 #pragma unroll
             for (u32 i = 0; i < 12; i++) {
               cons(ci + i, gl_sub(st[i], sb[i]));
@@ -291,7 +306,7 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
     if (b->n_log != n_log) return "quotient_polys: batch degree differs from the circuit's degree_bits";
     if (b->rate_bits < qb) return "quotient_polys: quotient_degree_bits exceeds a batch's rate_bits (max_quotient_degree_factor <= 2^rate_bits)";
     if (b->device != bcs->device) return "quotient_polys: the three batches live on different devices";
-    if (!b->leaves) return "quotient_polys: batch holds no leaf rows";
+    if (!b->leaves && !b->lde) return "quotient_polys: batch holds no LDE rows";
   }
   const u32 md = 1u << qb, npp = (R + md - 1) / md - 1;
   if (bcs->ncols != ci->num_constants + R) return "quotient_polys: constants_sigmas batch must hold num_constants + num_routed_wires columns";
@@ -389,7 +404,14 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
   P.gate_term_base = nch + nch * (npp + 1);
   P.nterms = P.gate_term_base + ngc;
   P.cs_cols = (u32)bcs->ncols; P.wi_cols = (u32)bwi->ncols; P.zp_cols = (u32)bzp->ncols;
-  P.cs = bcs->leaves; P.wi = bwi->leaves; P.zp = bzp->leaves;
+  // all three kept their column-major LDE: coalesced reads (MP2_QUOTIENT_ROWMAJOR=1 forces the row-major path: tests)
+  const char *force_rows = getenv("MP2_QUOTIENT_ROWMAJOR");
+  const bool colmajor = bcs->lde && bwi->lde && bzp->lde && !(force_rows && *force_rows == '1' && bcs->leaves && bwi->leaves && bzp->leaves);
+  if (!colmajor && (!bcs->leaves || !bwi->leaves || !bzp->leaves)) return "quotient_polys: batches hold no common layout";
+  P.cs = colmajor ? bcs->lde : bcs->leaves; P.wi = colmajor ? bwi->lde : bwi->leaves; P.zp = colmajor ? bzp->lde : bzp->leaves;
+  P.cs_stride = (size_t)1 << (bcs->n_log + bcs->rate_bits);
+  P.wi_stride = (size_t)1 << (bwi->n_log + bwi->rate_bits);
+  P.zp_stride = (size_t)1 << (bzp->n_log + bzp->rate_bits);
   for (u32 c = 0; c < nch; c++) { P.betas[c] = betas[c] % kP; P.gammas[c] = gammas[c] % kP; }
   for (u32 k = 0; k < 4; k++) P.pi_hash[k] = pi_hash ? pi_hash[k] % kP : 0;
   // ZeroPolyOnCoset: Z_H(g w^i) = g^n w_{2^qb}^(i mod 2^qb) - 1
@@ -424,7 +446,8 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
   P.k_is = d_tab.p + (size_t)nch * P.nterms;
   {
     ProfScope _p("k_quotient_points", st);
-    k_quotient_points<<<(unsigned)((Nq + 127) / 128), 128, 0, st>>>(P, d_q.p);
+    if (colmajor) k_quotient_points<true><<<(unsigned)((Nq + 127) / 128), 128, 0, st>>>(P, d_q.p);
+    else k_quotient_points<false><<<(unsigned)((Nq + 127) / 128), 128, 0, st>>>(P, d_q.p);
   }
   MP2_LAUNCH_CHECK();
   // the source vector `tab` must outlive the asynchronous upload

@@ -2,6 +2,7 @@
 SURVEY.md 8(f) row 3) through the C ABI: bit-exact against the oracle's restatement (oracle/quotient.py), accepted by
 the by-definition verifier identity (tests/plonk_ref.py) -- prove then verify, as every `run_circuit` test of the
 reference does -- and the commitment of the chunks equals from_coeffs of the same chunks."""
+import os
 import random
 
 import numpy as np
@@ -47,8 +48,13 @@ def test_quotient_matches_oracle_and_passes_the_verifier_identity(oracle, seed, 
     cap = min(4, degree_bits + rate_bits)
     b_cs, b_w, b_z = _commit3(G, inst, zs_pp, rate_bits, cap, kind)
     desc = Q.CircuitDesc.from_circuit(c)
-    qb = Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, rate_bits, cap,
-                                  hash_kind=kind, fetch_leaves=True)
+    # odd seeds read the batches' row-major leaves (what big batches keep), even seeds the column-major LDE
+    os.environ["MP2_QUOTIENT_ROWMAJOR"] = "1" if seed % 2 else "0"
+    try:
+        qb = Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, rate_bits, cap,
+                                      hash_kind=kind, fetch_leaves=True)
+    finally:
+        os.environ.pop("MP2_QUOTIENT_ROWMAJOR", None)
     chunks = qb.polynomials
     assert chunks.shape == (c.num_challenges * c.max_degree, c.n)
     if degree_bits <= 6:  # the pure-Python restatement is O(N * terms) big-int work
