@@ -30,11 +30,11 @@
 namespace mp2 {
 namespace {
 
-constexpr u32 kMaxGates = 32, kMaxChallenges = 4, kMaxQuotientBits = 4;
+constexpr u32 kMaxGates = 32, kMaxChallenges = 4, kMaxQuotientBits = 4, kMaxGateConstraints = 256;
 constexpr u64 kUnusedSelector = 0xFFFFFFFFull;
 
 struct QGate {
-  u32 kind, num_ops, selector, group_begin, group_end, param;
+  u32 kind, num_ops, selector, group_begin, group_end, param, nc;  // nc = number of constraints of the gate
 };
 struct QParams {
   u32 n_log, qb, nch, num_wires, R, num_constants, num_selectors, npp, num_gates, gate_term_base, nterms;
@@ -50,6 +50,7 @@ struct QParams {
   QGate gates[kMaxGates];
 };
 
+static __constant__ u32 c_circ[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
 GL_DEV u64 gl_neg(u64 a) { return gl_sub(0, a); }
 GL_DEV u64 gl_inv(u64 a) { return gl_pow(a, GL_P - 2); }
 
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
   }
   // evaluate_gate_constraints_base_batch: sum_g filter_g * sum_i alpha^(base + i) * constraint_{g,i}
   const R gc = cs + P.num_selectors;
+  u64 vals[kMaxGateConstraints];  // local memory: the constraints of the gate being evaluated
   for (u32 g = 0; g < P.num_gates; g++) {
     const QGate gate = P.gates[g];
     const u64 s = cs[gate.selector];
@@ -115,14 +117,10 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
     for (u32 j = gate.group_begin; j < gate.group_end; j++)
       if (j != g) filt = gl_mul(filt, gl_sub((u64)j, s));
     if (P.num_selectors > 1) filt = gl_mul(filt, gl_sub(kUnusedSelector, s));
-    u64 inner[kMaxChallenges];
-#pragma unroll
-    for (u32 c = 0; c < kMaxChallenges; c++) inner[c] = 0;
-    auto cons = [&](u32 idx, u64 v) {
-#pragma unroll
-      for (u32 c = 0; c < kMaxChallenges; c++)
-        if (c < P.nch) inner[c] = gl_mul_add(v, P.apow[c * P.nterms + P.gate_term_base + idx], inner[c]);
-    };
+    // A gate's constraint values go to a per-thread scratch array and are folded into the alpha-weighted sums by ONE
+    // rolled loop per gate.  (Folding at every constraint site -- 4 multiply-adds inlined ~150 times -- made the kernel
+    // 13 k SASS instructions, 210 KB, and `no_instruction` its second stall: profiles/r2z_quotient_points.summary.txt.)
+    auto cons = [&](u32 idx, u64 v) { vals[idx] = v; };
     if (gate.kind == MP2GPU_GATE_ARITHMETIC) {
       const u64 c0 = gc[0], c1 = gc[1];
       for (u32 op = 0; op < gate.num_ops; op++) {
@@ -180,14 +178,16 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
       }
       cons(nb, gl_sub(wi[1 + nb], iv[nb - 1]));
     } else if (gate.kind == MP2GPU_GATE_POSEIDON_MDS) {
-      constexpr u32 CIRC[12] = {17, 15, 41, 16, 2, 28, 13, 13, 39, 18, 34, 20};
+#pragma unroll 1
       for (u32 r = 0; r < 12; r++)
+#pragma unroll 1
         for (u32 comp = 0; comp < 2; comp++) {
           u64 acc = r == 0 ? gl_mul(8, wi[comp]) : 0;
+#pragma unroll 1
           for (u32 k = 0; k < 12; k++) {
             u32 src = k + r;
             src = src >= 12 ? src - 12 : src;
-            acc = gl_mul_add(wi[2 * src + comp], (u64)CIRC[k], acc);
+            acc = gl_mul_add(wi[2 * src + comp], (u64)c_circ[k], acc);
           }
           cons(2 * r + comp, gl_sub(wi[24 + 2 * r + comp], acc));
         }
@@ -265,6 +265,17 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
       }
 #pragma unroll
       for (u32 i = 0; i < 12; i++) cons(ci + i, gl_sub(st[i], wi[12 + i]));
+    }
+    u64 inner[kMaxChallenges];
+#pragma unroll
+    for (u32 c = 0; c < kMaxChallenges; c++) inner[c] = 0;
+    const u64 *ap = P.apow + P.gate_term_base;
+#pragma unroll 1
+    for (u32 k = 0; k < gate.nc; k++) {
+      const u64 v = vals[k];
+#pragma unroll
+      for (u32 c = 0; c < kMaxChallenges; c++)
+        if (c < P.nch) inner[c] = gl_mul_add(v, ap[c * P.nterms + k], inner[c]);
     }
 #pragma unroll
     for (u32 c = 0; c < kMaxChallenges; c++)
@@ -389,6 +400,8 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
       default:
         return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum, reducing, reducing_extension, random_access, exponentiation, poseidon_mds)";
     }
+    if (nc > kMaxGateConstraints) return "quotient_polys: a gate has more than " + std::to_string(kMaxGateConstraints) + " constraints";
+    d.nc = nc;
     ngc = std::max(ngc, nc);
     max_gate_constants = std::max(max_gate_constants, nk);
   }
