@@ -611,6 +611,18 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         for _ in range(steps):
             call_resident()
         dt_res = (time.perf_counter() - t0) / steps
+
+        # variant: what prover.prove() calls -- only the cap comes back, coefficients / rows / digests stay behind the handle
+        def call_cap():
+            _lib.call("mp2gpu_commit_from_values", ptrs(cols_h), a.ncols, a.n_log, a.rate_bits, a.cap_height, kind,
+                      None, None, None, C.cast(cap_h.data_ptr(), u64p), C.byref(handle))
+            _lib.load().mp2gpu_batch_free(handle)
+
+        call_cap()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call_cap()
+        dt_cap = (time.perf_counter() - t0) / steps
     else:
         cols_h = torch.empty((c_loc, n), dtype=torch.int64, pin_memory=True)
         cols_h.random_(0, 1 << 62)
@@ -659,6 +671,24 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
         t = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt_res = float(t.item())
+        # only the cap back (prover.prove()'s call): coefficients, rows and digests stay in HBM on their ranks
+        host_cap = S.HostOutputs(None, None, None, cap_h, host_out.copy_stream)
+
+        def call_cap():
+            cols_d.copy_(cols_h, non_blocking=True)
+            S.commit_sharded(cols_d, a.ncols, a.rate_bits, a.cap_height, kind, engine, scratch=scratch,
+                             exchange=a.exchange, host_out=host_cap)
+            torch.cuda.synchronize()
+
+        call_cap()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            call_cap()
+        dist.barrier()
+        t = torch.tensor([(time.perf_counter() - t0) / steps], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_cap = float(t.item())
     elems = a.ncols * N
     d2h_res = d2h - 8 * a.ncols * (N // world)
     # Headline e2e: the call a patched plonky2 makes now that every later reader of the LDE rows runs on the device
@@ -670,6 +700,10 @@ def run_e2e(a, G, D, S, torch, dist, world, rank, kind, engine, scratch, solo_bu
            "api": api + "; leaves_out = NULL + handle_out (rows stay device-resident)",
            "outputs": "coefficients + digests + cap copied back to the host every step; LDE rows stay in HBM behind "
                       "mp2gpu_batch_fetch_rows / _open / _eval / mp2gpu_quotient_polys",
+           "cap_only_to_host": {"value": elems / dt_cap / 1e9, "unit": "Gelem/s", "ms_per_step": dt_cap * 1e3,
+                                "d2h_bytes_per_step": 32 * ncap,
+                                "note": "the call prover.prove() makes: host columns in, the cap out; coefficients, rows and "
+                                        "digests stay in HBM behind the handle (openings / quotient / query rounds read them there)"},
            "all_outputs_to_host": {"value": elems / dt / 1e9, "unit": "Gelem/s", "ms_per_step": dt * 1e3,
                                    "d2h_bytes_per_step": d2h,
                                    "note": "the same call with leaves_out set: all %0.1f GB of row-major leaves cross PCIe "
