@@ -351,6 +351,22 @@ const char *mp2gpu_quotient_polys(const mp2gpu_circuit *circuit, const mp2gpu_ba
                                   uint32_t hash_kind, uint64_t *const *chunks_out, uint64_t *leaves_out,
                                   uint64_t *digests_out, uint64_t *cap_out, mp2gpu_batch **quotient_batch_out);
 
+/* ---- the permutation argument's running products on the device ------------------------------------
+ * plonky2 0.2.2 `all_wires_permutation_partial_products` / `wires_permutation_partial_products_and_zs`
+ * (plonk/prover.rs) followed by the prover's second commitment `PolynomialBatch::from_values(zs_partial_products,
+ * rate_bits, blinding = false, cap_height, ...)`: step 3 of every `circuit_data.prove(pw)` the reference issues
+ * (recursion-framework/src/circuit_builder.rs:308).  Inputs are the device-resident constants+sigmas and wires
+ * batches; the wire and sigma VALUES on the subgroup are recomputed from the coefficients they keep in HBM.
+ * Columns of the result: [Z_0 .. Z_{nch-1}, partial products of challenge 0 (num_partial_products of them), of
+ * challenge 1, ...] -- the layout the quotient step and the verifier's `zs_range` / `partial_products_range` expect.
+ * values_out (optional): that many host columns of n canonical values; the other outputs are those of
+ * mp2gpu_commit_from_values.  A zero denominator w + beta*sigma + gamma is an error (plonky2 panics there). */
+const char *mp2gpu_partial_products_and_zs(const mp2gpu_circuit *circuit, const mp2gpu_batch *constants_sigmas,
+                                           const mp2gpu_batch *wires, const uint64_t *betas, const uint64_t *gammas,
+                                           uint32_t rate_bits, uint32_t cap_height, uint32_t hash_kind,
+                                           uint64_t *const *values_out, uint64_t *leaves_out, uint64_t *digests_out,
+                                           uint64_t *cap_out, mp2gpu_batch **zs_partial_products_batch_out);
+
 /* Returns the calling thread's cached device blocks, the device's cached twiddle tables and the unused part of its
  * stream-ordered pool to the driver (the library keeps freed scratch for reuse: a prover repeats the same shapes;
  * tables are rebuilt on demand).  Call it when another allocator in the process needs the memory and no other

@@ -112,3 +112,34 @@ def compute_quotient_polys(desc: CircuitDesc, constants_sigmas: PolynomialBatch,
     del keep
     tree = MerkleTree(leaves, digests, MerkleCap(cap), hash_kind)
     return PolynomialBatch(chunks, tree, desc.degree_bits, rate_bits, False, handle if keep_on_device else None, ncols)
+
+
+def partial_products_and_zs(desc: CircuitDesc, constants_sigmas: PolynomialBatch, wires: PolynomialBatch,
+                            betas: Sequence[int], gammas: Sequence[int], rate_bits: int, cap_height: int,
+                            hash_kind: int = POSEIDON2, keep_on_device: bool = True, fetch_values: bool = True,
+                            fetch_leaves: bool = False, fetch_digests: bool = False) -> PolynomialBatch:
+    """plonky2 ``all_wires_permutation_partial_products`` + the second commitment of ``prove()`` on the device
+    (``mp2gpu_partial_products_and_zs``).  -> the ``zs_partial_products`` batch; with ``fetch_values`` its
+    ``polynomials`` are the VALUES on the subgroup, columns [Z_0.., pp(ch 0).., pp(ch 1)..]."""
+    for b in (constants_sigmas, wires):
+        if b._handle is None:
+            raise Mp2GpuError("partial_products_and_zs needs device-resident batches (commit with keep_on_device=True)")
+    nch, n = desc.num_challenges, 1 << desc.degree_bits
+    if not (len(betas) == len(gammas) == nch):
+        raise Mp2GpuError("betas / gammas must have num_challenges entries")
+    cc, keep = desc._c()
+    vec = lambda v: np.ascontiguousarray(np.array([int(x) for x in v], dtype=np.uint64))
+    b_, g_ = vec(betas), vec(gammas)
+    N, ncap, ncols = n << rate_bits, 1 << cap_height, nch * (1 + desc.num_partial_products)
+    values = np.empty((ncols, n), dtype=np.uint64) if fetch_values else None
+    leaves = np.empty((N, ncols), dtype=np.uint64) if fetch_leaves else None
+    digests = np.empty((max(2 * (N - ncap), 0), 4), dtype=np.uint64) if fetch_digests else None
+    cap = np.empty((ncap, 4), dtype=np.uint64)
+    handle = C.c_void_p(None)
+    _lib.call("mp2gpu_partial_products_and_zs", C.byref(cc), constants_sigmas._handle, wires._handle, _ptr(b_), _ptr(g_),
+              rate_bits, cap_height, hash_kind, _col_ptrs(values) if values is not None else None, _ptr(leaves),
+              _ptr(digests) if digests is not None and digests.size else None, _ptr(cap),
+              C.byref(handle) if keep_on_device else None)
+    del keep
+    tree = MerkleTree(leaves, digests, MerkleCap(cap), hash_kind)
+    return PolynomialBatch(values, tree, desc.degree_bits, rate_bits, False, handle if keep_on_device else None, ncols)
