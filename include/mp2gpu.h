@@ -367,6 +367,31 @@ const char *mp2gpu_partial_products_and_zs(const mp2gpu_circuit *circuit, const 
                                            uint64_t *const *values_out, uint64_t *leaves_out, uint64_t *digests_out,
                                            uint64_t *cap_out, mp2gpu_batch **zs_partial_products_batch_out);
 
+/* ---- the whole prove() from the witness on, as one call ---------------------------------------------
+ * plonky2 0.2.2 `prove_with_partition_witness` (plonk/prover.rs) after witness generation -- what every
+ * `circuit_data.prove(pw)` of the reference runs (recursion-framework/src/circuit_builder.rs:308,
+ * .../universal_verifier_gadget/wrap_circuit.rs:143): wires commitment, challenger, Z / partial products and their
+ * commitment, quotient polynomials and their commitment, OpeningSet at zeta and g*zeta, prove_openings (FRI commit
+ * phase, smallest proof-of-work witness, query rounds).  Data-path steps run on the device, the Fiat-Shamir
+ * transcript on the host; the rows, coefficients and digests of the four batches never leave HBM.
+ * constants_sigmas: the device-resident batch committed at circuit-build time (same rate_bits / cap_height).
+ * wires_values: num_wires host columns of n = 2^degree_bits values.  public_inputs_hash: 4 elements (the caller
+ * hashes the public inputs with the config's InnerHasher, as plonky2 does before this point).
+ * *proof_out receives bincode(ProofWithPublicInputs) -- mp2-common/src/proof.rs:86-90 `serialize_proof` -- in a
+ * buffer of *proof_len_out bytes that the caller releases with mp2gpu_free_bytes.  Gate coverage is
+ * mp2gpu_quotient_polys'; no lookups, no blinding. */
+typedef struct mp2gpu_prove_config {
+  uint32_t rate_bits, cap_height, hash_kind;  /* FriConfig::rate_bits / cap_height; MP2GPU_HASH_* */
+  uint32_t proof_of_work_bits, num_query_rounds;
+  uint32_t num_reductions;                    /* FriParams::reduction_arity_bits for this degree */
+  const uint32_t *reduction_arity_bits;
+} mp2gpu_prove_config;
+const char *mp2gpu_prove(const mp2gpu_circuit *circuit, const mp2gpu_prove_config *config,
+                         const mp2gpu_batch *constants_sigmas, const uint64_t *circuit_digest,
+                         const uint64_t *const *wires_values, const uint64_t *public_inputs, size_t num_public_inputs,
+                         const uint64_t *public_inputs_hash, uint8_t **proof_out, size_t *proof_len_out);
+void mp2gpu_free_bytes(uint8_t *p);
+
 /* Returns the calling thread's cached device blocks, the device's cached twiddle tables and the unused part of its
  * stream-ordered pool to the driver (the library keeps freed scratch for reuse: a prover repeats the same shapes;
  * tables are rebuilt on demand).  Call it when another allocator in the process needs the memory and no other

@@ -81,6 +81,9 @@ SIGNATURES = {
                                      C.c_uint32, C.c_uint32, u64pp, u64p, u64p, u64p, C.POINTER(C.c_void_p)]),
     "mp2gpu_partial_products_and_zs": (_ERR, [C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p, C.c_uint32, C.c_uint32,
                                               C.c_uint32, u64pp, u64p, u64p, u64p, C.POINTER(C.c_void_p)]),
+    "mp2gpu_prove": (_ERR, [C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64pp, u64p, C.c_size_t, u64p,
+                            C.POINTER(C.c_void_p), size_p]),
+    "mp2gpu_free_bytes": (None, [C.c_void_p]),
     "mp2gpu_transcript_permute": (_ERR, [u64p, C.c_uint32]),
     "mp2gpu_transcript_observe": (_ERR, [u64p, u64p, u32p, u64p, C.c_size_t, C.c_uint32, u32p]),
     "mp2gpu_trim": (_ERR, []),

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmp2gpu.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "ntt.cu", "merkle.cu", "tables.cu", "prof.cu", "fri.cu", "selftest.cu", "sharded.cu", "quotient.cu", "permutation.cu", "transcript.cpp"]
+SOURCES = ["api.cu", "ntt.cu", "merkle.cu", "tables.cu", "prof.cu", "fri.cu", "selftest.cu", "sharded.cu", "quotient.cu", "permutation.cu", "transcript.cpp", "prover.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
 

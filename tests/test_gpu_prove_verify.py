@@ -108,3 +108,67 @@ def test_invalid_witness_does_not_yield_an_accepted_proof():
     with pytest.raises(AssertionError):
         PR.verify_proof(c, digest.tolist(), cs.merkle_tree.cap.hashes.tolist(), inst.public_inputs_hash, _as_dict(proof), 0, pow_bits=8)
     cs.free()
+
+
+@pytest.mark.parametrize("seed,degree_bits,two_groups,kind,with_poseidon,default_cfg", [
+    (21, 5, False, 0, False, True), (22, 6, True, 1, False, False), (23, 8, True, 1, True, False),
+    (24, 10, True, 0, "both", False), (25, 12, True, 1, True, False)])
+def test_native_prove_is_byte_identical_to_the_python_mirror_and_verifies(seed, degree_bits, two_groups, kind, with_poseidon,
+                                                                          default_cfg):
+    """mp2gpu_prove (csrc/prover.cpp: one native call per proof) against prover.py's sequence of ~40 calls, with the
+    Z / partial-product values of the Python side coming from the by-definition restatement: same bytes."""
+    import mapreduce_plonky2_b200 as G
+    from mapreduce_plonky2_b200 import fri as GF
+    from mapreduce_plonky2_b200 import prover as GP
+    from mapreduce_plonky2_b200 import quotient as Q
+    from mapreduce_plonky2_b200 import wire as W
+
+    G.init(0)
+    cfg = GF.FriConfig() if default_cfg else GF.FriConfig(proof_of_work_bits=10, num_query_rounds=6)
+    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, two_groups=two_groups,
+                                 with_poseidon=with_poseidon in (True, "both"), extra_gates=with_poseidon in ("extra", "both"))
+    desc = Q.CircuitDesc.from_circuit(inst.circuit)
+    b_cs = G.PolynomialBatch.from_values(np.array(inst.constants + inst.sigmas, dtype=np.uint64), cfg.rate_bits, False,
+                                         cfg.cap_height, hash_kind=kind, keep_on_device=True, fetch_leaves=False)
+    digest = G.circuit_digest(b_cs.merkle_tree.cap.hashes, degree_bits, kind)
+    wires = np.array(inst.wires, dtype=np.uint64)
+    public_inputs = np.array([5, 6, 7], dtype=np.uint64)
+    data = GP.prove_native(desc, b_cs, digest, wires, public_inputs, inst.public_inputs_hash, cfg, hash_kind=kind)
+    ref = GP.prove(desc, b_cs, digest, wires, inst.public_inputs_hash,
+                   lambda betas, gammas: np.array(PR.zs_partial_products(inst, betas, gammas), dtype=np.uint64), cfg, kind)
+    assert data == W.write_proof_with_public_inputs(W.ProofWithPublicInputs(ref, public_inputs))
+    # the Python mirror with Z / partial products from the device gives the same proof
+    ref2 = GP.prove(desc, b_cs, digest, wires, inst.public_inputs_hash, None, cfg, kind)
+    assert data == W.write_proof_with_public_inputs(W.ProofWithPublicInputs(ref2, public_inputs))
+    # parsed back, the by-definition verifier accepts it; twice the same bytes (determinism pin, mp2-v1/src/api.rs:617-636)
+    back = W.read_proof_with_public_inputs(data)
+    assert np.array_equal(back.public_inputs, public_inputs)
+    PR.verify_proof(inst.circuit, digest.tolist(), b_cs.merkle_tree.cap.hashes.tolist(), inst.public_inputs_hash,
+                    _as_dict(back.proof), kind, pow_bits=cfg.proof_of_work_bits)
+    assert GP.prove_native(desc, b_cs, digest, wires, public_inputs, inst.public_inputs_hash, cfg, hash_kind=kind) == data
+    b_cs.free()
+
+
+def test_native_prove_errors():
+    import mapreduce_plonky2_b200 as G
+    from mapreduce_plonky2_b200 import fri as GF
+    from mapreduce_plonky2_b200 import prover as GP
+    from mapreduce_plonky2_b200 import quotient as Q
+
+    G.init(0)
+    cfg = GF.FriConfig()
+    inst = PR.synthetic_instance(3, degree_bits=5)
+    desc = Q.CircuitDesc.from_circuit(inst.circuit)
+    wires = np.array(inst.wires, dtype=np.uint64)
+    cs_vals = np.array(inst.constants + inst.sigmas, dtype=np.uint64)
+    b_cs = G.PolynomialBatch.from_values(cs_vals, 2, False, 4, hash_kind=1, keep_on_device=True, fetch_leaves=False)
+    with pytest.raises(G.Mp2GpuError, match="another rate"):
+        GP.prove_native(desc, b_cs, [1, 2, 3, 4], wires, [], inst.public_inputs_hash, cfg, hash_kind=1)
+    b_cs.free()
+    b_cs = G.PolynomialBatch.from_values(cs_vals, 3, False, 4, hash_kind=1, keep_on_device=True, fetch_leaves=False)
+    with pytest.raises(G.Mp2GpuError, match="num_wires"):
+        GP.prove_native(desc, b_cs, [1, 2, 3, 4], wires[:-1], [], inst.public_inputs_hash, cfg, hash_kind=1)
+    desc.gates[0].kind = "coset_interpolation"
+    with pytest.raises(G.Mp2GpuError, match="supported subset"):
+        GP.prove_native(desc, b_cs, [1, 2, 3, 4], wires, [], inst.public_inputs_hash, cfg, hash_kind=1)
+    b_cs.free()
