@@ -544,8 +544,9 @@ def measure_map_stage(a, torch, dist, G, world, rank):
                  "ms_per_proof_per_gpu": dt / nproofs * 1e3, "timing": "host wall clock around the threads, max over ranks; median of 3 runs",
                  "runs_proofs_per_s": [world * nproofs / x for x in samples],
                  "includes": T.PROVER_INCLUDES, "gpu_launches": int(launches),
-                 "excluded": "witness generation, the grand-product / partial-product values (host inputs of the second "
-                             "commitment), proof assembly; gates limited to the staged subset; degrees ASSUMED"}
+                 "api": "mp2gpu_prove (one native call per prove(): csrc/prover.cpp), proof bytes = bincode(ProofWithPublicInputs)",
+                 "excluded": "witness generation (host work in the reference); gates limited to the staged subset; "
+                             "degrees ASSUMED; synthetic (not satisfying) witness values -- the work does not depend on them"}
     if rank == 0 and out is not None and world == 1 and not a.no_cpu_baseline:
         # the commitments-only trace on the CPU port, one proof on all host threads (oracle/: the checker, timed as a baseline)
         threads = host_threads()

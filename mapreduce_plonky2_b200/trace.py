@@ -134,15 +134,17 @@ class TraceRunner:
 
 # ------------------------------------------------------------------------------------------------------------------
 # Whole device-side prover replay: every step of plonky2's prove() that this library implements, through the
-# host-buffer API (the calls a patched plonky2 makes), one prover per host thread (per-thread streams; ctypes drops
-# the GIL inside every call).  Still a replay on synthetic data: witness generation and the grand-product / partial
-# product computation that FEEDS the second commitment are host work in the reference and are not counted.
+# host-buffer API (the call a patched plonky2 makes: mp2gpu_prove, one native call per prove(); `native=False` replays
+# the same sequence through the Python mirror and can log per-stage times), one prover per host thread (per-thread
+# streams; ctypes drops the GIL inside every call).  Still a replay on synthetic data: witness generation is host
+# work in the reference and is not counted.
 # ------------------------------------------------------------------------------------------------------------------
-PROVER_INCLUDES = ("per prove(): from_values(135 wires) | challenger | from_values(20 Zs+partial products) | "
+PROVER_INCLUDES = ("per prove() = one mp2gpu_prove call: from_values(135 wires) | challenger | Z / partial products on the "
+                   "device + from_values(20 columns) | "
                    "compute_quotient_polys on the device + from_coeffs(16 chunks) | OpeningSet evaluations at zeta, g*zeta | "
                    "prove_openings: alpha-batched quotient, FRI commit phase, PoW grind (16 bits), 28 query rounds with "
-                   "Merkle paths; pinned host columns in; caps, openings and the FRI proof out (rows, coefficients and digests stay "
-                   "in HBM)")
+                   "Merkle paths | bincode(ProofWithPublicInputs); pinned host wire columns in; proof bytes out (rows, "
+                   "coefficients and digests stay in HBM)")
 NUM_ROUTED_WIRES = 80
 
 
@@ -160,7 +162,8 @@ def trace_circuit_desc(degree_bits: int):
 class ProverTrace:
     """``nthreads`` independent provers on the current device, each replaying whole proofs."""
 
-    def __init__(self, degrees=LEAF_PROOF_DEGREES, hash_kind: int = 1, nthreads: int = 8, seed: int = 0x7ACE):
+    def __init__(self, degrees=LEAF_PROOF_DEGREES, hash_kind: int = 1, nthreads: int = 8, seed: int = 0x7ACE,
+                 native: bool = True):
         import numpy as np
 
         from . import fri as GF
@@ -168,7 +171,8 @@ class ProverTrace:
 
         self.np, self.GF, self.P2 = np, GF, P2
         self.degrees, self.hash_kind, self.nthreads = tuple(degrees), hash_kind, nthreads
-        self.stage_log = None   # set to a list to collect (degree, [(stage, ms), ...]) per prove()
+        self.native = native    # mp2gpu_prove (csrc/prover.cpp) instead of the Python mirror's call sequence
+        self.stage_log = None   # set to a list to collect (degree, [(stage, ms), ...]) per prove() (Python mirror only)
         rng = np.random.default_rng(seed)
         self.circuits = {}
         for d in set(degrees):
@@ -191,6 +195,12 @@ class ProverTrace:
     def prove(self, degree_bits: int, wires, zs_pp):
         np, GF, P2 = self.np, self.GF, self.P2
         from .quotient import compute_quotient_polys
+
+        if self.native and self.stage_log is None:
+            from .prover import prove_native
+
+            desc, cs = self.circuits[degree_bits]
+            return prove_native(desc, cs, [5, 6, 7, 8], wires, [], [1, 2, 3, 4], GF.FriConfig(), hash_kind=self.hash_kind)
 
         import time
 
