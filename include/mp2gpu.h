@@ -322,13 +322,20 @@ const char *mp2gpu_transcript_observe(uint64_t *state12, uint64_t *buffer8, uint
                                          intermediate values from 2+n; (i ? iv_{i-1}^2 : 1)(b base + 1 - b) - iv_i with
                                          b = bit_{n-1-i}; then output - iv_{n-1} */
 #define MP2GPU_GATE_POSEIDON_MDS 12u   /* PoseidonMdsGate: 12 extension inputs at 2i, outputs at 24 + 2i; output - MDS(input) */
+#define MP2GPU_GATE_COSET_INTERPOLATION 13u /* CosetInterpolationGate{subgroup_bits = num_ops, degree = param}, D = 2: shift 0 |
+                                         2^bits extension values from 1 | evaluation_point | evaluation_value (routed up to
+                                         here) | intermediate evals | intermediate prods | shifted_evaluation_point;
+                                         barycentric fold eval' = eval (x - w^k) + value_k prod weight_k, prod' = prod (x - w^k)
+                                         cut after `degree` points, then every degree - 1; constraints (2 each):
+                                         point - shift * shifted_point, per cut (eval wire - eval, prod wire - prod), value - eval */
 typedef struct mp2gpu_gate {
   uint32_t kind;            /* MP2GPU_GATE_* */
   uint32_t num_ops;         /* see the kinds above */
   uint32_t selector_index;  /* SelectorsInfo::selector_indices[gate] */
   uint32_t group_begin;     /* SelectorsInfo::groups[selector_index] = group_begin..group_end (gate indices) */
   uint32_t group_end;
-  uint32_t param;           /* BaseSumGate: the base B; RandomAccessGate: bits | num_extra_constants << 8; 0 otherwise */
+  uint32_t param;           /* BaseSumGate: the base B; RandomAccessGate: bits | num_extra_constants << 8;
+                               CosetInterpolationGate: degree; 0 otherwise */
 } mp2gpu_gate;
 typedef struct mp2gpu_circuit {   /* the CommonCircuitData fields the vanishing polynomial depends on */
   uint32_t degree_bits;

@@ -17,7 +17,7 @@
 // Gate set: the staged subset of mp2-common/src/serialization/circuit_data_serialization.rs:234-266 that
 // oracle/quotient.py restates -- ArithmeticGate, ConstantGate, PublicInputGate, NoopGate, PoseidonGate,
 // ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate,
-// ExponentiationGate, PoseidonMdsGate; anything else is an error.
+// ExponentiationGate, PoseidonMdsGate, CosetInterpolationGate; anything else is an error.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -35,6 +35,7 @@ constexpr u64 kUnusedSelector = 0xFFFFFFFFull;
 
 struct QGate {
   u32 kind, num_ops, selector, group_begin, group_end, param, nc;  // nc = number of constraints of the gate
+  u32 aux;                                                          // CosetInterpolationGate: offset of its tables in gate_tab
 };
 struct QParams {
   u32 n_log, qb, nch, num_wires, R, num_constants, num_selectors, npp, num_gates, gate_term_base, nterms;
@@ -44,6 +45,7 @@ struct QParams {
   size_t cs_stride, wi_stride, zp_stride;
   const u64 *apow;                  // nch x nterms: alpha_c^j
   const u64 *k_is;                  // R coset shifts 7^j
+  const u64 *gate_tab;              // per-gate constant tables (CosetInterpolationGate: 2^bits subgroup points, then weights)
   u64 betas[kMaxChallenges], gammas[kMaxChallenges], pi_hash[4];
   u64 zh[1u << kMaxQuotientBits], zh_inv[1u << kMaxQuotientBits];
   u64 w_nq, n_field;                // w_{N_q};  n as a field element
@@ -165,6 +167,44 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
         a0 = n0;
         a1 = n1;
       }
+    } else if (gate.kind == MP2GPU_GATE_COSET_INTERPOLATION) {
+      // barycentric interpolation at the shifted point, folded point by point in GF(p^2); the running (eval, prod) pair
+      // is pinned to intermediate wires after `deg` points and then every `deg - 1`
+      const u32 bits = gate.num_ops, deg = gate.param, npts = 1u << bits, ni = (npts - 2) / (deg - 1);
+      const u64 *dom = P.gate_tab + gate.aux, *wt = dom + npts;
+      const u32 at_point = 1 + 2 * npts, at_value = at_point + 2, at_inter = at_point + 4, at_shifted = at_inter + 4 * ni;
+      const u64 shift = wi[0], x0 = wi[at_shifted], x1 = wi[at_shifted + 1];
+      cons(0, gl_sub(wi[at_point], gl_mul(x0, shift)));
+      cons(1, gl_sub(wi[at_point + 1], gl_mul(x1, shift)));
+      const u64 x1w = gl_mul(7, x1);
+      u64 e0 = 0, e1 = 0, p0 = 1, p1 = 0;
+      u32 ci = 2, cut = deg, run = 0;
+#pragma unroll 1
+      for (u32 k = 0; k < npts; k++) {
+        if (k == cut) {
+          const u32 ie = at_inter + 2 * run, ip = at_inter + 2 * (ni + run);
+          const u64 w0 = wi[ie], w1 = wi[ie + 1], w2 = wi[ip], w3 = wi[ip + 1];
+          cons(ci, gl_sub(w0, e0));
+          cons(ci + 1, gl_sub(w1, e1));
+          cons(ci + 2, gl_sub(w2, p0));
+          cons(ci + 3, gl_sub(w3, p1));
+          ci += 4;
+          e0 = w0; e1 = w1; p0 = w2; p1 = w3;
+          cut += deg - 1;
+          run++;
+        }
+        const u64 t0 = gl_sub(x0, dom[k]);                      // term = (t0, x1)
+        const u64 v0 = wi[1 + 2 * k], v1 = wi[2 + 2 * k];
+        const u64 q0 = gl_mul(p0, wt[k]), q1 = gl_mul(p1, wt[k]);
+        // eval * term + value * (prod * weight);  prod * term
+        const u64 n0 = gl_add(gl_mul_add(e1, x1w, gl_mul(e0, t0)), gl_mul_add(gl_mul(7, v1), q1, gl_mul(v0, q0)));
+        const u64 n1 = gl_add(gl_mul_add(e0, x1, gl_mul(e1, t0)), gl_mul_add(v0, q1, gl_mul(v1, q0)));
+        const u64 r0 = gl_mul_add(p1, x1w, gl_mul(p0, t0));
+        const u64 r1 = gl_mul_add(p0, x1, gl_mul(p1, t0));
+        e0 = n0; e1 = n1; p0 = r0; p1 = r1;
+      }
+      cons(ci, gl_sub(wi[at_value], e0));
+      cons(ci + 1, gl_sub(wi[at_value + 1], e1));
     } else if (gate.kind == MP2GPU_GATE_EXPONENTIATION) {
       const u32 nb = gate.num_ops;
       const u64 base = wi[0];
@@ -324,6 +364,7 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
   if (bwi->ncols != ci->num_wires) return "quotient_polys: wires batch must hold num_wires columns";
   if (bzp->ncols != (size_t)nch * (1 + npp)) return "quotient_polys: zs_partial_products batch must hold num_challenges * (1 + num_partial_products) columns";
   QParams P = {};
+  std::vector<u64> gate_tab;
   u32 ngc = 0, max_gate_constants = 0;
   for (u32 g = 0; g < ci->num_gates; g++) {
     const mp2gpu_gate &s = ci->gates[g];
@@ -389,6 +430,30 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
         if (s.num_ops == 0) return "quotient_polys: ExponentiationGate without power bits";
         if (2 + 2 * s.num_ops > ci->num_wires) return "quotient_polys: ExponentiationGate exceeds the wires";
         break;
+      case MP2GPU_GATE_COSET_INTERPOLATION: {
+        const u32 bits = s.num_ops, deg = s.param;
+        if (bits == 0 || bits > 6) return "quotient_polys: CosetInterpolationGate subgroup_bits must be 1..6";
+        const u32 npts = 1u << bits;
+        if (deg < 2 || deg > npts) return "quotient_polys: CosetInterpolationGate degree must be 2..2^subgroup_bits";
+        const u32 ni = (npts - 2) / (deg - 1);
+        nc = 4 + 4 * ni;
+        if (5 + 2 * npts + 2 * (2 * ni + 1) > ci->num_wires) return "quotient_polys: CosetInterpolationGate exceeds the wires";
+        d.aux = (u32)gate_tab.size();
+        {  // subgroup points w^k and barycentric weights 1 / prod_{j != k} (w^k - w^j), by definition
+          std::vector<u64> dom(npts);
+          const u64 g = h_root_of_unity(bits);
+          u64 x = 1;
+          for (u32 k = 0; k < npts; k++) { dom[k] = x; x = h_mul(x, g); }
+          gate_tab.insert(gate_tab.end(), dom.begin(), dom.end());
+          for (u32 k = 0; k < npts; k++) {
+            u64 den = 1;
+            for (u32 j = 0; j < npts; j++)
+              if (j != k) den = h_mul(den, dom[k] >= dom[j] ? dom[k] - dom[j] : dom[k] + (kP - dom[j]));  // (a sum with kP first would wrap)
+            gate_tab.push_back(h_inv(den));
+          }
+        }
+        break;
+      }
       case MP2GPU_GATE_POSEIDON_MDS:
         nc = 24;
         if (ci->num_wires < 48) return "quotient_polys: PoseidonMdsGate needs 48 wires";
@@ -398,7 +463,7 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
         if (ci->num_wires < 135) return "quotient_polys: PoseidonGate needs 135 wires";
         break;
       default:
-        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum, reducing, reducing_extension, random_access, exponentiation, poseidon_mds)";
+        return "quotient_polys: gate kind " + std::to_string(s.kind) + " is outside the supported subset (noop, arithmetic, constant, public_input, poseidon, arithmetic_extension, mul_extension, base_sum, reducing, reducing_extension, random_access, exponentiation, poseidon_mds, coset_interpolation)";
     }
     if (nc > kMaxGateConstraints) return "quotient_polys: a gate has more than " + std::to_string(kMaxGateConstraints) + " constraints";
     d.nc = nc;
@@ -438,7 +503,7 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
   }
   P.w_nq = h_root_of_unity(nq_log);
   P.n_field = (u64)n % kP;
-  std::vector<u64> tab((size_t)nch * P.nterms + R);
+  std::vector<u64> tab((size_t)nch * P.nterms + R + gate_tab.size());
   for (u32 c = 0; c < nch; c++) {
     u64 a = 1;
     for (u32 j = 0; j < P.nterms; j++) {
@@ -451,12 +516,14 @@ Status quotient_polys(const mp2gpu_circuit *ci, const mp2gpu_batch *bcs, const m
     tab[(size_t)nch * P.nterms + j] = k;
     k = h_mul(k, kCosetShift);
   }
+  for (size_t j = 0; j < gate_tab.size(); j++) tab[(size_t)nch * P.nterms + R + j] = gate_tab[j];
   DevBuf d_tab, d_q;
   MP2_TRY(d_tab.alloc(tab.size(), st));
   MP2_TRY(d_q.alloc((size_t)nch * Nq, st));
   MP2_CUDA(cudaMemcpyAsync(d_tab.p, tab.data(), tab.size() * sizeof(u64), cudaMemcpyHostToDevice, st));
   P.apow = d_tab.p;
   P.k_is = d_tab.p + (size_t)nch * P.nterms;
+  P.gate_tab = P.k_is + R;
   {
     ProfScope _p("k_quotient_points", st);
     if (colmajor) k_quotient_points<true><<<(unsigned)((Nq + 127) / 128), 128, 0, st>>>(P, d_q.p);

@@ -7,7 +7,7 @@ The descriptor mirrors the ``CommonCircuitData`` fields the vanishing polynomial
 order, ``SelectorsInfo { selector_indices, groups }``, ``num_constants`` (selectors + gate constants), the wire counts
 and ``quotient_degree_factor``.  Gate kinds outside the staged subset (ArithmeticGate, ConstantGate, PublicInputGate,
 NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate,
-ReducingExtensionGate, RandomAccessGate, ExponentiationGate, PoseidonMdsGate of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
+ReducingExtensionGate, RandomAccessGate, ExponentiationGate, PoseidonMdsGate, CosetInterpolationGate of mp2-common/src/serialization/circuit_data_serialization.rs:234-266) raise, they are never skipped.
 """
 from __future__ import annotations
 
@@ -23,7 +23,7 @@ from .plonky2 import POSEIDON2, MerkleCap, MerkleTree, PolynomialBatch, _arr, _c
 
 GATE_KINDS = {"noop": 0, "arithmetic": 1, "constant": 2, "public_input": 3, "poseidon": 4, "arithmetic_extension": 5,
               "mul_extension": 6, "base_sum": 7, "reducing": 8, "reducing_extension": 9, "random_access": 10,
-              "exponentiation": 11, "poseidon_mds": 12}
+              "exponentiation": 11, "poseidon_mds": 12, "coset_interpolation": 13}
 
 
 class _CGate(C.Structure):

@@ -141,22 +141,50 @@ class TraceRunner:
 # ------------------------------------------------------------------------------------------------------------------
 PROVER_INCLUDES = ("per prove() = one mp2gpu_prove call: from_values(135 wires) | challenger | Z / partial products on the "
                    "device + from_values(20 columns) | "
-                   "compute_quotient_polys on the device + from_coeffs(16 chunks) | OpeningSet evaluations at zeta, g*zeta | "
+                   "compute_quotient_polys on the device over the 14-kind recursion gate set (trace_circuit_desc) + from_coeffs(16 chunks) | "
+                   "OpeningSet evaluations at zeta, g*zeta | "
                    "prove_openings: alpha-batched quotient, FRI commit phase, PoW grind (16 bits), 28 query rounds with "
                    "Merkle paths | bincode(ProofWithPublicInputs); pinned host wire columns in; proof bytes out (rows, "
                    "coefficients and digests stay in HBM)")
 NUM_ROUTED_WIRES = 80
 
 
-def trace_circuit_desc(degree_bits: int):
+def trace_circuit_desc(degree_bits: int, recursion_gate_set: bool = True):
     """A circuit descriptor of the standard_recursion_config shape (135 wires, 80 routed, 2 challenges, quotient
-    degree factor 8) over the staged gate subset incl. PoseidonGate (the gate recursion circuits are made of); gives
-    4 + 80 constants/sigma columns and 2 * (1 + 9) Z columns."""
+    degree factor 8).  With ``recursion_gate_set`` (default) it carries the 14 gate kinds a recursive verifier circuit
+    is built from, at that config's sizes (ArithmeticGate 20 ops, ArithmeticExtension 10, MulExtension 13, BaseSum<2> 63
+    limbs, Reducing 43, ReducingExtension 32, RandomAccess 4 bits x 4 copies + 2 constants, Exponentiation 66 bits,
+    CosetInterpolation 16 points degree 6, Poseidon, PoseidonMds, Constant, PublicInput, Noop) in five selector groups
+    whose filtered degrees stay <= 9; otherwise the five-gate subset round 2 started with.  Every gate's constraints are
+    evaluated at every point of the quotient coset, so the set decides the quotient kernel's cost."""
     from .quotient import CircuitDesc, GateDesc
 
-    return CircuitDesc(degree_bits, NUM_WIRES, NUM_ROUTED_WIRES, 4,
-                       [GateDesc("arithmetic", NUM_ROUTED_WIRES // 4), GateDesc("constant", 2), GateDesc("noop"),
-                        GateDesc("public_input"), GateDesc("poseidon")], [0, 0, 0, 0, 1], [(0, 4), (4, 5)], 3, 2)
+    if not recursion_gate_set:
+        return CircuitDesc(degree_bits, NUM_WIRES, NUM_ROUTED_WIRES, 4,
+                           [GateDesc("arithmetic", NUM_ROUTED_WIRES // 4), GateDesc("constant", 2), GateDesc("noop"),
+                            GateDesc("public_input"), GateDesc("poseidon")], [0, 0, 0, 0, 1], [(0, 4), (4, 5)], 3, 2)
+    gates = [GateDesc("noop"), GateDesc("constant", 2), GateDesc("public_input"), GateDesc("poseidon_mds"),
+             GateDesc("base_sum", 63, 2),
+             GateDesc("arithmetic", 20), GateDesc("arithmetic_extension", 10), GateDesc("mul_extension", 13),
+             GateDesc("reducing", 43), GateDesc("reducing_extension", 32),
+             GateDesc("random_access", 4, 4 | (2 << 8)), GateDesc("exponentiation", 66),
+             GateDesc("coset_interpolation", 4, 6),
+             GateDesc("poseidon")]
+    groups = [(0, 5), (5, 10), (10, 12), (12, 13), (13, 14)]
+    selector_indices = [s for s, (a, b) in enumerate(groups) for _ in range(a, b)]
+    return CircuitDesc(degree_bits, NUM_WIRES, NUM_ROUTED_WIRES, len(groups) + 2, gates, selector_indices, groups, 3, 2)
+
+
+def trace_selector_columns(desc, n: int, rng):
+    """One gate index per row, written into the selector column of its group (UNUSED_SELECTOR = 2^32 - 1 elsewhere)."""
+    import numpy as np
+
+    row_gate = rng.integers(0, len(desc.gates), n)
+    cols = np.full((len(desc.groups), n), (1 << 32) - 1, dtype=np.uint64)
+    for s, (a, b) in enumerate(desc.groups):
+        m = (row_gate >= a) & (row_gate < b)
+        cols[s, m] = row_gate[m].astype(np.uint64)
+    return cols
 
 
 class ProverTrace:
@@ -179,7 +207,7 @@ class ProverTrace:
             n = 1 << d
             desc = trace_circuit_desc(d)
             cs = rng.integers(0, 1 << 62, (desc.num_constants + NUM_ROUTED_WIRES, n), dtype=np.uint64)
-            cs[0] = rng.integers(0, 4, n, dtype=np.uint64)  # selector column: a gate index per row
+            cs[:desc.num_selectors] = trace_selector_columns(desc, n, rng)
             batch = P2.PolynomialBatch.from_values(cs, RATE_BITS, False, CAP_HEIGHT, hash_kind=hash_kind, keep_on_device=True,
                                                    fetch_leaves=False)
             self.circuits[d] = (desc, batch)

@@ -11,7 +11,7 @@ then `coset_ifft` turns each q_c into coefficients and cuts it into `quotient_de
 committed with `from_coeffs`.  Gate set restated here (the staged subset of
 mp2-common/src/serialization/circuit_data_serialization.rs:234-266): ArithmeticGate, ConstantGate, PublicInputGate,
 NoopGate, PoseidonGate, ArithmeticExtensionGate, MulExtensionGate, BaseSumGate<B>, ReducingGate, ReducingExtensionGate, RandomAccessGate,
-ExponentiationGate, PoseidonMdsGate behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
+ExponentiationGate, PoseidonMdsGate, CosetInterpolationGate behind plonky2's selector filters; no lookups, no blinding (the reference never enables zero_knowledge).
 
 Pinned by definition, not by the Rust prover (absent): tests/plonk_ref.py restates the VERIFIER's
 `eval_vanishing_poly` + final identity, and the quotients computed here must pass it at random points
@@ -62,6 +62,45 @@ def _poseidon_gate(w):
               for row in range(12)]
     out.extend((st[i] - w[12 + i]) % P for i in range(12))
     return out
+
+
+_CI_TABLES = {}
+
+
+def _coset_interpolation_gate(w, bits, degree):
+    """CosetInterpolationGate::eval_unfiltered_base_one (plonky2 gates/coset_interpolation.rs), D = 2: barycentric
+    interpolation of the 2^bits extension values (wires 1 + 2k) at shifted_evaluation_point, folded point by point --
+    eval <- eval (x - w^k) + value_k prod weight_k, prod <- prod (x - w^k) -- and cut after `degree` points, then every
+    `degree - 1`, where the running (eval, prod) pair is pinned to intermediate wires.  The barycentric weight of the
+    point w^k of the order-m subgroup is 1 / prod_{j != k} (w^k - w^j) = w^k / m (the derivative of X^m - 1)."""
+    m = 1 << bits
+    if bits not in _CI_TABLES:
+        g = O.root_of_unity(bits)
+        dom = [pow(g, k, P) for k in range(m)]
+        m_inv = pow(m, P - 2, P)
+        _CI_TABLES[bits] = (dom, [x * m_inv % P for x in dom])
+    dom, wts = _CI_TABLES[bits]
+    ni = (m - 2) // (degree - 1)
+    at_point, at_value, at_inter = 1 + 2 * m, 3 + 2 * m, 5 + 2 * m
+    at_shifted = at_inter + 4 * ni
+    x0, x1 = w[at_shifted], w[at_shifted + 1]
+    cons = [(w[at_point] - x0 * w[0]) % P, (w[at_point + 1] - x1 * w[0]) % P]
+    e0, e1, p0, p1 = 0, 0, 1, 0
+    cut = degree                      # index of the first point of the next run
+    for k in range(m):
+        if k == cut:                  # pin the running pair to the next intermediate wires and continue from them
+            i = (k - degree) // (degree - 1)
+            ie, ip = at_inter + 2 * i, at_inter + 2 * (ni + i)
+            cons += [(w[ie] - e0) % P, (w[ie + 1] - e1) % P, (w[ip] - p0) % P, (w[ip + 1] - p1) % P]
+            e0, e1, p0, p1 = w[ie], w[ie + 1], w[ip], w[ip + 1]
+            cut += degree - 1
+        t0 = (x0 - dom[k]) % P        # term = x - w^k  (its second component is x1)
+        v0, v1 = w[1 + 2 * k], w[2 + 2 * k]
+        q0, q1 = p0 * wts[k] % P, p1 * wts[k] % P
+        e0, e1 = ((e0 * t0 + 7 * e1 * x1) + (v0 * q0 + 7 * v1 * q1)) % P, ((e0 * x1 + e1 * t0) + (v0 * q1 + v1 * q0)) % P
+        p0, p1 = (p0 * t0 + 7 * p1 * x1) % P, (p0 * x1 + p1 * t0) % P
+    cons += [(w[at_value] - e0) % P, (w[at_value + 1] - e1) % P]
+    return cons
 
 
 def _gate_constraints(desc, local_constants, local_wires, pi_hash):
@@ -142,6 +181,8 @@ def _gate_constraints(desc, local_constants, local_wires, pi_hash):
                     items = [(items[2 * k] + b * (items[2 * k + 1] - items[2 * k])) % P for k in range(len(items) // 2)]
                 cons.append((items[0] - w[b0 + 1]) % P)
             cons += [(gc[i] - w[(2 + vec) * copies + i]) % P for i in range(nx)]
+        elif gate.kind == "coset_interpolation":    # gates/coset_interpolation.rs: subgroup_bits = num_ops, degree = param
+            cons = _coset_interpolation_gate(local_wires, gate.num_ops, gate.param)
         elif gate.kind == "base_sum":               # gates/base_sum.rs BaseSumGate<B>{num_limbs}: B = gate.param
             limbs = local_wires[1:1 + gate.num_ops]
             total = sum(l * pow(gate.param, i, P) for i, l in enumerate(limbs)) % P

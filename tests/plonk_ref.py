@@ -227,6 +227,69 @@ def poseidon_mds_constraints(w):
     return [cons[comp][r] for r in range(12) for comp in range(2)]
 
 
+# ---- CosetInterpolationGate{subgroup_bits, degree} (plonky2 gates/coset_interpolation.rs), D = 2 --------------------------
+#   Interpolates the 2^subgroup_bits extension values given on the coset shift * <w> at an extension point, by the
+#   barycentric formula split into runs of `degree` (first) and `degree - 1` (later) points so that no constraint exceeds
+#   `degree`.  Wires: shift 0 | values 1 + 2i | evaluation_point | evaluation_value | (routed up to here) intermediate
+#   evals (2 each) | intermediate prods | shifted_evaluation_point.  Constraints (2 each): evaluation_point - shift *
+#   shifted_point; per intermediate i: its eval wire - computed eval, its prod wire - computed prod; evaluation_value -
+#   computed eval.  One fold step: eval' = eval * (x - x_k) + value_k * prod * weight_k, prod' = prod * (x - x_k);
+#   weight_k = 1 / prod_{j != k} (x_k - x_j) over the subgroup points x_k = w^k (field/interpolation.rs barycentric_weights).
+def coset_interpolation_degree(subgroup_bits: int, max_degree: int) -> int:
+    """CosetInterpolationGate::with_max_degree's choice of `degree`."""
+    n_points = 1 << subgroup_bits
+    n_intermediates = (n_points - 2) // (max_degree - 1)
+    return (n_points - 2) // (n_intermediates + 1) + 2
+
+
+def coset_interpolation_layout(bits: int, degree: int):
+    """-> (num_points, num_intermediates, start_evaluation_point, start_evaluation_value, start_intermediates = routed
+    wires, start of the shifted evaluation point, total wires)."""
+    npts = 1 << bits
+    ni = (npts - 2) // (degree - 1)
+    start_ep = 1 + 2 * npts
+    start_int = start_ep + 4
+    return npts, ni, start_ep, start_ep + 2, start_int, start_int + 4 * ni, start_int + 2 * (2 * ni + 1)
+
+
+def barycentric_weights(points: List[int]) -> List[int]:
+    out = []
+    for i, xi in enumerate(points):
+        d = 1
+        for j, xj in enumerate(points):
+            if j != i:
+                d = d * (xi - xj) % P
+        out.append(pow(d, P - 2, P))
+    return out
+
+
+def _ci_fold(values, dom, wts, a, b, point, ev, pr):
+    for k in range(a, b):
+        term = ((point[0] - dom[k]) % P, point[1])
+        ev = _ext_add(ext_mul(ev, term), ext_mul(values[k], ((pr[0] * wts[k]) % P, (pr[1] * wts[k]) % P)))
+        pr = ext_mul(pr, term)
+    return ev, pr
+
+
+def coset_interpolation_constraints(w, bits, degree):
+    npts, ni, start_ep, start_ev, start_int, start_sep, _ = coset_interpolation_layout(bits, degree)
+    dom = subgroup(bits)
+    wts = barycentric_weights(dom)
+    shift = w[0]
+    values = [(w[1 + 2 * i], w[2 + 2 * i]) for i in range(npts)]
+    ep, sep = (w[start_ep], w[start_ep + 1]), (w[start_sep], w[start_sep + 1])
+    cons = [(ep[0] - sep[0] * shift) % P, (ep[1] - sep[1] * shift) % P]
+    ev, pr = _ci_fold(values, dom, wts, 0, degree, sep, (0, 0), (1, 0))
+    for i in range(ni):
+        ie = (w[start_int + 2 * i], w[start_int + 2 * i + 1])
+        ip = (w[start_int + 2 * (ni + i)], w[start_int + 2 * (ni + i) + 1])
+        cons += [(ie[0] - ev[0]) % P, (ie[1] - ev[1]) % P, (ip[0] - pr[0]) % P, (ip[1] - pr[1]) % P]
+        a = 1 + (degree - 1) * (i + 1)
+        ev, pr = _ci_fold(values, dom, wts, a, min(a + degree - 1, npts), sep, ie, ip)
+    cons += [(w[start_ev] - ev[0]) % P, (w[start_ev + 1] - ev[1]) % P]
+    return cons
+
+
 @dataclass
 class Gate:
     kind: str           # "arithmetic" | "constant" | "public_input" | "noop" | "poseidon" | "arithmetic_extension" |
@@ -242,13 +305,14 @@ class Gate:
                 "mul_extension": 2 * self.num_ops, "base_sum": 1 + self.num_ops, "reducing": 2 * self.num_ops,
                 "reducing_extension": 2 * self.num_ops,
                 "random_access": self.num_ops * ((self.param & 0xFF) + 2) + (self.param >> 8),
-                "exponentiation": self.num_ops + 1, "poseidon_mds": 24}[self.kind]
+                "exponentiation": self.num_ops + 1, "poseidon_mds": 24,
+                "coset_interpolation": 4 + 4 * (((1 << self.num_ops) - 2) // max(self.param - 1, 1))}[self.kind]
 
     @property
     def num_constants(self) -> int:
         return {"arithmetic": 2, "constant": self.num_ops, "public_input": 0, "noop": 0, "poseidon": 0,
                 "arithmetic_extension": 2, "mul_extension": 1, "base_sum": 0, "reducing": 0, "reducing_extension": 0,
-                "random_access": self.param >> 8, "exponentiation": 0, "poseidon_mds": 0}[self.kind]
+                "random_access": self.param >> 8, "exponentiation": 0, "poseidon_mds": 0, "coset_interpolation": 0}[self.kind]
 
 
 @dataclass
@@ -357,6 +421,16 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
                 selector_indices += [len(groups)] * 2
                 groups.append((b3, b3 + 2))
                 extra += [b3, b3 + 1]
+                # a sixth group: CosetInterpolationGate alone (filtered degree (0 + 1) + degree <= 9); 8 points in runs of
+                # 4 + 3 + 1 (two intermediates) fit 24 routed wires; with >= 37 routed wires also the shape the recursive
+                # FRI verifier uses under standard_recursion_config: 16 points, degree 6 (runs of 6 + 5 + 5)
+                b4 = len(gates)
+                gates.append(Gate("coset_interpolation", 3, 4))
+                if num_routed_wires >= 37:
+                    gates.append(Gate("coset_interpolation", 4, coset_interpolation_degree(4, 8)))
+                selector_indices += [len(groups)] * (len(gates) - b4)
+                groups.append((b4, len(gates)))
+                extra += list(range(b4, len(gates)))
     c = Circuit(degree_bits, num_wires, num_routed_wires, gates, selector_indices, groups)
     pi_hash = [rng.randrange(P) for _ in range(4)]
     row_gate = [3] + [rng.choice([0, 0, 0, 1, 2] + ([4, 4] if with_poseidon else []) + extra) for _ in range(n - 1)]     # row 0: the public-input gate
@@ -440,6 +514,25 @@ def synthetic_instance(seed: int, degree_bits: int = 4, num_wires: int = 11, num
                 wires[2 + nb + i][row] = acc
             wires[1 + nb][row] = acc
             outputs.append((1 + nb, row))
+        elif gates[g].kind == "coset_interpolation":
+            bits, deg = gates[g].num_ops, gates[g].param
+            npts, ni, start_ep, start_ev, start_int, start_sep, _ = coset_interpolation_layout(bits, deg)
+            dom = subgroup(bits)
+            wts = barycentric_weights(dom)
+            shift = wires[0][row] or 1
+            wires[0][row] = shift
+            sinv = pow(shift, P - 2, P)
+            sep = (wires[start_ep][row] * sinv % P, wires[start_ep + 1][row] * sinv % P)
+            wires[start_sep][row], wires[start_sep + 1][row] = sep
+            values = [(wires[1 + 2 * i][row], wires[2 + 2 * i][row]) for i in range(npts)]
+            ev, pr = _ci_fold(values, dom, wts, 0, deg, sep, (0, 0), (1, 0))
+            for i in range(ni):
+                wires[start_int + 2 * i][row], wires[start_int + 2 * i + 1][row] = ev
+                wires[start_int + 2 * (ni + i)][row], wires[start_int + 2 * (ni + i) + 1][row] = pr
+                a = 1 + (deg - 1) * (i + 1)
+                ev, pr = _ci_fold(values, dom, wts, a, min(a + deg - 1, npts), sep, ev, pr)
+            wires[start_ev][row], wires[start_ev + 1][row] = ev
+            outputs += [(start_ev, row), (start_ev + 1, row)]
         elif gates[g].kind == "poseidon_mds":
             for comp in range(2):
                 res = _pos_mds([wires[2 * i + comp][row] for i in range(12)])
@@ -564,6 +657,8 @@ def gate_constraints(c: Circuit, local_constants: List[int], local_wires: List[i
             cons = exponentiation_constraints(local_wires, gate.num_ops)
         elif gate.kind == "poseidon_mds":
             cons = poseidon_mds_constraints(local_wires)
+        elif gate.kind == "coset_interpolation":
+            cons = coset_interpolation_constraints(local_wires, gate.num_ops, gate.param)
         else:
             cons = []
         for i, v in enumerate(cons):

@@ -168,7 +168,7 @@ def test_native_prove_errors():
     b_cs = G.PolynomialBatch.from_values(cs_vals, 3, False, 4, hash_kind=1, keep_on_device=True, fetch_leaves=False)
     with pytest.raises(G.Mp2GpuError, match="num_wires"):
         GP.prove_native(desc, b_cs, [1, 2, 3, 4], wires[:-1], [], inst.public_inputs_hash, cfg, hash_kind=1)
-    desc.gates[0].kind = "coset_interpolation"
+    desc.gates[0].kind = "lookup_table"
     with pytest.raises(G.Mp2GpuError, match="supported subset"):
         GP.prove_native(desc, b_cs, [1, 2, 3, 4], wires, [], inst.public_inputs_hash, cfg, hash_kind=1)
     b_cs.free()

@@ -102,9 +102,15 @@ def test_unsupported_gate_and_shape_errors(oracle):
     zs_pp = PR.zs_partial_products(inst, betas, gammas)
     b_cs, b_w, b_z = _commit3(G, inst, zs_pp, 3, 2, 0)
     desc = Q.CircuitDesc.from_circuit(c)
-    desc.gates[2] = Q.GateDesc("coset_interpolation")
+    desc.gates[2] = Q.GateDesc("lookup")
     with pytest.raises(G.Mp2GpuError, match="outside the supported subset"):
         Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, 3, 2, hash_kind=0)
+    for bad, msg in ((Q.GateDesc("coset_interpolation", 7, 4), "subgroup_bits must be"), (Q.GateDesc("coset_interpolation", 2, 1), "degree must be"),
+                     (Q.GateDesc("coset_interpolation", 4, 6), "exceeds the wires")):
+        desc = Q.CircuitDesc.from_circuit(c)
+        desc.gates[2] = bad
+        with pytest.raises(G.Mp2GpuError, match=msg):
+            Q.compute_quotient_polys(desc, b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash, 3, 2, hash_kind=0)
     desc = Q.CircuitDesc.from_circuit(c)
     with pytest.raises(G.Mp2GpuError, match="wires batch must hold"):
         Q.compute_quotient_polys(desc, b_cs, b_z, b_z, betas, gammas, alphas, inst.public_inputs_hash, 3, 2, hash_kind=0)
@@ -139,5 +145,39 @@ def test_quotient_other_shapes(oracle, nch, routed, qbits, degree_bits):
     if qbits == 3:
         zeta = rng.randrange(2, P)
         assert PR.check_quotient_identity(inst, zs_pp, [list(map(int, ch)) for ch in qb.polynomials], betas, gammas, alphas, zeta)
+    for b in (b_cs, b_w, b_z, qb):
+        b.free()
+
+
+@pytest.mark.parametrize("seed,degree_bits,kind", [(31, 5, 1), (32, 7, 0)])
+def test_recursion_gate_set_with_both_coset_interpolation_shapes(oracle, seed, degree_bits, kind):
+    """standard_recursion_config's shape (135 wires, 80 routed) with every supported gate kind, including the
+    CosetInterpolationGate the recursive FRI verifier uses (16 points, degree 6: runs of 6 + 5 + 5) next to an 8-point one."""
+    import mapreduce_plonky2_b200 as G
+    from mapreduce_plonky2_b200 import quotient as Q
+    from oracle import quotient as OQ
+
+    G.init(0)
+    rng = random.Random(0xC0 + seed)
+    inst = PR.synthetic_instance(seed, degree_bits=degree_bits, num_wires=135, num_routed_wires=80, two_groups=True,
+                                 with_poseidon=True, extra_gates=True)
+    c = inst.circuit
+    kinds = [(g.kind, g.num_ops, g.param) for g in c.gates]
+    assert ("coset_interpolation", 4, 6) in kinds and ("coset_interpolation", 3, 4) in kinds
+    used = {c.gates[g].kind for g in inst.row_gate}
+    betas, gammas, alphas = ([rng.randrange(P) for _ in range(c.num_challenges)] for _ in range(3))
+    zs_pp = PR.zs_partial_products(inst, betas, gammas)
+    b_cs, b_w, b_z = _commit3(G, inst, zs_pp, 3, 4, kind)
+    qb = Q.compute_quotient_polys(Q.CircuitDesc.from_circuit(c), b_cs, b_w, b_z, betas, gammas, alphas, inst.public_inputs_hash,
+                                  3, 4, hash_kind=kind)
+    chunks = qb.polynomials
+    if degree_bits <= 5:
+        want = OQ.compute_quotient_polys(c, _coeffs(inst.constants + inst.sigmas), _coeffs(inst.wires), _coeffs(zs_pp), betas,
+                                         gammas, alphas, inst.public_inputs_hash)
+        assert np.array_equal(chunks, want)
+    for _ in range(2):
+        assert PR.check_quotient_identity(inst, zs_pp, [list(map(int, ch)) for ch in chunks], betas, gammas, alphas,
+                                          rng.randrange(2, P))
+    assert "coset_interpolation" in used, "the seed must place the gate on some row"
     for b in (b_cs, b_w, b_z, qb):
         b.free()

@@ -71,3 +71,61 @@ def test_violated_gate_makes_the_vanishing_polynomial_indivisible(oracle):
                                        betas, gammas, alphas, inst.public_inputs_hash)
     assert not PR.check_quotient_identity(inst, zs_pp, [list(map(int, ch)) for ch in chunks], betas, gammas, alphas,
                                           rng.randrange(2, P))
+
+
+def test_coset_interpolation_gate_interpolates_and_both_restatements_agree(oracle):
+    """CosetInterpolationGate (plonky2 gates/coset_interpolation.rs): the generated witness satisfies the constraints, its
+    evaluation_value IS the Lagrange interpolant of the values on shift * <w> at evaluation_point (by definition, in
+    GF(p^2)), tampering breaks a constraint, and the oracle's restatement (closed-form weights w^k / m, one loop with
+    cuts) agrees with the by-definition one (product weights, run by run) on random wires for several shapes."""
+    rng = random.Random(0xC1)
+    assert PR.coset_interpolation_degree(4, 8) == 6 and PR.coset_interpolation_degree(2, 8) == 4
+    assert PR.coset_interpolation_layout(4, 6)[4:] == (37, 45, 47)      # routed wires, shifted point, total wires
+    for bits, deg in [(2, 4), (3, 4), (3, 8), (4, 6), (4, 3), (5, 8), (1, 2)]:
+        total = PR.coset_interpolation_layout(bits, deg)[-1]
+        for _ in range(2):
+            w = [rng.randrange(P) for _ in range(total)]
+            a = PR.coset_interpolation_constraints(w, bits, deg)
+            assert a == OQ._coset_interpolation_gate(w, bits, deg)
+            assert len(a) == PR.Gate("coset_interpolation", bits, deg).num_constraints
+    inst = PR.synthetic_instance(31, degree_bits=5, num_wires=135, num_routed_wires=80, two_groups=True, with_poseidon=True,
+                                 extra_gates=True)
+    c = inst.circuit
+    rows = [r for r, g in enumerate(inst.row_gate) if c.gates[g].kind == "coset_interpolation"]
+    assert {c.gates[inst.row_gate[r]].num_ops for r in rows} == {3, 4}
+    E = PR.Ext
+    for r in rows:
+        g = c.gates[inst.row_gate[r]]
+        w = [inst.wires[j][r] for j in range(c.num_wires)]
+        assert PR.coset_interpolation_constraints(w, g.num_ops, g.param) == [0] * g.num_constraints
+        npts, _, at_point, at_value, *_ = PR.coset_interpolation_layout(g.num_ops, g.param)
+        dom, shift = PR.subgroup(g.num_ops), w[0]
+        x = E(w[at_point], w[at_point + 1])
+        total = E(0)
+        for i in range(npts):
+            num, den = E(1), 1
+            for j in range(npts):
+                if j != i:
+                    num = num * (x - shift * dom[j] % P)
+                    den = den * ((shift * dom[i] - shift * dom[j]) % P) % P
+            total = total + E(w[1 + 2 * i], w[2 + 2 * i]) * num * pow(den, P - 2, P)
+        assert total == E(w[at_value], w[at_value + 1])
+        bad = list(w)
+        bad[5] = (bad[5] + 1) % P
+        assert any(PR.coset_interpolation_constraints(bad, g.num_ops, g.param))
+
+
+def test_quotient_with_the_recursion_gate_set_passes_the_verifier_identity(oracle):
+    """135 wires / 80 routed (standard_recursion_config) with all 14 supported gate kinds incl. both CosetInterpolationGate
+    shapes: the oracle's quotient passes the verifier's identity."""
+    rng = random.Random(0xC2)
+    inst = PR.synthetic_instance(31, degree_bits=5, num_wires=135, num_routed_wires=80, two_groups=True, with_poseidon=True,
+                                 extra_gates=True)
+    c = inst.circuit
+    betas, gammas, alphas = ([rng.randrange(P) for _ in range(c.num_challenges)] for _ in range(3))
+    zs_pp = PR.zs_partial_products(inst, betas, gammas)
+    chunks = OQ.compute_quotient_polys(c, _coeffs(inst.constants + inst.sigmas), _coeffs(inst.wires), _coeffs(zs_pp),
+                                       betas, gammas, alphas, inst.public_inputs_hash)
+    for _ in range(2):
+        assert PR.check_quotient_identity(inst, zs_pp, [list(map(int, ch)) for ch in chunks], betas, gammas, alphas,
+                                          rng.randrange(2, P))
