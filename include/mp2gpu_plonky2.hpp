@@ -18,6 +18,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mp2gpu.h"
@@ -341,6 +342,64 @@ FriCommitPhase<H> prove_openings_begin(const FriInstanceInfo &instance, const st
                                   ph.final_poly.empty() ? nullptr : ph.final_poly[0].data(), &f));
   ph.state.reset(f, mp2gpu_fri_free);
   return ph;
+}
+
+// The CommonCircuitData fields the device-side prover needs (mp2gpu_circuit with owned storage)
+struct GateInfo {
+  uint32_t kind = MP2GPU_GATE_NOOP, num_ops = 0, param = 0;   // see the MP2GPU_GATE_* notes in mp2gpu.h
+};
+struct CircuitDesc {
+  size_t degree_bits = 0, num_wires = 135, num_routed_wires = 80, num_constants = 0;
+  size_t quotient_degree_bits = 3, num_challenges = 2;
+  std::vector<GateInfo> gates;                       // CommonCircuitData::gates order
+  std::vector<size_t> selector_indices;              // SelectorsInfo::selector_indices
+  std::vector<std::pair<size_t, size_t>> groups;     // SelectorsInfo::groups (gate index ranges)
+
+  // fills `storage` and returns a descriptor pointing into it (valid while `storage` lives)
+  mp2gpu_circuit c_desc(std::vector<mp2gpu_gate> &storage) const {
+    if (selector_indices.size() != gates.size()) throw Panic("CircuitDesc: one selector index per gate");
+    storage.resize(gates.size());
+    for (size_t g = 0; g < gates.size(); g++) {
+      if (selector_indices[g] >= groups.size()) throw Panic("CircuitDesc: selector index out of range");
+      const auto &grp = groups[selector_indices[g]];
+      storage[g] = mp2gpu_gate{gates[g].kind, gates[g].num_ops, (uint32_t)selector_indices[g], (uint32_t)grp.first,
+                               (uint32_t)grp.second, gates[g].param};
+    }
+    return mp2gpu_circuit{(uint32_t)degree_bits, (uint32_t)quotient_degree_bits, (uint32_t)num_challenges, (uint32_t)num_wires,
+                          (uint32_t)num_routed_wires, (uint32_t)num_constants, (uint32_t)groups.size(),
+                          (uint32_t)gates.size(), storage.data()};
+  }
+};
+
+// plonky2 `prove_with_partition_witness` after witness generation, as one call on the device (mp2gpu_prove):
+// -> bincode(ProofWithPublicInputs) bytes (mp2-common/src/proof.rs:86-90 `serialize_proof`).  `constants_sigmas` is the
+// device-resident batch committed at circuit-build time; `wires` are the num_wires witness columns.
+template <Hasher H>
+std::vector<uint8_t> prove(const CircuitDesc &circuit, const PolynomialBatch<H> &constants_sigmas,
+                           const std::array<F, 4> &circuit_digest, const std::vector<PolynomialValues> &wires,
+                           const std::vector<F> &public_inputs, const std::array<F, 4> &public_inputs_hash,
+                           const FriConfig &config = FriConfig()) {
+  if (!constants_sigmas.device) throw Panic("prove needs a device-resident constants_sigmas batch (keep_on_device)");
+  if (wires.size() != circuit.num_wires) throw Panic("prove: one column per wire");
+  for (auto &w : wires)
+    if (w.values.size() != (size_t(1) << circuit.degree_bits)) throw Panic("prove: wire columns must have 2^degree_bits values");
+  std::vector<mp2gpu_gate> storage;
+  const mp2gpu_circuit cd = circuit.c_desc(storage);
+  std::vector<uint32_t> arity;
+  for (size_t a : config.reduction_arity_bits(circuit.degree_bits)) arity.push_back((uint32_t)a);
+  const mp2gpu_prove_config cf{(uint32_t)config.rate_bits, (uint32_t)config.cap_height, (uint32_t)H,
+                               (uint32_t)config.proof_of_work_bits, (uint32_t)config.num_query_rounds,
+                               (uint32_t)arity.size(), arity.data()};
+  std::vector<const uint64_t *> cols(wires.size());
+  for (size_t c = 0; c < wires.size(); c++) cols[c] = wires[c].values.data();
+  uint8_t *bytes = nullptr;
+  size_t len = 0;
+  check(mp2gpu_prove(&cd, &cf, constants_sigmas.device.get(), circuit_digest.data(), cols.data(),
+                     public_inputs.empty() ? nullptr : public_inputs.data(), public_inputs.size(), public_inputs_hash.data(),
+                     &bytes, &len));
+  std::vector<uint8_t> out(bytes, bytes + len);
+  mp2gpu_free_bytes(bytes);
+  return out;
 }
 
 }  // namespace mp2gpu

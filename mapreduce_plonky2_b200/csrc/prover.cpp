@@ -116,6 +116,7 @@ Status prove(const mp2gpu_circuit *ci, const mp2gpu_prove_config *cf, const mp2g
   if (red > n_log) return "prove: FRI reductions exceed the degree";
   const size_t ncap = (size_t)1 << cap_height;
   const u32 md = 1u << ci->quotient_degree_bits, npp = (R + md - 1) / md - 1;
+  DeviceScope scope(bcs->device);  // the whole proof runs where the circuit's constants/sigmas batch lives
   Handles h;
   std::vector<uint64_t> cap_w(ncap * 4), cap_z(ncap * 4), cap_q(ncap * 4);
 

@@ -119,6 +119,60 @@ static int run(uint32_t kind) {
   return 0;
 }
 
+// prove(): one native call from the C++ mirror.  Synthetic (not satisfying) wires: the call does not check the witness;
+// what is pinned here is the plumbing -- descriptor, config, byte buffer ownership, determinism -- the proof CONTENT is
+// pinned from Python (tests/test_gpu_prove_verify.py: byte-identical to the mirror's sequence, accepted by a verifier).
+template <Hasher H>
+static int run_prove() {
+  uint64_t seed = 4242;
+  CircuitDesc c;
+  c.degree_bits = 6;
+  c.num_wires = 12;
+  c.num_routed_wires = 8;
+  c.num_constants = 1 + 2;
+  c.gates = {GateInfo{MP2GPU_GATE_ARITHMETIC, 2, 0}, GateInfo{MP2GPU_GATE_CONSTANT, 2, 0}, GateInfo{MP2GPU_GATE_NOOP, 0, 0},
+             GateInfo{MP2GPU_GATE_PUBLIC_INPUT, 0, 0}};
+  c.selector_indices = {0, 0, 0, 0};
+  c.groups = {{0, 4}};
+  const size_t n = size_t(1) << c.degree_bits;
+  FriConfig cfg;
+  std::vector<PolynomialValues> cs(c.num_constants + c.num_routed_wires), wires(c.num_wires);
+  for (auto &col : cs) {
+    col.values.resize(n);
+    for (auto &v : col.values) v = splitmix(seed) % 0xFFFFFFFF00000001ULL;
+  }
+  for (auto &v : cs[0].values) v %= 4;  // the selector column
+  for (auto &col : wires) {
+    col.values.resize(n);
+    for (auto &v : col.values) v = splitmix(seed) % 0xFFFFFFFF00000001ULL;
+  }
+  auto b_cs = PolynomialBatch<H>::from_values(cs, cfg.rate_bits, false, cfg.cap_height);
+  const std::array<F, 4> digest{1, 2, 3, 4}, pi_hash{5, 6, 7, 8};
+  const std::vector<F> pis{9, 10};
+  const std::vector<uint8_t> a = prove<H>(c, b_cs, digest, wires, pis, pi_hash, cfg);
+  const std::vector<uint8_t> b = prove<H>(c, b_cs, digest, wires, pis, pi_hash, cfg);
+  REQUIRE(a == b);                       // smallest PoW witness: reproducible bytes
+  REQUIRE(a.size() > 3 * (8 + 16 * 32));
+  uint64_t ncap = 0;
+  for (int i = 0; i < 8; i++) ncap |= (uint64_t)a[i] << (8 * i);
+  REQUIRE(ncap == (uint64_t(1) << cfg.cap_height));   // Vec<HashOut> length of wires_cap
+  uint64_t last = 0, npis = 0;
+  for (int i = 0; i < 8; i++) last |= (uint64_t)a[a.size() - 8 + i] << (8 * i);
+  for (int i = 0; i < 8; i++) npis |= (uint64_t)a[a.size() - 24 + i] << (8 * i);
+  REQUIRE(last == 10 && npis == 2);      // ... and the public inputs at the end
+  // errors come back as Panic
+  CircuitDesc bad = c;
+  bad.gates[0].kind = 99;
+  bool threw = false;
+  try {
+    prove<H>(bad, b_cs, digest, wires, pis, pi_hash, cfg);
+  } catch (const Panic &) {
+    threw = true;
+  }
+  REQUIRE(threw);
+  return 0;
+}
+
 int main() {
   try {
     init(0);
@@ -127,6 +181,7 @@ int main() {
     return 2;
   }
   if (run<Hasher::Poseidon>(0) || run<Hasher::Poseidon2>(1)) return 1;
+  if (run_prove<Hasher::Poseidon>() || run_prove<Hasher::Poseidon2>()) return 1;
   std::printf("cpp host mirror OK\n");
   return 0;
 }
