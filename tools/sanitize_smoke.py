@@ -1,5 +1,5 @@
 """Small end-to-end run for compute-sanitizer (memcheck / racecheck): both hashers, single-pass and four-step transforms,
-quotient, FRI proof -- sizes chosen so the run finishes in a minute under the sanitizer."""
+quotient, FRI proof, the native prove() -- sizes chosen so the run finishes in a minute under the sanitizer."""
 import os, sys, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -30,4 +30,12 @@ for kind in (0, 1):
     GF.open_batches(batches, oracles)
     proof = GF.prove_openings(batches, oracles, ch, GF.FriConfig().fri_params(5))
     for x in oracles: x.free()
+    # the permutation argument's kernels and the native prove() (all 15 gate kinds incl. CosetInterpolationGate rows)
+    from mapreduce_plonky2_b200 import prover as GP
+    cfg = GF.FriConfig(proof_of_work_bits=8, num_query_rounds=3)
+    cs = mk(inst.constants + inst.sigmas)
+    data = GP.prove_native(Q.CircuitDesc.from_circuit(c), cs, [1, 2, 3, 4], np.array(inst.wires, dtype=np.uint64), [7],
+                           inst.public_inputs_hash, cfg, hash_kind=kind)
+    assert len(data) > 1000
+    cs.free()
 print("sanitize smoke done; launches:", G.launch_count())
