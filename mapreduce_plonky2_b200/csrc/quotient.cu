@@ -65,6 +65,18 @@ struct Row {
   GL_DEV Row operator+(u32 c) const { return Row{COLMAJOR ? p + (size_t)c * stride : p + c, stride}; }
 };
 
+// Folds `count` buffered constraint values into the per-challenge sums: inner[c] += v_k * alpha_c^(first + k), `ap`
+// already pointing at alpha_c^first of challenge 0.  Deliberately NOT inlined: it is reached from ~150 constraint sites.
+constexpr u32 kRing = 16;
+__device__ __noinline__ void q_fold_ring(const u64 *ring, u32 count, const u64 *ap, u32 nterms, u32 nch, u64 *inner) {
+#pragma unroll 1
+  for (u32 k = 0; k < count; k++) {
+    const u64 v = ring[k];
+#pragma unroll 1
+    for (u32 c = 0; c < nch; c++) inner[c] = gl_mul_add(v, ap[c * nterms + k], inner[c]);
+  }
+}
+
 template <bool COLMAJOR>
 __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__ QParams P, u64 *__restrict__ out) {
   const u32 nq_log = P.n_log + P.qb;
@@ -111,7 +123,15 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
   }
   // evaluate_gate_constraints_base_batch: sum_g filter_g * sum_i alpha^(base + i) * constraint_{g,i}
   const R gc = cs + P.num_selectors;
-  u64 vals[kMaxGateConstraints];  // local memory: the constraints of the gate being evaluated
+  // A gate's constraint values pass through a 16-entry per-thread ring (128 B: stays in L1) that a non-inlined helper
+  // folds into the alpha-weighted sums whenever it is full; every gate emits its constraints in index order.
+  // (History: folding at every constraint site -- 4 multiply-adds inlined ~150 times -- made the kernel 13 k SASS
+  // instructions with `no_instruction` its second stall; a whole-gate scratch array of 256 values fixed that but put
+  // 2 KB per thread in local memory: 227 MB for the resident threads, more than L2 -- ncu: 384 MB written and 1.14 GB
+  // read for 2^17 points whose inputs are 0.25 GB, `long_scoreboard` the top stall; profiles/r2z_prove_kernels.summary.txt.)
+  u64 ring[kRing];
+  u64 inner[kMaxChallenges];
+  const u64 *ap0 = P.apow + P.gate_term_base;
   for (u32 g = 0; g < P.num_gates; g++) {
     const QGate gate = P.gates[g];
     const u64 s = cs[gate.selector];
@@ -119,10 +139,12 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
     for (u32 j = gate.group_begin; j < gate.group_end; j++)
       if (j != g) filt = gl_mul(filt, gl_sub((u64)j, s));
     if (P.num_selectors > 1) filt = gl_mul(filt, gl_sub(kUnusedSelector, s));
-    // A gate's constraint values go to a per-thread scratch array and are folded into the alpha-weighted sums by ONE
-    // rolled loop per gate.  (Folding at every constraint site -- 4 multiply-adds inlined ~150 times -- made the kernel
-    // 13 k SASS instructions, 210 KB, and `no_instruction` its second stall: profiles/r2z_quotient_points.summary.txt.)
-    auto cons = [&](u32 idx, u64 v) { vals[idx] = v; };
+#pragma unroll
+    for (u32 c = 0; c < kMaxChallenges; c++) inner[c] = 0;
+    auto cons = [&](u32 idx, u64 v) {
+      ring[idx & (kRing - 1)] = v;
+      if ((idx & (kRing - 1)) == kRing - 1) q_fold_ring(ring, kRing, ap0 + (idx - (kRing - 1)), P.nterms, P.nch, inner);
+    };
     if (gate.kind == MP2GPU_GATE_ARITHMETIC) {
       const u64 c0 = gc[0], c1 = gc[1];
       for (u32 op = 0; op < gate.num_ops; op++) {
@@ -306,17 +328,7 @@ __global__ void __launch_bounds__(128) k_quotient_points(const __grid_constant__
 #pragma unroll
       for (u32 i = 0; i < 12; i++) cons(ci + i, gl_sub(st[i], wi[12 + i]));
     }
-    u64 inner[kMaxChallenges];
-#pragma unroll
-    for (u32 c = 0; c < kMaxChallenges; c++) inner[c] = 0;
-    const u64 *ap = P.apow + P.gate_term_base;
-#pragma unroll 1
-    for (u32 k = 0; k < gate.nc; k++) {
-      const u64 v = vals[k];
-#pragma unroll
-      for (u32 c = 0; c < kMaxChallenges; c++)
-        if (c < P.nch) inner[c] = gl_mul_add(v, ap[c * P.nterms + k], inner[c]);
-    }
+    if (gate.nc & (kRing - 1)) q_fold_ring(ring, gate.nc & (kRing - 1), ap0 + (gate.nc & ~(kRing - 1)), P.nterms, P.nch, inner);
 #pragma unroll
     for (u32 c = 0; c < kMaxChallenges; c++)
       if (c < P.nch) acc[c] = gl_mul_add(filt, inner[c], acc[c]);
