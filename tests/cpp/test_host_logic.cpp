@@ -95,6 +95,27 @@ int main() {
   REQUIRE((cfg.reduction_arity_bits(13) == std::vector<size_t>{4, 4}));
   REQUIRE((cfg.reduction_arity_bits(12) == std::vector<size_t>{4, 4}));
   REQUIRE(cfg.reduction_arity_bits(5).empty());
+  // CircuitDesc -> mp2gpu_circuit: selector groups resolved per gate, inconsistent descriptors refused
+  CircuitDesc cd;
+  cd.degree_bits = 5;
+  cd.num_constants = 4;
+  cd.gates = {GateInfo{MP2GPU_GATE_ARITHMETIC, 20, 0}, GateInfo{MP2GPU_GATE_NOOP, 0, 0},
+              GateInfo{MP2GPU_GATE_COSET_INTERPOLATION, 4, 6}};
+  cd.selector_indices = {0, 0, 1};
+  cd.groups = {{0, 2}, {2, 3}};
+  std::vector<mp2gpu_gate> storage;
+  const mp2gpu_circuit c = cd.c_desc(storage);
+  REQUIRE(c.num_gates == 3 && c.num_selectors == 2 && c.gates == storage.data() && c.num_wires == 135 && c.num_routed_wires == 80);
+  REQUIRE(storage[1].group_begin == 0 && storage[1].group_end == 2 && storage[2].selector_index == 1);
+  REQUIRE(storage[2].kind == MP2GPU_GATE_COSET_INTERPOLATION && storage[2].num_ops == 4 && storage[2].param == 6);
+  cd.selector_indices = {0, 0, 2};
+  bool threw = false;
+  try {
+    cd.c_desc(storage);
+  } catch (const Panic &) {
+    threw = true;
+  }
+  REQUIRE(threw);
   std::printf("cpp host logic OK\n");
   return 0;
 }
